@@ -1,0 +1,107 @@
+// C-ABI plumbing: error strings, version, launch counter, TMA tensor-map cache.
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "host_util.h"
+
+namespace cb {
+
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  uint64_t base, inner, rows, ld;
+  uint32_t box_inner, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && rows == o.rows && ld == o.ld &&
+           box_inner == o.box_inner && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.ld + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= ((static_cast<uint64_t>(k.box_inner) << 32 | k.box_rows) + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+
+const CUtensorMap* get_tmap_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                               uint32_t box_inner, uint32_t box_rows) {
+  static std::mutex mu;
+  // node-based map: pointers to values stay valid across rehash
+  static std::unordered_map<TmapKey, CUtensorMap*, TmapKeyHash> cache;
+  TmapKey key{reinterpret_cast<uint64_t>(base), inner, rows, ld, box_inner, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return nullptr;
+  }
+  if ((reinterpret_cast<uint64_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) {
+    set_error("TMA operand must be 16-byte aligned (base %p, row pitch %llu elements)", base,
+              (unsigned long long)ld);
+    return nullptr;
+  }
+  CUtensorMap* m = static_cast<CUtensorMap*>(aligned_alloc(64, sizeof(CUtensorMap)));
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld, box_inner,
+              box_rows);
+    free(m);
+    return nullptr;
+  }
+  if (cache.size() > 65536) {  // unbounded growth guard (pointers churn under a caching allocator)
+    for (auto& kv : cache) free(kv.second);
+    cache.clear();
+  }
+  cache.emplace(key, m);
+  return m;
+}
+
+}  // namespace cb
+
+extern "C" {
+const char* cb_last_error(void) { return cb::t_err; }
+int cb_version(void) { return 100; }
+int cb_sm_arch(void) { return 100; }
+int64_t cb_launch_count(void) { return cb::g_launches.load(std::memory_order_relaxed); }
+}
