@@ -1,0 +1,292 @@
+// Memory-bound CNN-side kernels for the GridFeat ResNet-50 path (reference call sites:
+// src/modeling/grid_feat.py:89-105 -> detectron2 BasicStem / BottleneckBlock / MaxPool, and the
+// grid_encoder MaxPool2d+ReLU at grid_feat.py:43-48). Activations are NHWC bf16; every thread moves
+// 8 channels with one 128-bit access. All convolution FLOPs run in gemm.cu (tcgen05).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace cb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem im2col: fp32 NCHW RGB (mean-subtracted, 0..255 scale) -> bf16 [N*Ho*Wo, KP] rows of the
+// 7x7/s2/p3 patches, K index = (r*7 + s)*3 + c with c in BGR order (the x[:, [2,1,0]] flip of
+// grid_feat.py:92-94 is folded into the gather). KP = 152 (147 zero-padded to a multiple of 8).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void stem_im2col_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Ho,
+                                   int Wo, int KP, float m0, float m1, float m2) {
+  const int chunks = KP / 8;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * chunks;
+  if (t >= total) return;
+  const int chunk = static_cast<int>(t % chunks);
+  const int64_t pix = t / chunks;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+  const float mean_rgb[3] = {m0, m1, m2};
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float val = 0.f;
+    if (k < 147) {
+      const int c = k % 3, rs = k / 3, s = rs % 7, r = rs / 7;
+      const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + s;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const int cin = 2 - c;  // BGR channel c reads RGB channel 2-c
+        val = static_cast<float>(x[((static_cast<int64_t>(n) * 3 + cin) * H + iy) * W + ix]) - mean_rgb[cin];
+      }
+    }
+    f[j] = val;
+  }
+  *reinterpret_cast<uint4*>(out + pix * KP + chunk * 8) = pack8(f);
+}
+
+// 3x3 stride-2 pad-1 max pool, NHWC
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                    int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
+  const int c8 = static_cast<int>(t % c8n);
+  const int64_t pix = t / c8n;
+  const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy * 2 - 1 + r;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = ox * 2 - 1 + s;
+      if (ix < 0 || ix >= W) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c8 * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = pack8(m);
+}
+
+// stride-2 pixel subsample (input of a stride-2 1x1 conv): y[n, oy, ox] = x[n, 2oy, 2ox]
+__global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                  int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
+  const int c8 = static_cast<int>(t % c8n);
+  const int64_t pix = t / c8n;
+  const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) =
+      *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + 2 * oy) * W + 2 * ox) * C + c8 * 8);
+}
+
+// backward of subsample2 fused with the ReLU mask of the producer of x:
+//   dx[n,y,x] = (y,x even ? dsub[n,y/2,x/2] : 0) * (act[n,y,x] > 0)
+__global__ void unsubsample2_mask_kernel(const __nv_bfloat16* __restrict__ dsub, const __nv_bfloat16* __restrict__ act,
+                                         __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * H * W * c8n) return;
+  const int c8 = static_cast<int>(t % c8n);
+  const int64_t pix = t / c8n;
+  const int xx = static_cast<int>(pix % W), yy = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if ((yy & 1) == 0 && (xx & 1) == 0) {
+    float g[8], a[8];
+    unpack8(*reinterpret_cast<const uint4*>(dsub + ((static_cast<int64_t>(n) * Ho + yy / 2) * Wo + xx / 2) * C + c8 * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(act + pix * C + c8 * 8), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    o = pack8(g);
+  }
+  *reinterpret_cast<uint4*>(dx + pix * C + c8 * 8) = o;
+}
+
+// grid_encoder tail: MaxPool2d(2,2) (floor) then ReLU, NHWC compact -> NHWC compact
+__global__ void maxpool2x2_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                           int W, int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
+  const int c8 = static_cast<int>(t % c8n);
+  const int64_t pix = t / c8n;
+  const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = 0.f;  // ReLU folded: max(0, window max)
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + 2 * oy + r) * W + 2 * ox + s) * C + c8 * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = pack8(m);
+}
+
+// backward of the above into the zero-bordered ("padded") layout the 3x3 dgrad / wgrad GEMMs read.
+// Writes EVERY element of dx_pad [N, H+2, W+2, C] (zeros on the border and on non-argmax pixels).
+__global__ void maxpool2x2_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                           __nv_bfloat16* __restrict__ dx_pad, int N, int H, int W, int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * Hp * Wp * c8n) return;
+  const int c8 = static_cast<int>(t % c8n);
+  const int64_t pix = t / c8n;
+  const int xp = static_cast<int>(pix % Wp), yp = static_cast<int>((pix / Wp) % Hp);
+  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wp) * Hp));
+  uint4 o = make_uint4(0, 0, 0, 0);
+  const int yy = yp - 1, xx = xp - 1;
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+    const int oy = yy / 2, ox = xx / 2;
+    if (oy < Ho && ox < Wo) {
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + 2 * oy + r) * W + 2 * ox + s) * C + c8 * 8), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (f[j] > best[j]) { best[j] = f[j]; arg[j] = r * 2 + s; }  // first maximum wins (ATen semantics)
+        }
+      const int me = (yy - 2 * oy) * 2 + (xx - 2 * ox);
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + ((static_cast<int64_t>(n) * Ho + oy) * Wo + ox) * C + c8 * 8), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = (arg[j] == me && best[j] > 0.f) ? g[j] : 0.f;
+      o = pack8(g);
+    }
+  }
+  *reinterpret_cast<uint4*>(dx_pad + pix * C + c8 * 8) = o;
+}
+
+// y = dy * (act > 0), both compact: ReLU backward where no GEMM epilogue can carry it
+__global__ void relu_mask_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act,
+                                 __nv_bfloat16* __restrict__ dx, int64_t n8) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n8) return;
+  float g[8], a[8];
+  unpack8(reinterpret_cast<const uint4*>(dy)[t], g);
+  unpack8(reinterpret_cast<const uint4*>(act)[t], a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+  reinterpret_cast<uint4*>(dx)[t] = pack8(g);
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+/* in_dtype: 0 = fp32 (already mean-subtracted: pass mean = 0), 1 = uint8 (mean subtracted here, as
+ * ImageNorm does: src/datasets/data_utils.py:256-276). x is NCHW RGB; out is bf16 [n*ho*wo, kp]. */
+int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, int kp, float mean_r, float mean_g,
+                   float mean_b, void* stream) {
+  CB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "cb_stem_im2col: bad arguments");
+  CB_REQUIRE(kp >= 152 && kp % 8 == 0, "cb_stem_im2col: kp must be a multiple of 8 and >= 152");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * (kp / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == 0)
+    stem_im2col_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n,
+                                                                    h, w, ho, wo, kp, mean_r, mean_g, mean_b);
+  else if (in_dtype == 1)
+    stem_im2col_kernel<uint8_t><<<ceil_div(total, 256), 256, 0, st>>>(static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out),
+                                                                      n, h, w, ho, wo, kp, mean_r, mean_g, mean_b);
+  else
+    CB_REQUIRE(false, "cb_stem_im2col: in_dtype must be 0 (fp32) or 1 (uint8)");
+  return check_launch("cb_stem_im2col");
+}
+
+#define CB_NHWC_CHECK(name) \
+  CB_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, name ": bad arguments (c must be a multiple of 8)")
+
+int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  CB_NHWC_CHECK("cb_maxpool3x3s2");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
+  maxpool3x3s2_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
+  return check_launch("cb_maxpool3x3s2");
+}
+
+int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  CB_NHWC_CHECK("cb_subsample2");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
+  subsample2_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
+  return check_launch("cb_subsample2");
+}
+
+/* dsub: [n, ho, wo, c]; act, dx: [n, h, w, c] */
+int cb_unsubsample2_mask(const void* dsub, const void* act, void* dx, int n, int h, int w, int c, void* stream) {
+  CB_REQUIRE(dsub && act && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "cb_unsubsample2_mask: bad arguments");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
+  unsubsample2_mask_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dsub), static_cast<const __nv_bfloat16*>(act), static_cast<__nv_bfloat16*>(dx), n, h, w, c,
+      ho, wo);
+  return check_launch("cb_unsubsample2_mask");
+}
+
+int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  CB_NHWC_CHECK("cb_maxpool2x2_relu_fwd");
+  CB_REQUIRE(h >= 2 && w >= 2, "cb_maxpool2x2_relu_fwd: spatial size must be >= 2");
+  const int ho = h / 2, wo = w / 2;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
+  maxpool2x2_relu_fwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
+  return check_launch("cb_maxpool2x2_relu_fwd");
+}
+
+/* dy: [n, h/2, w/2, c]; x: conv output [n, h, w, c]; dx_pad: [n, h+2, w+2, c] fully overwritten */
+int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, int h, int w, int c, void* stream) {
+  CB_REQUIRE(dy && x && dx_pad && n > 0 && h >= 2 && w >= 2 && c > 0 && c % 8 == 0, "cb_maxpool2x2_relu_bwd: bad arguments");
+  const int64_t total = static_cast<int64_t>(n) * (h + 2) * (w + 2) * (c / 8);
+  maxpool2x2_relu_bwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx_pad), n, h, w, c,
+      h / 2, w / 2);
+  return check_launch("cb_maxpool2x2_relu_bwd");
+}
+
+int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* stream) {
+  CB_REQUIRE(dy && act && dx && n > 0 && n % 8 == 0, "cb_relu_mask: n must be a positive multiple of 8");
+  relu_mask_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), static_cast<__nv_bfloat16*>(dx), n / 8);
+  return check_launch("cb_relu_mask");
+}
+
+}  // extern "C"

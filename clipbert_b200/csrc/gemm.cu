@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   // ---- per-CTA iteration space ----
   int tap = 0, it_begin = 0, it_end = 0;
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 2) {
     const int kc = (K + BK - 1) / BK;
     it_begin = 0;
     it_end = ntaps * kc;
@@ -122,6 +122,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (ntaps == 9) shift = tap_sign * ((t / 3 - 1) * tap_w + (t % 3 - 1));
             tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, m0 + shift);
             tma_load_2d(sb, &tmB, &full_bar[s], t * K + kc * BK, n0);
+          } else if (MODE == 2) {
+            const int t = it / kc_per_tap;
+            const int kc = it - t * kc_per_tap;
+            int shift = 0;
+            if (ntaps == 9) shift = tap_sign * ((t / 3 - 1) * tap_w + (t % 3 - 1));
+            tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, m0 + shift);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], t * N + n0 + j * 64, kc * BK);
           } else {
             int shift = 0;
             if (ntaps == 9) shift = tap_sign * ((tap / 3 - 1) * tap_w + (tap % 3 - 1));
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE, MODE);
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == 1, MODE != 0);
         for (int i = 0; i < n_iters; ++i) {
           const int s = i % STAGES;
           const uint32_t ph = (i / STAGES) & 1;
@@ -152,6 +161,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (MODE == 0) {
               ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
               bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            } else if (MODE == 2) {
+              ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+              bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
             } else {
               ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
               bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
@@ -329,6 +341,10 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
     tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN);
     grid = dim3(ceil_div(d.n, BN), ceil_div(d.m, BM), 1);
+  } else if (MODE == 2) {
+    ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
+    tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
+    grid = dim3(ceil_div(d.n, BN), ceil_div(d.m, BM), 1);
   } else {
     ta = get_tmap_2d(d.a, d.m, d.a_rows, d.a_ld, 64, BK);
     tb = get_tmap_2d(d.b, d.n, d.b_rows, d.b_ld, 64, BK);
@@ -355,7 +371,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   CB_REQUIRE(d.a && d.b && d.out, "cb_gemm: null operand pointer");
   CB_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "cb_gemm: empty problem m=%d n=%d k=%d", d.m, d.n, d.k);
   CB_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "cb_gemm: ntaps must be 1 or 9 (got %d)", d.ntaps);
-  CB_REQUIRE(d.mode == CB_GEMM_TN || d.mode == CB_GEMM_WGRAD, "cb_gemm: bad mode %d", d.mode);
+  CB_REQUIRE(d.mode == CB_GEMM_TN || d.mode == CB_GEMM_WGRAD || d.mode == CB_GEMM_NN, "cb_gemm: bad mode %d", d.mode);
   CB_REQUIRE(d.dropout_p >= 0.0f && d.dropout_p < 1.0f, "cb_gemm: dropout_p out of range");
 
   GemmEpi epi;
@@ -386,7 +402,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     epi.drop_inv_keep = 1.0f;
   }
 
-  if (d.mode == CB_GEMM_TN) {
+  if (d.mode == CB_GEMM_TN || d.mode == CB_GEMM_NN) {
+    const bool nn = d.mode == CB_GEMM_NN;
     CB_REQUIRE(d.n % 8 == 0, "cb_gemm(TN): n must be a multiple of 8 (got %d)", d.n);
     CB_REQUIRE(d.k % 8 == 0, "cb_gemm(TN): k must be a multiple of 8 (got %d)", d.k);
     CB_REQUIRE(d.out_ld % 8 == 0, "cb_gemm(TN): out_ld must be a multiple of 8");
@@ -404,9 +421,9 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
       else bn = (d.n >= 128 && mt * ceil_div(d.n, 64) > 2 * 296) ? 128 : 64;
     }
     switch (bn) {
-      case 64: return launch_gemm<64, 0>(d, epi, stream);
-      case 128: return launch_gemm<128, 0>(d, epi, stream);
-      case 256: return launch_gemm<256, 0>(d, epi, stream);
+      case 64: return nn ? launch_gemm<64, 2>(d, epi, stream) : launch_gemm<64, 0>(d, epi, stream);
+      case 128: return nn ? launch_gemm<128, 2>(d, epi, stream) : launch_gemm<128, 0>(d, epi, stream);
+      case 256: return nn ? launch_gemm<256, 2>(d, epi, stream) : launch_gemm<256, 0>(d, epi, stream);
       default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
     }
   } else {

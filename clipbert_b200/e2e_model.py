@@ -1,0 +1,83 @@
+"""ClipBert: CNN + transformer, the module the reference task scripts instantiate
+(``src/modeling/e2e_model.py:13-50``). Same constructor, same ``forward(batch: dict) -> dict``,
+same attribute names (``.cnn``, ``.transformer``, ``.retrieval``), so ``src/tasks/run_*.py`` can
+use it unchanged; parameter names still contain "cnn" / "grid_encoder" / "transformer" so that
+``setup_e2e_optimizer`` (src/optimization/utils.py:96-161) yields its 8 parameter groups.
+"""
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from .grid_feat import GridFeatBackbone
+from .modeling import (ClipBertForMultipleChoice, ClipBertForSequenceClassification,  # noqa: F401
+                       ClipBertForVideoTextRetrieval)
+
+
+class ClipBert(nn.Module):
+    def __init__(self, config, input_format="BGR", detectron2_model_cfg=None, transformer_cls=ClipBertForVideoTextRetrieval,
+                 freeze_at=2):
+        super().__init__()
+        self.config = config
+        self.detectron2_model_cfg = detectron2_model_cfg
+        self.cnn = GridFeatBackbone(detectron2_model_cfg=detectron2_model_cfg, config=config, input_format=input_format,
+                                    freeze_at=freeze_at)
+        self.transformer = transformer_cls(config)
+        self.retrieval = transformer_cls == ClipBertForVideoTextRetrieval
+        self._comm_stream = None
+
+    def forward(self, batch):
+        # used to make visual feature copies (repeat_tensor_rows is fused into the visual-embedding kernel)
+        repeat_counts = batch["n_examples_list"]
+        del batch["n_examples_list"]
+        visual_features = self.cnn(batch["visual_inputs"])
+        batch["visual_inputs"] = visual_features
+        if self.retrieval:
+            batch["sample_size"] = len(repeat_counts)  # batch size
+        return self.transformer(_repeat_counts=list(repeat_counts), **batch)
+
+    def load_separate_ckpt(self, cnn_weights_path=None, bert_weights_path=None):
+        if cnn_weights_path:
+            self.cnn.load_state_dict(cnn_weights_path)
+        if bert_weights_path:
+            sd = torch.load(bert_weights_path, map_location="cpu") if isinstance(bert_weights_path, str) else bert_weights_path
+            own = self.transformer.state_dict()
+            self.transformer.load_state_dict({k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}, strict=False)
+            self.transformer.mark_weights_updated()
+
+    def freeze_cnn_backbone(self):
+        for n, p in self.cnn.feature.named_parameters():
+            p.requires_grad = False
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the reference checkpoint layout; silently drops the dead d2 heads."""
+        own = self.state_dict()
+        sd = {k: v for k, v in state_dict.items() if k in own}
+        out = super().load_state_dict(sd, strict=False)
+        self.cnn.mark_weights_updated()
+        self.transformer.mark_weights_updated()
+        return out
+
+    # ---- data-parallel gradient exchange (replaces hvd.DistributedOptimizer.synchronize) -----------
+    def flat_grads(self):
+        out = []
+        for m in (self.transformer, self.cnn):
+            if m._flat is not None and m._flat.grad is not None:
+                out.append(m._flat.grad)
+        return out
+
+    def zero_grad(self, set_to_none=False):
+        for m in (self.transformer, self.cnn):
+            if m._flat is not None and m._flat.grad is not None:
+                m._flat.grad.zero_()
+
+    def allreduce_grads(self, group=None, average=True, async_op=False):
+        """Sum (average) the two flat fp32 gradient buffers over the data-parallel group (NCCL)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        ws = dist.get_world_size(group)
+        works = []
+        for g in self.flat_grads():
+            if average:
+                g.mul_(1.0 / ws)
+            works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+        return works

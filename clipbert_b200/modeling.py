@@ -1,0 +1,638 @@
+"""Cross-modal transformer half of ClipBERT on B200.
+
+Mirrors the reference classes in ``src/modeling/modeling.py`` / ``src/modeling/transformers.py``
+(ClipBertBaseModel, ClipBertForVideoTextRetrieval, ClipBertForSequenceClassification,
+ClipBertForMultipleChoice, ClipBertForPreTraining): same constructor (a BertConfig-like object),
+same forward signatures and return dicts, same state_dict keys. The torch.nn
+modules below are PARAMETER CONTAINERS only — their own ``forward`` is never called. All arithmetic
+is the hand-written sm_100a kernels behind libclipbert_sm100.so:
+
+  embeddings     cb_embed_text_fwd / cb_embed_visual_fwd (gather + sum + LN + dropout; the visual
+                 kernel also fuses the frame mean, the row/col/type adds, repeat_tensor_rows and
+                 the [text ; visual] concat by writing at sequence offset Lt)
+  encoder layer  cb_gemm (QKV fused N=2304, +bias) -> cb_attention_fwd -> cb_gemm (+bias, dropout,
+                 +residual) -> cb_layernorm_fwd -> cb_gemm (+bias, GELU, pre-activation stash) ->
+                 cb_gemm (+bias, dropout, +residual) -> cb_layernorm_fwd
+  pooler / head  cb_gemm (strided [CLS] rows, +bias, tanh) -> cb_dropout -> cb_gemm (ReLU) -> cb_gemm
+  backward       mirror image; dgrad = cb_gemm NN straight from the forward weight layout, wgrad =
+                 cb_gemm WGRAD accumulating fp32 into the flat gradient buffer, activation
+                 derivatives and dropout masks fused into the dgrad / LayerNorm-backward epilogues.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .params import FlatGroup
+
+_SEED_STRIDE = 0x9E3779B97F4A7C15
+
+
+def _cfg(config, name, default=None):
+    if isinstance(config, dict):
+        return config.get(name, default)
+    return getattr(config, name, default)
+
+
+# ----------------------------------------------------------------------------------------------------
+# parameter containers (names = reference attribute names => identical state_dict keys)
+# ----------------------------------------------------------------------------------------------------
+class BertEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.word_embeddings = nn.Embedding(_cfg(config, "vocab_size"), h, padding_idx=_cfg(config, "pad_token_id", 0))
+        self.position_embeddings = nn.Embedding(_cfg(config, "max_position_embeddings"), h)
+        self.token_type_embeddings = nn.Embedding(_cfg(config, "type_vocab_size"), h)
+        self.LayerNorm = nn.LayerNorm(h, eps=_cfg(config, "layer_norm_eps"))
+
+
+class VisualInputEmbedding(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.position_embeddings = nn.Embedding(_cfg(config, "max_position_embeddings"), h)   # unused (modeling.py:97)
+        self.row_position_embeddings = nn.Embedding(_cfg(config, "max_grid_row_position_embeddings"), h)
+        self.col_position_embeddings = nn.Embedding(_cfg(config, "max_grid_col_position_embeddings"), h)
+        self.token_type_embeddings = nn.Embedding(1, h)
+        self.LayerNorm = nn.LayerNorm(h, eps=_cfg(config, "layer_norm_eps"))
+
+
+class BertSelfAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.query, self.key, self.value = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h)
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.dense = nn.Linear(h, h)
+        self.LayerNorm = nn.LayerNorm(h, eps=_cfg(config, "layer_norm_eps"))
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = BertSelfAttention(config)
+        self.output = BertSelfOutput(config)
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(_cfg(config, "hidden_size"), _cfg(config, "intermediate_size"))
+
+
+class BertOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(_cfg(config, "intermediate_size"), _cfg(config, "hidden_size"))
+        self.LayerNorm = nn.LayerNorm(_cfg(config, "hidden_size"), eps=_cfg(config, "layer_norm_eps"))
+
+
+class BertLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attention = BertAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(config) for _ in range(_cfg(config, "num_hidden_layers"))])
+
+
+class BertPooler(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.dense = nn.Linear(h, h)
+
+
+class ClipBertBaseModel(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.embeddings = BertEmbeddings(config)
+        self.visual_embeddings = VisualInputEmbedding(config)
+        self.encoder = BertEncoder(config)
+        self.pooler = BertPooler(config)
+
+
+def _init_bert_weights(module, std):
+    """BertPreTrainedModel._init_weights (src/modeling/transformers.py:559-570)."""
+    for m in module.modules():
+        if isinstance(m, (nn.Linear, nn.Embedding)):
+            m.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(m, nn.LayerNorm):
+            m.bias.data.zero_()
+            m.weight.data.fill_(1.0)
+        if isinstance(m, nn.Linear) and m.bias is not None:
+            m.bias.data.zero_()
+
+
+class _Lin:
+    """Packed views of one (possibly fused / zero-padded) linear layer."""
+    __slots__ = ("w", "b", "gw", "gb", "n", "k")
+
+
+class _TransformerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, grid, anchor, ids, mask, repeat):
+        out, stash = module._forward_impl(ids, grid, mask, repeat, need_backward=True)
+        ctx.module, ctx.stash = module, stash
+        ctx.grid_needs_grad = grid.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        stash, ctx.stash = ctx.stash, None
+        dgrid = ctx.module._backward_impl(stash, dout, ctx.grid_needs_grad)
+        return None, dgrid, None, None, None, None
+
+
+class _ClipBertHeadModel(nn.Module):
+    """Shared engine: ClipBertBaseModel + an MLP head; subclasses set the head and the loss."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.bert = ClipBertBaseModel(config)
+        self.dropout = nn.Dropout(_cfg(config, "hidden_dropout_prob"))
+        self._flat = None
+        self._dirty = True
+        self._call_count = 0
+        self._seed_base = None
+        self._capture = None     # tests set this to a dict to receive per-layer activations
+
+    # ---- flat parameter storage -------------------------------------------------------------------
+    def _head_linears(self):
+        raise NotImplementedError
+
+    def _ensure_ready(self, device):
+        if self._flat is None or not self._flat.is_current() or self._flat.device != device:
+            self._build_flat(device)
+            self._dirty = True
+        if self._dirty or self._flat.needs_repack():
+            self._repack()
+            self._dirty = False
+            self._flat.needs_repack()
+
+    def mark_weights_updated(self):
+        self._dirty = True
+
+    def _add_linear(self, flat, name, lins, pad_rows=None):
+        """Register weight(s) then bias(es) of one or several nn.Linear (fused along the output dim)."""
+        ews = [flat.add(name + ".w%d" % i, l.weight) for i, l in enumerate(lins[:-1])]
+        n = sum(l.weight.shape[0] for l in lins)
+        k = lins[0].weight.shape[1]
+        npad = n if pad_rows is None else pad_rows
+        last_rows = lins[-1].weight.shape[0] + (npad - n)
+        ews.append(flat.add(name + ".w%d" % (len(lins) - 1), lins[-1].weight, slot_numel=last_rows * k))
+        ebs = [flat.add(name + ".b%d" % i, l.bias) for i, l in enumerate(lins[:-1])]
+        ebs.append(flat.add(name + ".b%d" % (len(lins) - 1), lins[-1].bias, slot_numel=lins[-1].bias.shape[0] + (npad - n)))
+        # fused layout requires contiguity of the pieces: every piece but the last must fill its slot
+        for e in ews[:-1] + ebs[:-1]:
+            assert e["numel"] == e["slot"], "fused linear pieces must be multiples of %d elements" % 64
+        return dict(w_off=ews[0]["offset"], b_off=ebs[0]["offset"], n=npad, k=k)
+
+    def _build_flat(self, device):
+        flat = FlatGroup(device)
+        self._spec = {}
+        bert = self.bert
+        for i, layer in enumerate(bert.encoder.layer):
+            att = layer.attention
+            self._spec["l%d.qkv" % i] = self._add_linear(flat, "l%d.qkv" % i, [att.self.query, att.self.key, att.self.value])
+            self._spec["l%d.ao" % i] = self._add_linear(flat, "l%d.ao" % i, [att.output.dense])
+            self._spec["l%d.ln1" % i] = (flat.add("l%d.ln1.w" % i, att.output.LayerNorm.weight), flat.add("l%d.ln1.b" % i, att.output.LayerNorm.bias))
+            self._spec["l%d.inter" % i] = self._add_linear(flat, "l%d.inter" % i, [layer.intermediate.dense])
+            self._spec["l%d.out" % i] = self._add_linear(flat, "l%d.out" % i, [layer.output.dense])
+            self._spec["l%d.ln2" % i] = (flat.add("l%d.ln2.w" % i, layer.output.LayerNorm.weight), flat.add("l%d.ln2.b" % i, layer.output.LayerNorm.bias))
+        self._spec["pooler"] = self._add_linear(flat, "pooler", [bert.pooler.dense])
+        for name, lin in self._head_linears():
+            n = lin.weight.shape[0]
+            self._spec[name] = self._add_linear(flat, name, [lin], pad_rows=(n + 7) // 8 * 8)
+        for name, ln in self._extra_layernorms():
+            self._spec[name] = (flat.add(name + ".w", ln.weight), flat.add(name + ".b", ln.bias))
+        flat.mark_packed_prefix()
+        emb, vis = bert.embeddings, bert.visual_embeddings
+        self._spec["emb.ln"] = (flat.add("emb.ln.w", emb.LayerNorm.weight), flat.add("emb.ln.b", emb.LayerNorm.bias))
+        self._spec["vis.ln"] = (flat.add("vis.ln.w", vis.LayerNorm.weight), flat.add("vis.ln.b", vis.LayerNorm.bias))
+        for key, mod in (("emb.word", emb.word_embeddings), ("emb.pos", emb.position_embeddings), ("emb.type", emb.token_type_embeddings),
+                         ("vis.pos", vis.position_embeddings), ("vis.row", vis.row_position_embeddings),
+                         ("vis.col", vis.col_position_embeddings), ("vis.type", vis.token_type_embeddings)):
+            self._spec[key] = flat.add(key, mod.weight)
+        for name, p in self._extra_params():
+            self._spec[name] = flat.add(name, p)
+        flat.materialize()
+        self._flat = flat
+        # resolve views
+        self._lin = {}
+        for key, sp in self._spec.items():
+            if isinstance(sp, dict) and "w_off" in sp:
+                li = _Lin()
+                n, k = sp["n"], sp["k"]
+                li.n, li.k = n, k
+                li.w = flat.packed[sp["w_off"]: sp["w_off"] + n * k].view(n, k)
+                li.gw = flat.grad[sp["w_off"]: sp["w_off"] + n * k].view(n, k)
+                li.b = flat.master[sp["b_off"]: sp["b_off"] + n]
+                li.gb = flat.grad[sp["b_off"]: sp["b_off"] + n]
+                self._lin[key] = li
+
+    def _extra_layernorms(self):
+        return []
+
+    def _extra_params(self):
+        return []
+
+    def _ln(self, key):
+        ew, eb = self._spec[key]
+        f = self._flat
+        return (f.master[ew["offset"]: ew["offset"] + ew["numel"]], f.master[eb["offset"]: eb["offset"] + eb["numel"]],
+                f.grad[ew["offset"]: ew["offset"] + ew["numel"]], f.grad[eb["offset"]: eb["offset"] + eb["numel"]])
+
+    def _emb(self, key):
+        e = self._spec[key]
+        f = self._flat
+        shape = e["param"].shape
+        return (f.master[e["offset"]: e["offset"] + e["numel"]].view(shape), f.grad[e["offset"]: e["offset"] + e["numel"]].view(shape))
+
+    @torch.no_grad()
+    def _repack(self):
+        """fp32 masters -> bf16 tensor-core operands: ONE cast kernel over the linear-weight prefix."""
+        f = self._flat
+        n = f.packed_prefix
+        ops.cast_scale(f.master[:n], f.packed[:n])
+
+    # ---- seeds ------------------------------------------------------------------------------------
+    def _next_seed(self):
+        if self._seed_base is None:
+            self._seed_base = torch.initial_seed() & 0xFFFFFFFFFFFF
+        self._call_count += 1
+        return (self._seed_base + self._call_count * 1000003) & 0xFFFFFFFFFFFFFFFF
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _run(self, text_input_ids, visual_inputs, text_input_mask, repeat_counts=None):
+        """Returns fp32 logits (B', num_outputs). visual_inputs: (B or B', T, h, w, 768)."""
+        assert text_input_ids.is_cuda, "ClipBERT transformer runs on CUDA only (no CPU fallback)"
+        dev = text_input_ids.device
+        self._ensure_ready(dev)
+        nseq = text_input_ids.shape[0]
+        nvid = visual_inputs.shape[0]
+        if repeat_counts is None:
+            assert nvid == nseq, "visual_inputs must have one row per text example (or pass repeat counts)"
+            repeat = (1, None, None)
+        else:
+            assert len(repeat_counts) == nvid and sum(repeat_counts) == nseq
+            if len(set(repeat_counts)) == 1:
+                repeat = (int(repeat_counts[0]), None, None)
+            else:
+                s2v = torch.tensor([i for i, r in enumerate(repeat_counts) for _ in range(r)], dtype=torch.int32)
+                starts = torch.tensor([0] + list(torch.tensor(repeat_counts).cumsum(0)), dtype=torch.int32)
+                repeat = (0, s2v.to(dev), starts.to(dev))
+        grid = visual_inputs
+        if grid.dtype != torch.bfloat16:
+            grid = grid.to(torch.bfloat16)
+        grid = grid.contiguous()
+        ids = text_input_ids.contiguous()
+        mask = text_input_mask.to(torch.int64).contiguous()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            anchor = self.bert.pooler.dense.weight
+            return _TransformerFn.apply(self, grid, anchor, ids, mask, repeat)
+        return self._forward_impl(ids, grid, mask, repeat, need_backward=False)[0]
+
+    def _gemm_fwd(self, x, m, li, out, **kw):
+        ops.gemm(mode=ops.CB_GEMM_TN, m=m, n=li.n, k=li.k, a=x, a_rows=m, a_ld=kw.pop("a_ld", li.k), b=li.w, b_rows=li.n, b_ld=li.k,
+                 shift=li.b, out=out, out_ld=li.n, **kw)
+
+    def _forward_impl(self, ids, grid, mask, repeat, need_backward):
+        dev = ids.device
+        cfg = self.config
+        H = _cfg(cfg, "hidden_size")
+        heads = _cfg(cfg, "num_attention_heads")
+        eps = float(_cfg(cfg, "layer_norm_eps"))
+        train = self.training
+        p_h = float(_cfg(cfg, "hidden_dropout_prob")) if train else 0.0
+        p_a = float(_cfg(cfg, "attention_probs_dropout_prob")) if train else 0.0
+        seed = self._next_seed()
+        nseq, lt = ids.shape
+        nvid, T, gh, gw, _ = grid.shape
+        L = lt + gh * gw
+        M = nseq * L
+        bf16, f32 = torch.bfloat16, torch.float32
+        n_ex, s2v, starts = repeat
+
+        def new(*shape, dtype=bf16):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        st = dict(ids=ids, mask=mask, grid=grid, repeat=repeat, seed=seed, p_h=p_h, p_a=p_a, dims=(nseq, nvid, T, gh, gw, lt, L), layers=[])
+        # ---- embeddings: [text ; visual] written straight into one (B', L, 768) buffer ----
+        x = new(M, H)
+        st["stats_t"] = new(nseq * lt, 2, dtype=f32)
+        st["stats_v"] = new(nseq * gh * gw, 2, dtype=f32)
+        g_t, b_t, _, _ = self._ln("emb.ln")
+        g_v, b_v, _, _ = self._ln("vis.ln")
+        word, pos, typ = self._emb("emb.word")[0], self._emb("emb.pos")[0], self._emb("emb.type")[0]
+        ops.embed_text_fwd(ids, word, pos, typ, g_t, b_t, x, st["stats_t"], nseq, lt, L, eps, p_h, seed + 1)
+        ops.embed_visual_fwd(grid, s2v, n_ex, self._emb("vis.row")[0], self._emb("vis.col")[0], self._emb("vis.type")[0], g_v, b_v,
+                             x, st["stats_v"], nseq, T, gh, gw, lt, L, eps, p_h, seed + 2)
+        if self._capture is not None:
+            self._capture["embeddings"] = x.view(nseq, L, H).clone()
+        # ---- encoder ----
+        for i in range(len(self.bert.encoder.layer)):
+            ls = seed + 16 * (i + 1)
+            qkv_l, ao_l, in_l, out_l = (self._lin["l%d.%s" % (i, k)] for k in ("qkv", "ao", "inter", "out"))
+            g1, b1, _, _ = self._ln("l%d.ln1" % i)
+            g2, b2, _, _ = self._ln("l%d.ln2" % i)
+            qkv = new(M, 3 * H)
+            self._gemm_fwd(x, M, qkv_l, qkv)
+            ctx = new(M, H)
+            lse = new(nseq, heads, L, dtype=f32) if need_backward else None
+            ops.attention_fwd(qkv, mask, ctx, lse, nseq, L, lt, heads, p_a, ls + 1)
+            s1 = new(M, H)
+            self._gemm_fwd(ctx, M, ao_l, s1, residual=x, res_ld=H, dropout_p=p_h, dropout_seed=ls + 2)
+            a = new(M, H)
+            st1 = new(M, 2, dtype=f32)
+            ops.layernorm_fwd(s1, g1, b1, a, st1, eps)
+            u = new(M, in_l.n) if need_backward else None
+            gel = new(M, in_l.n)
+            if need_backward:
+                self._gemm_fwd(a, M, in_l, gel, act=ops.ACT_GELU, out2=u, out2_ld=in_l.n)
+            else:
+                self._gemm_fwd(a, M, in_l, gel, act=ops.ACT_GELU)
+            s2 = new(M, H)
+            self._gemm_fwd(gel, M, out_l, s2, residual=a, res_ld=H, dropout_p=p_h, dropout_seed=ls + 3)
+            y = new(M, H)
+            st2 = new(M, 2, dtype=f32)
+            ops.layernorm_fwd(s2, g2, b2, y, st2, eps)
+            if need_backward:
+                st["layers"].append(dict(x=x, qkv=qkv, ctx=ctx, lse=lse, s1=s1, st1=st1, a=a, u=u, gel=gel, s2=s2, st2=st2, seed=ls))
+            x = y
+            if self._capture is not None:
+                self._capture["layer%d" % i] = x.view(nseq, L, H)
+        st["x_last"] = x
+        # ---- pooler on the [CLS] rows (row pitch L*768, no gather) ----
+        pl = self._lin["pooler"]
+        pooled = new(nseq, H)
+        self._gemm_fwd(x, nseq, pl, pooled, a_ld=L * H, act=ops.ACT_TANH)
+        st["pooled"] = pooled
+        if self._capture is not None:
+            self._capture["pooled"] = pooled
+        out = self._head_forward(pooled, st, nseq, p_h, seed, need_backward)
+        return out, (st if need_backward else None)
+
+    # generic 2-layer MLP head: dropout -> Linear -> ReLU -> Linear (modeling.py:534-539,552-553)
+    def _mlp_head_forward(self, pooled, st, nseq, p_h, seed, num_out):
+        dev = pooled.device
+        c0, c2 = self._lin["cls0"], self._lin["cls2"]
+        if p_h > 0:
+            pd = torch.empty_like(pooled)
+            ops.dropout(pooled, pd, p_h, seed + 5)
+        else:
+            pd = pooled
+        c1 = torch.empty(nseq, c0.n, dtype=torch.bfloat16, device=dev)
+        self._gemm_fwd(pd, nseq, c0, c1, act=ops.ACT_RELU)
+        logits = torch.empty(nseq, c2.n, dtype=torch.float32, device=dev)
+        self._gemm_fwd(c1, nseq, c2, logits, out_fp32=1)
+        st["pd"], st["c1"], st["num_out"] = pd, c1, num_out
+        if self._capture is not None:
+            self._capture["c1"] = c1
+        return logits[:, :num_out]
+
+    def _head_forward(self, pooled, st, nseq, p_h, seed, need_backward):
+        return self._mlp_head_forward(pooled, st, nseq, p_h, seed, self._num_head_outputs())
+
+    # ---- backward ---------------------------------------------------------------------------------
+    def _wgrad(self, li, dy, x, rows, x_ld=None):
+        ops.gemm(mode=ops.CB_GEMM_WGRAD, m=li.n, n=li.k, k=rows, a=dy, a_rows=rows, a_ld=li.n, b=x, b_rows=rows,
+                 b_ld=li.k if x_ld is None else x_ld, split_k=ops.wgrad_split(li.n, li.k, rows), out=li.gw, out_ld=li.k, out_fp32=1)
+
+    def _dgrad(self, li, dy, rows, out, **kw):
+        ops.gemm(mode=ops.CB_GEMM_NN, m=rows, n=li.k, k=li.n, a=dy, a_rows=rows, a_ld=li.n, b=li.w, b_rows=li.n, b_ld=li.k,
+                 out=out, out_ld=kw.pop("out_ld", li.k), **kw)
+
+    def _mlp_head_backward(self, st, dlogits, nseq, H):
+        """Returns d(pooled) (bf16, [nseq, H])."""
+        dev = dlogits.device
+        bf16 = torch.bfloat16
+        c0, c2, pl = self._lin["cls0"], self._lin["cls2"], self._lin["pooler"]
+        dl = torch.empty(nseq, c2.n, dtype=bf16, device=dev)
+        ops.pad_cast(dlogits.float().contiguous() if dlogits.dtype != torch.float32 or not dlogits.is_contiguous() else dlogits, dl)
+        self._wgrad(c2, dl, st["c1"], nseq)
+        ops.colsum(dl, c2.gb, nseq, c2.n)
+        dc1 = torch.empty(nseq, c0.n, dtype=bf16, device=dev)
+        self._dgrad(c2, dl, nseq, dc1, aux=st["c1"], aux_ld=c0.n, aux_mode=ops.AUX_RELU_MASK)
+        self._wgrad(c0, dc1, st["pd"], nseq)
+        ops.colsum(dc1, c0.gb, nseq, c0.n)
+        dpooled = torch.empty(nseq, H, dtype=bf16, device=dev)
+        # d(pooler pre-activation) = (dc1 @ W0) * dropout_mask * tanh'(pooled)
+        self._dgrad(c0, dc1, nseq, dpooled, dropout_p=st["p_h"], dropout_seed=st["seed"] + 5, aux=st["pooled"], aux_ld=H,
+                    aux_mode=ops.AUX_TANH_GRAD)
+        return dpooled
+
+    def _head_backward(self, st, dout, nseq, H):
+        return self._mlp_head_backward(st, dout, nseq, H)
+
+    def _backward_impl(self, st, dout, grid_needs_grad):
+        self._flat.attach_grads()
+        dev = dout.device
+        cfg = self.config
+        H = _cfg(cfg, "hidden_size")
+        heads = _cfg(cfg, "num_attention_heads")
+        nseq, nvid, T, gh, gw, lt, L = st["dims"]
+        M = nseq * L
+        p_h, p_a = st["p_h"], st["p_a"]
+        bf16, f32 = torch.bfloat16, torch.float32
+        n_ex, s2v, starts = st["repeat"]
+
+        def new(*shape, dtype=bf16):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        dpre = self._head_backward(st, dout, nseq, H)      # grad w.r.t. pooler pre-activation
+        pl = self._lin["pooler"]
+        x_last = st["x_last"]
+        self._wgrad(pl, dpre, x_last, nseq, x_ld=L * H)
+        ops.colsum(dpre, pl.gb, nseq, H)
+        dx = torch.zeros(M, H, dtype=bf16, device=dev)
+        self._dgrad(pl, dpre, nseq, dx, out_ld=L * H)      # scatters into the [CLS] rows
+        extra = self._extra_sequence_grad(st)
+        if extra is not None:
+            dx += extra
+        for i in reversed(range(len(st["layers"]))):
+            ly = st["layers"][i]
+            ls = ly["seed"]
+            qkv_l, ao_l, in_l, out_l = (self._lin["l%d.%s" % (i, k)] for k in ("qkv", "ao", "inter", "out"))
+            g1, _, dg1, db1 = self._ln("l%d.ln1" % i)
+            g2, _, dg2, db2 = self._ln("l%d.ln2" % i)
+            # y = LN2(s2), s2 = dropout(gel @ Wo^T + bo) + a
+            ds2 = new(M, H)
+            ds2d = new(M, H) if p_h > 0 else None
+            ops.layernorm_bwd(dx, ly["s2"], ly["st2"], g2, ds2, ds2d, dg2, db2, out_l.gb, p_h, ls + 3)
+            dd = ds2d if ds2d is not None else ds2
+            self._wgrad(out_l, dd, ly["gel"], M)
+            du = new(M, in_l.n)
+            self._dgrad(out_l, dd, M, du, aux=ly["u"], aux_ld=in_l.n, aux_mode=ops.AUX_GELU_GRAD)
+            self._wgrad(in_l, du, ly["a"], M)
+            ops.colsum(du, in_l.gb, M, in_l.n)
+            da = new(M, H)
+            self._dgrad(in_l, du, M, da, residual=ds2, res_ld=H)
+            # a = LN1(s1), s1 = dropout(ctx @ Wao^T + b) + x
+            ds1 = new(M, H)
+            ds1d = new(M, H) if p_h > 0 else None
+            ops.layernorm_bwd(da, ly["s1"], ly["st1"], g1, ds1, ds1d, dg1, db1, ao_l.gb, p_h, ls + 2)
+            dd1 = ds1d if ds1d is not None else ds1
+            self._wgrad(ao_l, dd1, ly["ctx"], M)
+            dctx = new(M, H)
+            self._dgrad(ao_l, dd1, M, dctx)
+            dqkv = new(M, 3 * H)
+            ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], dctx, ly["lse"], dqkv, nseq, L, lt, heads, p_a, ls + 1)
+            self._wgrad(qkv_l, dqkv, ly["x"], M)
+            ops.colsum(dqkv, qkv_l.gb, M, 3 * H)
+            dxn = new(M, H)
+            self._dgrad(qkv_l, dqkv, M, dxn, residual=ds1, res_ld=H)
+            dx = dxn
+            st["layers"][i] = None     # free this layer's stash
+        # ---- embeddings ----
+        g_t, _, dg_t, db_t = self._ln("emb.ln")
+        g_v, _, dg_v, db_v = self._ln("vis.ln")
+        (word, dword), (pos, dpos), (typ, dtyp) = self._emb("emb.word"), self._emb("emb.pos"), self._emb("emb.type")
+        ops.embed_text_bwd(dx, st["ids"], word, pos, typ, g_t, st["stats_t"], dword, dpos, dtyp, dg_t, db_t, nseq, lt, L, p_h,
+                           st["seed"] + 1)
+        (row, drow), (col, dcol), (vtyp, dvtyp) = self._emb("vis.row"), self._emb("vis.col"), self._emb("vis.type")
+        dv_tmp = new(nseq * gh * gw, H, dtype=f32)
+        dgrid = new(nvid, T, gh, gw, H) if grid_needs_grad else None
+        ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row, col, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow, dcol, dvtyp,
+                             dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
+        self._dirty = True
+        return dgrid
+
+    def _extra_sequence_grad(self, st):
+        return None
+
+    # ---- misc -------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none=False):
+        if self._flat is not None and self._flat.grad is not None:
+            self._flat.zero_grad()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
+
+
+class _MlpHeadMixin:
+    def _make_classifier(self, config, num_out):
+        h = _cfg(config, "hidden_size")
+        self.classifier = nn.Sequential(nn.Linear(h, h * 2), nn.ReLU(True), nn.Linear(h * 2, num_out))
+
+    def _head_linears(self):
+        return [("cls0", self.classifier[0]), ("cls2", self.classifier[2])]
+
+
+class ClipBertForVideoTextRetrieval(_MlpHeadMixin, _ClipBertHeadModel):
+    """src/modeling/modeling.py:523-580."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._make_classifier(config, _cfg(config, "num_labels"))
+        self.margin = _cfg(config, "margin", 0.2)
+        _init_bert_weights(self, _cfg(config, "initializer_range", 0.02))
+
+    def _num_head_outputs(self):
+        return _cfg(self.config, "num_labels")
+
+    def forward(self, text_input_ids, visual_inputs, text_input_mask, labels=None, sample_size=-1, _repeat_counts=None):
+        logits = self._run(text_input_ids, visual_inputs, text_input_mask, _repeat_counts)
+        logits, loss = self.calc_loss(logits, labels, sample_size=sample_size)
+        return dict(logits=logits, loss=loss)
+
+    def calc_loss(self, logits, labels, sample_size=-1):
+        if labels is None:
+            return logits, 0
+        loss_type = _cfg(self.config, "loss_type")
+        if loss_type == "ce":
+            loss = F.cross_entropy(logits.view(-1, _cfg(self.config, "num_labels")), labels.view(-1), reduction="none")
+        elif loss_type == "rank":
+            scores = torch.sigmoid(logits).squeeze()
+            assert sample_size > 0
+            scores = scores.contiguous().view(sample_size, -1)
+            loss = torch.clamp(self.margin + scores[:, 1:] - scores[:, :1], min=0)
+        else:
+            raise ValueError("Invalid option for config.loss_type")
+        return logits, loss
+
+
+def instance_bce_with_logits(logits, labels, reduction="mean"):
+    """src/modeling/modeling.py:310-316."""
+    assert logits.dim() == 2
+    loss = F.binary_cross_entropy_with_logits(logits, labels, reduction=reduction)
+    if reduction == "mean":
+        loss *= labels.size(1)
+    return loss
+
+
+class ClipBertForSequenceClassification(_MlpHeadMixin, _ClipBertHeadModel):
+    """src/modeling/modeling.py:327-384."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._make_classifier(config, _cfg(config, "num_labels"))
+        _init_bert_weights(self, _cfg(config, "initializer_range", 0.02))
+
+    def _num_head_outputs(self):
+        return _cfg(self.config, "num_labels")
+
+    def forward(self, text_input_ids, visual_inputs, text_input_mask, labels=None, _repeat_counts=None, **_unused):
+        logits = self._run(text_input_ids, visual_inputs, text_input_mask, _repeat_counts)
+        logits, loss = self.calc_loss(logits, labels)
+        return dict(logits=logits, loss=loss)
+
+    def calc_loss(self, logits, labels):
+        if labels is None:
+            return logits, 0
+        nl = _cfg(self.config, "num_labels")
+        if nl == 1:
+            loss = F.mse_loss(logits.view(-1), labels.view(-1), reduction="none")
+        elif _cfg(self.config, "loss_type") == "bce":
+            loss = instance_bce_with_logits(logits, labels, reduction="none")
+        elif _cfg(self.config, "loss_type") == "ce":
+            loss = F.cross_entropy(logits.view(-1, nl), labels.view(-1), reduction="none")
+        else:
+            raise ValueError("Invalid option for config.loss_type")
+        return logits, loss
+
+
+class ClipBertForMultipleChoice(_MlpHeadMixin, _ClipBertHeadModel):
+    """src/modeling/modeling.py:387-451 — one score per (video, option); CE over options."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._make_classifier(config, 1)
+        _init_bert_weights(self, _cfg(config, "initializer_range", 0.02))
+
+    def _num_head_outputs(self):
+        return 1
+
+    def forward(self, text_input_ids, visual_inputs, text_input_mask, labels=None, _repeat_counts=None, **_unused):
+        logits = self._run(text_input_ids, visual_inputs, text_input_mask, _repeat_counts)
+        logits, loss = self.calc_loss(logits, labels)
+        return dict(logits=logits, loss=loss)
+
+    def calc_loss(self, logits, labels):
+        nl = _cfg(self.config, "num_labels")
+        loss_type = _cfg(self.config, "loss_type")
+        if loss_type == "ce":
+            logits = logits.reshape(-1, nl)
+        if labels is None:
+            return logits, 0
+        if nl == 1:
+            loss = F.mse_loss(logits.view(-1), labels.view(-1), reduction="none")
+        elif loss_type == "bce":
+            loss = instance_bce_with_logits(logits, labels, reduction="none")
+        elif loss_type == "ce":
+            loss = F.cross_entropy(logits, labels.view(-1), reduction="none")
+        else:
+            raise ValueError("Invalid option for config.loss_type")
+        return logits, loss

@@ -1,0 +1,190 @@
+"""Thin Python wrappers over the C ABI (include/clipbert_b200.h). Each function takes CUDA torch
+tensors (used only as device buffers), validates the few things the C side cannot see (dtype,
+contiguity, device) and enqueues the kernel on the current torch stream. No arithmetic happens in
+Python or in torch on this path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_GELU_GRAD, AUX_NONE, AUX_RELU_MASK,  # noqa: F401
+                   AUX_TANH_GRAD, CB_GEMM_TN, CB_GEMM_WGRAD, ROWMAP_NONE, ROWMAP_PAD, ROWMAP_UNPAD)
+
+CB_GEMM_NN = 2
+_c = ctypes
+_vp, _i, _i64, _f, _u64 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_uint64
+
+_SIGS = {
+    "cb_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "cb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _vp],
+    "cb_embed_text_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _u64, _vp],
+    "cb_embed_text_bwd": [_vp] * 12 + [_i, _i, _i, _i, _i, _f, _u64, _vp],
+    "cb_embed_visual_fwd": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _vp],
+    "cb_embed_visual_bwd": [_vp, _vp, _vp, _vp, _i] + [_vp] * 12 + [_i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "cb_colsum": [_vp, _i64, _vp, _i, _i, _vp],
+    "cb_dropout": [_vp, _vp, _i64, _f, _u64, _vp],
+    "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
+    "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "cb_attention_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "cb_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _u64, _vp],
+    "cb_stem_im2col": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
+    "cb_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_subsample2": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_unsubsample2_mask": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_maxpool2x2_relu_fwd": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_maxpool2x2_relu_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_relu_mask": [_vp, _vp, _vp, _i64, _vp],
+}
+_bound = {}
+
+
+def _fn(name):
+    f = _bound.get(name)
+    if f is None:
+        f = getattr(L.lib(), name)
+        f.argtypes = _SIGS[name]
+        f.restype = _c.c_int
+        _bound[name] = f
+    return f
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    rc = _fn(name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, L.lib().cb_last_error().decode()))
+
+
+def launch_count():
+    return int(L.lib().cb_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core contraction
+# ------------------------------------------------------------------------------------------------
+_GEMM_PTR_FIELDS = ("a", "b", "scale", "shift", "residual", "aux", "out", "out2")
+
+
+def gemm(**kw):
+    """cb_gemm with keyword fields of cb_gemm_desc; tensor-valued fields are converted to pointers."""
+    d = L.GemmDesc()
+    d.ntaps = 1
+    d.tap_sign = 1
+    d.split_k = 1
+    for k, v in kw.items():
+        if k in _GEMM_PTR_FIELDS:
+            v = _p(v) if isinstance(v, torch.Tensor) else v
+        setattr(d, k, v)
+    rc = L.lib().cb_gemm(ctypes.byref(d), _s())
+    if rc != 0:
+        raise RuntimeError("cb_gemm failed (%d): %s" % (rc, L.lib().cb_last_error().decode()))
+
+
+def wgrad_split(m, n, k, ntaps=1, block_n=128):
+    """Number of K-splits so that a wgrad launch fills the 148 SMs about twice."""
+    bn = block_n if n >= 128 else 64
+    tiles = -(-m // 128) * -(-n // bn) * ntaps
+    iters = -(-k // 64)
+    want = max(1, -(-296 // tiles))
+    return max(1, min(want, iters))
+
+
+# ------------------------------------------------------------------------------------------------
+# BERT-side memory-bound ops
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, y, stats, eps):
+    _call("cb_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), x.shape[0], x.shape[1], eps, _s())
+
+
+def layernorm_bwd(dy, x, stats, gamma, dx, dx_drop, dgamma, dbeta, dbias_drop, p, seed):
+    _call("cb_layernorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta),
+          _p(dbias_drop), x.shape[0], x.shape[1], p, seed, _s())
+
+
+def embed_text_fwd(ids, word, pos, type0, gamma, beta, out, stats, nseq, lt, l, eps, p, seed):
+    _call("cb_embed_text_fwd", _p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(beta), _p(out), _p(stats), nseq, lt, l,
+          word.shape[0], word.shape[1], eps, p, seed, _s())
+
+
+def embed_text_bwd(dh, ids, word, pos, type0, gamma, stats, dword, dpos, dtype0, dgamma, dbeta, nseq, lt, l, p, seed):
+    _call("cb_embed_text_bwd", _p(dh), _p(ids), _p(word), _p(pos), _p(type0), _p(gamma), _p(stats), _p(dword), _p(dpos),
+          _p(dtype0), _p(dgamma), _p(dbeta), nseq, lt, l, word.shape[0], word.shape[1], p, seed, _s())
+
+
+def embed_visual_fwd(grid, seq2vid, n_ex, rowemb, colemb, type0, gamma, beta, out, stats, nseq, t, gh, gw, lt, l, eps, p,
+                     seed):
+    _call("cb_embed_visual_fwd", _p(grid), _p(seq2vid), n_ex, _p(rowemb), _p(colemb), _p(type0), _p(gamma), _p(beta), _p(out),
+          _p(stats), nseq, t, gh, gw, lt, l, rowemb.shape[1], eps, p, seed, _s())
+
+
+def embed_visual_bwd(dh, grid, seq2vid, vid_start, n_ex, rowemb, colemb, type0, gamma, stats, dv_tmp, dgrid, drow, dcol,
+                     dtype0, dgamma, dbeta, nseq, nvid, t, gh, gw, lt, l, p, seed):
+    _call("cb_embed_visual_bwd", _p(dh), _p(grid), _p(seq2vid), _p(vid_start), n_ex, _p(rowemb), _p(colemb), _p(type0),
+          _p(gamma), _p(stats), _p(dv_tmp), _p(dgrid), _p(drow), _p(dcol), _p(dtype0), _p(dgamma), _p(dbeta), nseq, nvid, t,
+          gh, gw, lt, l, rowemb.shape[1], p, seed, _s())
+
+
+def colsum(x, out, m, n, ld=None):
+    _call("cb_colsum", _p(x), n if ld is None else ld, _p(out), m, n, _s())
+
+
+def dropout(x, y, p, seed):
+    _call("cb_dropout", _p(x), _p(y), x.numel(), p, seed, _s())
+
+
+def pad_cast(src, dst):
+    _call("cb_pad_cast", _p(src), src.stride(0), _p(dst), src.shape[0], src.shape[1], dst.shape[1], _s())
+
+
+def cast_scale(src, dst, rowscale=None, row_len=1):
+    _call("cb_cast_scale", _p(src), _p(rowscale), row_len, _p(dst), src.numel(), _s())
+
+
+def attention_fwd(qkv, text_mask, ctx, lse, nseq, l, lt, heads, p, seed):
+    _call("cb_attention_fwd", _p(qkv), qkv.shape[1], _p(text_mask), _p(ctx), ctx.shape[1], _p(lse), nseq, l, lt, heads, 64, p,
+          seed, _s())
+
+
+def attention_bwd(qkv, text_mask, ctx, dctx, lse, dqkv, nseq, l, lt, heads, p, seed):
+    _call("cb_attention_bwd", _p(qkv), qkv.shape[1], _p(text_mask), _p(ctx), _p(dctx), ctx.shape[1], _p(lse), _p(dqkv),
+          dqkv.shape[1], nseq, l, lt, heads, 64, p, seed, _s())
+
+
+# ------------------------------------------------------------------------------------------------
+# CNN-side memory-bound ops (NHWC bf16)
+# ------------------------------------------------------------------------------------------------
+def stem_im2col(x, out, n, h, w, kp, mean=(0.0, 0.0, 0.0)):
+    dt = 0 if x.dtype == torch.float32 else 1
+    _call("cb_stem_im2col", _p(x), dt, _p(out), n, h, w, kp, mean[0], mean[1], mean[2], _s())
+
+
+def maxpool3x3s2(x, y, n, h, w, c):
+    _call("cb_maxpool3x3s2", _p(x), _p(y), n, h, w, c, _s())
+
+
+def subsample2(x, y, n, h, w, c):
+    _call("cb_subsample2", _p(x), _p(y), n, h, w, c, _s())
+
+
+def unsubsample2_mask(dsub, act, dx, n, h, w, c):
+    _call("cb_unsubsample2_mask", _p(dsub), _p(act), _p(dx), n, h, w, c, _s())
+
+
+def maxpool2x2_relu_fwd(x, y, n, h, w, c):
+    _call("cb_maxpool2x2_relu_fwd", _p(x), _p(y), n, h, w, c, _s())
+
+
+def maxpool2x2_relu_bwd(dy, x, dx_pad, n, h, w, c):
+    _call("cb_maxpool2x2_relu_bwd", _p(dy), _p(x), _p(dx_pad), n, h, w, c, _s())
+
+
+def relu_mask(dy, act, dx):
+    _call("cb_relu_mask", _p(dy), _p(act), _p(dx), dy.numel(), _s())

@@ -51,6 +51,9 @@ int64_t cb_launch_count(void);
  *     ntaps = 1 for Linear / 1x1 conv. ntaps = 9 is a 3x3 pad-1 conv over a zero-bordered
  *     ("padded") NHWC activation whose rows are flat pixels p = (img*(H+2) + y)*(W+2) + x;
  *     shift_t = tap_sign * ((t/3 - 1)*(W+2) + (t%3 - 1)). tap_sign = -1 gives the dgrad conv.
+ * mode CB_GEMM_NN : as TN but B is stored [K, ntaps*N] row-major (the forward weight [out=K, in=N]
+ *     read "MN-major"): out[m, n] = epi( sum_t sum_k A[m + shift_t, k] * B[k, t*N + n] ). This is
+ *     the dgrad of Linear / conv straight from the forward weight layout (no transposed copy).
  * mode CB_GEMM_WGRAD : out[m, t*N + n] += rowscale[m] * sum_p A[p, m] * B[p + shift_t, n]
  *     A: bf16 [P, M] (dY), B: bf16 [P, N] (X); both operands are read "MN-major" straight from
  *     the activation layout; fp32 red.global.add accumulation (split over P across grid.z).
@@ -65,7 +68,7 @@ int64_t cb_launch_count(void);
  *     out[row(m), n] = v                 (bf16 or fp32)
  * row(m) re-maps between compact NHWC pixel rows and zero-bordered rows (cb_rowmap).
  * ------------------------------------------------------------------------------------------ */
-enum { CB_GEMM_TN = 0, CB_GEMM_WGRAD = 1 };
+enum { CB_GEMM_TN = 0, CB_GEMM_WGRAD = 1, CB_GEMM_NN = 2 };
 enum { CB_ACT_NONE = 0, CB_ACT_RELU = 1, CB_ACT_GELU = 2, CB_ACT_TANH = 3 };
 enum {
   CB_AUX_NONE = 0,
@@ -110,6 +113,102 @@ typedef struct cb_gemm_desc {
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over rows of a bf16 [m, 768] matrix (fp32 statistics, warp-shuffle reductions).
+ * Replaces apex FusedLayerNorm (src/modeling/transformers.py:32,165,293,373; modeling.py:12,58).
+ * The residual add / dropout that precede it in BertSelfOutput / BertOutput
+ * (transformers.py:297-301, 377-381) are fused into the producing cb_gemm epilogue.
+ *   fwd : y = (x - mean) * rstd * gamma + beta ; stats[m] = (mean, rstd)
+ *   bwd : dx (bf16) ; dx_drop = dx * dropout_mask(seed, element) (bf16, optional: the gradient
+ *         entering the dense layer that fed this LN through dropout) ; dgamma / dbeta / dbias_drop
+ *         (fp32, atomically accumulated; dbias_drop = column sums of dx_drop = that dense's bias grad)
+ * ------------------------------------------------------------------------------------------ */
+int cb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int m, int hidden,
+                     float eps, void* stream);
+int cb_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, void* dx, void* dx_drop,
+                     float* dgamma, float* dbeta, float* dbias_drop, int m, int hidden, float dropout_p,
+                     uint64_t dropout_seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embeddings. out is the bf16 [nseq * l, 768] encoder input; text rows go to positions [0, lt),
+ * visual rows to [lt, l) of every sequence, i.e. the torch.cat([text; visual]) of
+ * src/modeling/modeling.py:219-223 is a write offset, not a copy.
+ *   text   : BertEmbeddings.forward (transformers.py:172-199): LN(word[id] + pos[t] + type[0]), dropout
+ *   visual : VisualInputEmbedding.forward (modeling.py:62-101): mean over frames, + row/col position
+ *            (modeling.py:124-153), + type[0], LN, dropout; the row gather of repeat_tensor_rows
+ *            (src/datasets/data_utils.py:344-357) is fused: sequence s reads video seq2vid[s]
+ *            (or s / n_ex when seq2vid is NULL). Tables / LN parameters are fp32.
+ *   bwd    : scatter-adds into the fp32 table gradients; the visual backward also reduces over the
+ *            sequences of a video and the frame mean, producing dgrid (bf16 [nvid, t, gh*gw, 768]).
+ * ------------------------------------------------------------------------------------------ */
+int cb_embed_text_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                      const float* beta, void* out, float* stats, int nseq, int lt, int l, int vocab, int hidden,
+                      float eps, float dropout_p, uint64_t seed, void* stream);
+int cb_embed_text_bwd(const void* dh, const int64_t* ids, const float* word, const float* pos, const float* type0,
+                      const float* gamma, const float* stats, float* dword, float* dpos, float* dtype0, float* dgamma,
+                      float* dbeta, int nseq, int lt, int l, int vocab, int hidden, float dropout_p, uint64_t seed,
+                      void* stream);
+int cb_embed_visual_fwd(const void* grid, const int32_t* seq2vid, int n_ex, const float* rowemb, const float* colemb,
+                        const float* type0, const float* gamma, const float* beta, void* out, float* stats, int nseq,
+                        int t, int gh, int gw, int lt, int l, int hidden, float eps, float dropout_p, uint64_t seed,
+                        void* stream);
+int cb_embed_visual_bwd(const void* dh, const void* grid, const int32_t* seq2vid, const int32_t* vid_start, int n_ex,
+                        const float* rowemb, const float* colemb, const float* type0, const float* gamma,
+                        const float* stats, float* dv_tmp, void* dgrid, float* drow, float* dcol, float* dtype0,
+                        float* dgamma, float* dbeta, int nseq, int nvid, int t, int gh, int gw, int lt, int l, int hidden,
+                        float dropout_p, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused self-attention, BertSelfAttention.forward (transformers.py:230-286):
+ *   S = Q K^T / 8 + (1 - mask) * -10000 ; P = softmax(S) (fp32) ; dropout(P) ; ctx = P V ; heads merged.
+ * qkv: bf16 [nseq*l, 3*heads*64] (Q | K | V as produced by the fused N=2304 projection);
+ * text_mask: int64 [nseq, lt] (visual tokens are always attendable, modeling.py:217-220);
+ * ctx: bf16 [nseq*l, heads*64]; lse: fp32 [nseq, heads, l] log-sum-exp saved for the backward.
+ * The backward recomputes P tile by tile from Q, K, lse and regenerates the dropout mask.
+ * ------------------------------------------------------------------------------------------ */
+int cb_attention_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse,
+                     int nseq, int l, int lt, int heads, int head_dim, float dropout_p, uint64_t seed, void* stream);
+int cb_attention_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx,
+                     int64_t ld_ctx, const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads,
+                     int head_dim, float dropout_p, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small helpers on the transformer side.
+ *   cb_colsum     out[n] += sum_m x[m, n]            bias gradients of nn.Linear (autograd of F.linear)
+ *   cb_dropout    y = dropout(x)                     nn.Dropout before the classifier (modeling.py:552)
+ *   cb_pad_cast   fp32 [rows, c] -> bf16 [rows, cpad] zero padded (d logits -> padded head gradient)
+ *   cb_cast_scale fp32 -> bf16 operand packing, optional per-row scale (FrozenBN scale folded into the
+ *                 conv weight: w'[o, :] = w[o, :] * gamma[o] * rsqrt(var[o] + 1e-5), d2 FrozenBatchNorm2d)
+ * ------------------------------------------------------------------------------------------ */
+int cb_colsum(const void* x, int64_t ld, float* out, int m, int n, void* stream);
+int cb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int cpad, void* stream);
+int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CNN-side data movement (NHWC bf16, 8 channels per 128-bit access). Call sites replaced:
+ * GridFeatBackbone.forward (src/modeling/grid_feat.py:89-105) -> detectron2 BasicStem /
+ * BottleneckBlock (stride-in-1x1) / grid_encoder MaxPool2d+ReLU (grid_feat.py:43-48).
+ *   cb_stem_im2col          7x7/s2/p3 patch gather of the NCHW RGB input into bf16 [n*ho*wo, kp] rows,
+ *                           K = (r, s, c) with c in BGR order (the x[:, [2,1,0]] flip of grid_feat.py:92-94
+ *                           is folded in); in_dtype 1 = uint8 frames with the ImageNorm mean subtraction
+ *                           (src/datasets/data_utils.py:256-276) fused. The stem GEMM follows.
+ *   cb_maxpool3x3s2         BasicStem max_pool2d(3, 2, 1)
+ *   cb_subsample2           input of a stride-2 1x1 conv (res3/4/5 block 0 conv1 + shortcut)
+ *   cb_unsubsample2_mask    its backward fused with the ReLU mask of the producing block
+ *   cb_maxpool2x2_relu_fwd  grid_encoder MaxPool2d(2,2) + ReLU (7x7 -> 3x3 at 224 px, 14x14 -> 7x7 at 448)
+ *   cb_maxpool2x2_relu_bwd  its backward, written into the zero-bordered layout read by the 3x3 dgrad/wgrad
+ *   cb_relu_mask            dx = dy * (act > 0)
+ * ------------------------------------------------------------------------------------------ */
+int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, int kp, float mean_r, float mean_g,
+                   float mean_b, void* stream);
+int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int cb_unsubsample2_mask(const void* dsub, const void* act, void* dx, int n, int h, int w, int c, void* stream);
+int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, int h, int w, int c, void* stream);
+int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

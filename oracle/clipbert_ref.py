@@ -41,6 +41,38 @@ FROZEN_BN_EPS = 1e-5
 
 
 # ----------------------------------------------------------------------------------------------
+# Rounding hooks. With the defaults (identity) every function below is the plain fp32 restatement
+# that is pinned against the reference. ``Rounding.bf16()`` turns the SAME functions into the
+# "bf16-rounding-matched oracle" of SURVEY.md §7: values are rounded to bf16 at exactly the points
+# where the B200 path stores bf16 (activations after each fused conv / linear epilogue, tensor-core
+# weight operands, FrozenBN scale folded into the conv weight before rounding), all sums stay fp32.
+# ----------------------------------------------------------------------------------------------
+class Rounding:
+    def __init__(self, act=None, weight=None, fold_bn=False, relu_masks=None):
+        self.act = act or (lambda x: x)
+        self.weight = weight or (lambda w: w)
+        self.fold_bn = fold_bn
+        # Optional {site name: bool tensor}: replace relu(z) by z * mask at that site. Gradient tests use the
+        # masks of the run under test: a ReLU net's gradient is discontinuous in its activation pattern, so two
+        # forwards that differ by bf16 rounding flip ~0.1 % of the units per layer and their gradients drift apart
+        # by several % per layer for reasons unrelated to the backward kernels being checked.
+        self.relu_masks = relu_masks or {}
+        self.pool_indices = None   # optional argmax indices (F.max_pool2d layout) for the grid_encoder max-pool
+
+    def relu(self, z, site):
+        m = self.relu_masks.get(site)
+        return F.relu(z) if m is None else z * m.to(z.dtype)
+
+    @staticmethod
+    def bf16():
+        r = lambda x: x.to(torch.bfloat16).to(torch.float32)   # noqa: E731
+        return Rounding(act=r, weight=r, fold_bn=True)
+
+
+EXACT = Rounding()
+
+
+# ----------------------------------------------------------------------------------------------
 # CNN: GridFeatBackbone.forward  (src/modeling/grid_feat.py:89-105)
 # ----------------------------------------------------------------------------------------------
 def frozen_bn(x, sd, prefix):
@@ -50,43 +82,49 @@ def frozen_bn(x, sd, prefix):
     return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
 
 
-def conv_bn(x, sd, prefix, stride=1, padding=0):
+def conv_bn(x, sd, prefix, stride=1, padding=0, rnd=EXACT):
+    if rnd.fold_bn:
+        n = prefix + "norm."
+        scale = sd[n + "weight"] * (sd[n + "running_var"] + FROZEN_BN_EPS).rsqrt()
+        shift = sd[n + "bias"] - sd[n + "running_mean"] * scale
+        w = rnd.weight(sd[prefix + "weight"] * scale.view(-1, 1, 1, 1))
+        return F.conv2d(x, w, None, stride=stride, padding=padding) + shift.view(1, -1, 1, 1)
     y = F.conv2d(x, sd[prefix + "weight"], None, stride=stride, padding=padding)
     return frozen_bn(y, sd, prefix + "norm.")
 
 
-def basic_stem(x, sd, prefix):
+def basic_stem(x, sd, prefix, rnd=EXACT):
     """d2 BasicStem: conv7x7 s2 p3 -> FrozenBN -> ReLU -> maxpool 3x3 s2 p1."""
-    x = F.relu(conv_bn(x, sd, prefix + "conv1.", stride=2, padding=3))
+    x = rnd.act(F.relu(conv_bn(rnd.act(x), sd, prefix + "conv1.", stride=2, padding=3, rnd=rnd)))
     return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
 
 
-def bottleneck_block(x, sd, prefix, stride, has_shortcut):
+def bottleneck_block(x, sd, prefix, stride, has_shortcut, rnd=EXACT):
     """d2 BottleneckBlock with stride_in_1x1=True (MSRA R-50)."""
-    out = F.relu(conv_bn(x, sd, prefix + "conv1.", stride=stride))
-    out = F.relu(conv_bn(out, sd, prefix + "conv2.", stride=1, padding=1))
-    out = conv_bn(out, sd, prefix + "conv3.")
-    shortcut = conv_bn(x, sd, prefix + "shortcut.", stride=stride) if has_shortcut else x
-    return F.relu(out + shortcut)
+    out = rnd.act(rnd.relu(conv_bn(x, sd, prefix + "conv1.", stride=stride, rnd=rnd), prefix + "conv1"))
+    out = rnd.act(rnd.relu(conv_bn(out, sd, prefix + "conv2.", stride=1, padding=1, rnd=rnd), prefix + "conv2"))
+    out = conv_bn(out, sd, prefix + "conv3.", rnd=rnd)
+    shortcut = rnd.act(conv_bn(x, sd, prefix + "shortcut.", stride=stride, rnd=rnd)) if has_shortcut else x
+    return rnd.act(rnd.relu(out + shortcut, prefix + "out"))
 
 
-def resnet50_res5(x, sd, prefix="cnn.feature.backbone.", freeze_at=2, return_stages=False):
+def resnet50_res5(x, sd, prefix="cnn.feature.backbone.", freeze_at=2, return_stages=False, rnd=EXACT):
     """feature.backbone(x)["res5"]; stem/res2 detached from autograd when freeze_at >= 2."""
     stages = {}
-    x = basic_stem(x, sd, prefix + "stem.")
+    x = basic_stem(x, sd, prefix + "stem.", rnd)
     if freeze_at >= 1:
         x = x.detach()
     stages["stem"] = x
     for si, (name, nblocks, _, _, stride) in enumerate(RESNET50_STAGES):
         for b in range(nblocks):
-            x = bottleneck_block(x, sd, "%s%s.%d." % (prefix, name, b), stride if b == 0 else 1, b == 0)
+            x = bottleneck_block(x, sd, "%s%s.%d." % (prefix, name, b), stride if b == 0 else 1, b == 0, rnd)
         if freeze_at >= si + 2:
             x = x.detach()
         stages[name] = x
     return (x, stages) if return_stages else x
 
 
-def grid_feat_backbone(visual_inputs, sd, prefix="cnn.", freeze_at=2, return_stages=False):
+def grid_feat_backbone(visual_inputs, sd, prefix="cnn.", freeze_at=2, return_stages=False, rnd=EXACT):
     """GridFeatBackbone.forward: (B,T,3,H,W) RGB float -> (B,T,h,w,768).
 
     view -> BGR flip (grid_feat.py:92-94) -> backbone res5 -> get_conv5_features (identity,
@@ -96,9 +134,14 @@ def grid_feat_backbone(visual_inputs, sd, prefix="cnn.", freeze_at=2, return_sta
     bsz, n_frms, c, h, w = visual_inputs.shape
     x = visual_inputs.reshape(bsz * n_frms, c, h, w)
     x = x[:, [2, 1, 0], :, :]
-    res5, stages = resnet50_res5(x, sd, prefix + "feature.backbone.", freeze_at, return_stages=True)
-    g = F.conv2d(res5, sd[prefix + "grid_encoder.0.weight"], None, stride=1, padding=1)
-    g = F.relu(F.max_pool2d(g, kernel_size=2, stride=2))
+    res5, stages = resnet50_res5(x, sd, prefix + "feature.backbone.", freeze_at, return_stages=True, rnd=rnd)
+    g = rnd.act(F.conv2d(res5, rnd.weight(sd[prefix + "grid_encoder.0.weight"]), None, stride=1, padding=1))
+    if rnd.pool_indices is not None:      # same selection as the run under test (ties / near-ties differ otherwise)
+        n_, c_ = g.shape[:2]
+        g = g.flatten(2).gather(2, rnd.pool_indices.flatten(2)).view(n_, c_, g.shape[2] // 2, g.shape[3] // 2)
+    else:
+        g = F.max_pool2d(g, kernel_size=2, stride=2)
+    g = rnd.relu(g, prefix + "grid_encoder")
     nc, nh, nw = g.shape[-3:]
     g = g.view(bsz, n_frms, nc, nh, nw).permute(0, 1, 3, 4, 2)
     if return_stages:
@@ -122,8 +165,8 @@ def layer_norm(x, sd, prefix, eps):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
 
 
-def linear(x, sd, prefix):
-    return F.linear(x, sd[prefix + "weight"], sd[prefix + "bias"])
+def linear(x, sd, prefix, rnd=EXACT):
+    return F.linear(x, rnd.weight(sd[prefix + "weight"]), sd[prefix + "bias"])
 
 
 def bert_embeddings(input_ids, sd, prefix, eps):
@@ -145,48 +188,49 @@ def visual_embeddings(grid, sd, prefix, eps):
     return layer_norm(v, sd, prefix + "LayerNorm.", eps)
 
 
-def bert_layer(h, ext_mask, sd, prefix, n_heads, eps):
+def bert_layer(h, ext_mask, sd, prefix, n_heads, eps, rnd=EXACT):
     """BertLayer.forward (transformers.py:394-418) = attention + intermediate + output."""
     b, l, d = h.shape
     hd = d // n_heads
+    r = rnd.act
 
     def split(x):
         return x.view(b, l, n_heads, hd).permute(0, 2, 1, 3)
 
-    q = split(linear(h, sd, prefix + "attention.self.query."))
-    k = split(linear(h, sd, prefix + "attention.self.key."))
-    v = split(linear(h, sd, prefix + "attention.self.value."))
+    q = split(r(linear(h, sd, prefix + "attention.self.query.", rnd)))
+    k = split(r(linear(h, sd, prefix + "attention.self.key.", rnd)))
+    v = split(r(linear(h, sd, prefix + "attention.self.value.", rnd)))
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd) + ext_mask       # :257-264
     p = torch.softmax(s, dim=-1)
-    ctx = torch.matmul(p, v).permute(0, 2, 1, 3).reshape(b, l, d)
-    a = layer_norm(linear(ctx, sd, prefix + "attention.output.dense.") + h, sd,
-                   prefix + "attention.output.LayerNorm.", eps)               # :297-301
-    i = F.gelu(linear(a, sd, prefix + "intermediate.dense."))                 # :363-366 (erf gelu)
-    return layer_norm(linear(i, sd, prefix + "output.dense.") + a, sd, prefix + "output.LayerNorm.", eps)
+    ctx = r(torch.matmul(p, v).permute(0, 2, 1, 3).reshape(b, l, d))
+    a = r(layer_norm(r(linear(ctx, sd, prefix + "attention.output.dense.", rnd) + h), sd,
+                     prefix + "attention.output.LayerNorm.", eps))            # :297-301
+    i = r(F.gelu(linear(a, sd, prefix + "intermediate.dense.", rnd)))         # :363-366 (erf gelu)
+    return r(layer_norm(r(linear(i, sd, prefix + "output.dense.", rnd) + a), sd, prefix + "output.LayerNorm.", eps))
 
 
 def clipbert_base_model(text_input_ids, grid, text_mask, sd, prefix="transformer.bert.", cfg=BERT_CFG,
-                        return_layers=False):
+                        return_layers=False, rnd=EXACT):
     """ClipBertBaseModel.forward: returns (sequence_output, pooled_output)."""
     eps = cfg["layer_norm_eps"]
-    te = bert_embeddings(text_input_ids, sd, prefix + "embeddings.", eps)
-    ve = visual_embeddings(grid, sd, prefix + "visual_embeddings.", eps)
+    te = rnd.act(bert_embeddings(text_input_ids, sd, prefix + "embeddings.", eps))
+    ve = rnd.act(visual_embeddings(rnd.act(grid), sd, prefix + "visual_embeddings.", eps))
     mask = torch.cat([text_mask, text_mask.new_ones(ve.shape[:2])], dim=-1)      # modeling.py:217-220
     h = torch.cat([te, ve], dim=1)                                               # [text ; visual]
     ext = (1.0 - mask[:, None, None, :].to(h.dtype)) * -10000.0                  # hf get_extended_attention_mask
     layers = [h]
     for i in range(cfg["num_hidden_layers"]):
-        h = bert_layer(h, ext, sd, "%sencoder.layer.%d." % (prefix, i), cfg["num_attention_heads"], eps)
+        h = bert_layer(h, ext, sd, "%sencoder.layer.%d." % (prefix, i), cfg["num_attention_heads"], eps, rnd)
         layers.append(h)
-    pooled = torch.tanh(linear(h[:, 0], sd, prefix + "pooler.dense."))          # transformers.py:470-476
+    pooled = rnd.act(torch.tanh(linear(h[:, 0], sd, prefix + "pooler.dense.", rnd)))   # transformers.py:470-476
     if return_layers:
         return h, pooled, layers
     return h, pooled
 
 
-def mlp_head(pooled, sd, prefix="transformer.classifier."):
+def mlp_head(pooled, sd, prefix="transformer.classifier.", rnd=EXACT):
     """nn.Sequential(Linear(768,1536), ReLU, Linear(1536,num_labels)) (modeling.py:534-539)."""
-    return linear(F.relu(linear(pooled, sd, prefix + "0.")), sd, prefix + "2.")
+    return linear(rnd.act(rnd.relu(linear(pooled, sd, prefix + "0.", rnd), prefix + "relu")), sd, prefix + "2.", rnd)
 
 
 def retrieval_loss(logits, labels, loss_type="ce", margin=0.2, sample_size=-1):
@@ -198,26 +242,26 @@ def retrieval_loss(logits, labels, loss_type="ce", margin=0.2, sample_size=-1):
 
 
 def video_text_retrieval(text_input_ids, grid, text_mask, sd, labels=None, loss_type="ce", margin=0.2,
-                         sample_size=-1):
+                         sample_size=-1, rnd=EXACT):
     """ClipBertForVideoTextRetrieval.forward (modeling.py:543-558), eval mode (dropout off)."""
-    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd)
-    logits = mlp_head(pooled, sd)
+    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd, rnd=rnd)
+    logits = mlp_head(pooled, sd, rnd=rnd)
     loss = retrieval_loss(logits, labels, loss_type, margin, sample_size) if labels is not None else 0
     return dict(logits=logits, loss=loss)
 
 
-def multiple_choice(text_input_ids, grid, text_mask, sd, num_labels, labels=None):
+def multiple_choice(text_input_ids, grid, text_mask, sd, num_labels, labels=None, rnd=EXACT):
     """ClipBertForMultipleChoice.forward + calc_loss with loss_type 'ce' (modeling.py:403-451)."""
-    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd)
-    logits = mlp_head(pooled, sd).view(-1, num_labels)
+    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd, rnd=rnd)
+    logits = mlp_head(pooled, sd, rnd=rnd).view(-1, num_labels)
     loss = F.cross_entropy(logits, labels.view(-1), reduction="none") if labels is not None else 0
     return dict(logits=logits, loss=loss)
 
 
-def sequence_classification(text_input_ids, grid, text_mask, sd, labels=None, loss_type="bce"):
+def sequence_classification(text_input_ids, grid, text_mask, sd, labels=None, loss_type="bce", rnd=EXACT):
     """ClipBertForSequenceClassification.forward (modeling.py:347-384)."""
-    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd)
-    logits = mlp_head(pooled, sd)
+    _, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd, rnd=rnd)
+    logits = mlp_head(pooled, sd, rnd=rnd)
     if labels is None:
         loss = 0
     elif loss_type == "bce":
@@ -248,7 +292,7 @@ def pretraining(text_input_ids, grid, text_mask, sd, mlm_labels=None, itm_labels
 # ----------------------------------------------------------------------------------------------
 def clipbert_forward(batch, sd, head="retrieval", freeze_at=2, **head_kw):
     """ClipBert.forward (src/modeling/e2e_model.py:29-39) for one clip."""
-    feats = grid_feat_backbone(batch["visual_inputs"], sd, "cnn.", freeze_at)
+    feats = grid_feat_backbone(batch["visual_inputs"], sd, "cnn.", freeze_at, rnd=head_kw.get("rnd", EXACT))
     feats = repeat_tensor_rows(feats, batch["n_examples_list"])
     if head == "retrieval":
         return video_text_retrieval(batch["text_input_ids"], feats, batch["text_input_mask"], sd,

@@ -1,0 +1,402 @@
+"""Per-kernel parity: every C-ABI entry point against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import TOL_BF16_OP, TOL_FP32_OP, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from clipbert_b200 import ops
+    return ops
+
+
+def _rnd(g, *shape, scale=1.0, dev="cuda"):
+    return (torch.randn(*shape, generator=g) * scale).to(dev).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (1312, 768, 768), (77, 264, 1096)])
+def test_gemm_tn_fp32_out(cuda, bn, shape):
+    ops = _ops()
+    M, N, K = shape
+    g = torch.Generator().manual_seed(1)
+    A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
+    C = torch.full((M, N), 7.0, device=cuda)
+    ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N, out_fp32=1, block_n=bn)
+    assert relerr(C, A.float() @ B.float().t()) < TOL_FP32_OP
+
+
+@pytest.mark.parametrize("shape", [(500, 384, 256), (1312, 2304, 768), (64, 768, 3072)])
+def test_gemm_nn_dgrad(cuda, shape):
+    ops = _ops()
+    M, N, K = shape     # out [M, N] = A [M, K] @ B [K, N]
+    g = torch.Generator().manual_seed(2)
+    A, B = _rnd(g, M, K), _rnd(g, K, N, scale=0.1)
+    C = torch.zeros(M, N, device=cuda)
+    ops.gemm(mode=ops.CB_GEMM_NN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=K, b_ld=N, out=C, out_ld=N, out_fp32=1)
+    assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
+
+
+def test_gemm_epilogues(cuda):
+    ops = _ops()
+    M, N, K = 500, 384, 256
+    g = torch.Generator().manual_seed(3)
+    A, B, R, AUX = _rnd(g, M, K), _rnd(g, N, K, scale=0.1), _rnd(g, M, N), _rnd(g, M, N)
+    scale = (torch.rand(N, generator=g) + 0.5).to(cuda)
+    shift = torch.randn(N, generator=g).to(cuda)
+    acc = A.float() @ B.float().t()
+    base = dict(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out_ld=N)
+    C, C2 = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16), torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(**base, scale=scale, shift=shift, residual=R, res_ld=N, act=ops.ACT_RELU, out=C, out2=C2, out2_ld=N)
+    pre = acc * scale + shift + R.float()
+    assert relerr(C, pre.relu()) < TOL_BF16_OP and relerr(C2, pre) < TOL_BF16_OP
+    ops.gemm(**base, shift=shift, act=ops.ACT_GELU, out=C)
+    assert relerr(C, F.gelu(acc + shift)) < TOL_BF16_OP
+    ops.gemm(**base, shift=shift, act=ops.ACT_TANH, out=C)
+    assert relerr(C, torch.tanh(acc + shift)) < TOL_BF16_OP
+    a = AUX.float()
+    gelu_grad = 0.5 * (1 + torch.erf(a / math.sqrt(2))) + a * torch.exp(-0.5 * a * a) / math.sqrt(2 * math.pi)
+    for mode, fac in [(ops.AUX_RELU_MASK, (a > 0).float()), (ops.AUX_GELU_GRAD, gelu_grad), (ops.AUX_TANH_GRAD, 1 - a * a)]:
+        ops.gemm(**base, residual=R, res_ld=N, aux=AUX, aux_ld=N, aux_mode=mode, out=C)
+        assert relerr(C, (acc + R.float()) * fac) < TOL_BF16_OP
+
+
+@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64)])
+def test_conv3x3_fwd_and_dgrad(cuda, dims):
+    ops = _ops()
+    NB, H, W, Cin, Cout = dims
+    g = torch.Generator().manual_seed(4)
+    x = _rnd(g, NB, H, W, Cin)
+    w = _rnd(g, Cout, Cin, 3, 3, scale=0.05)
+    xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
+    xp[:, 1:-1, 1:-1] = x
+    P = NB * (H + 2) * (W + 2)
+    y = torch.zeros(NB * H * W, Cout, device=cuda, dtype=torch.bfloat16)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
+    ops.gemm(mode=ops.CB_GEMM_TN, m=P, n=Cout, k=Cin, a=xp, a_rows=P, a_ld=Cin, b=wk, b_rows=Cout, b_ld=9 * Cin, ntaps=9,
+             tap_w=W + 2, tap_sign=1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert relerr(y, ref) < TOL_BF16_OP
+    # dgrad of a conv whose forward weight is wf [Cin(out), Cout(in), 3, 3] stored KRSC: x plays dY
+    wf = _rnd(g, Cin, Cout, 3, 3, scale=0.05)
+    wfk = wf.permute(0, 2, 3, 1).contiguous().view(Cin, 9 * Cout)         # [out_f, (r,s,in_f)] = forward layout
+    ops.gemm(mode=ops.CB_GEMM_NN, m=P, n=Cout, k=Cin, a=xp, a_rows=P, a_ld=Cin, b=wfk, b_rows=Cin, b_ld=9 * Cout, ntaps=9,
+             tap_w=W + 2, tap_sign=-1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wf.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert relerr(y, ref) < TOL_BF16_OP
+
+
+def test_rowmap_pad_keeps_border_zero(cuda):
+    ops = _ops()
+    NB, H, W, K, N = 3, 5, 6, 64, 64
+    M = NB * H * W
+    g = torch.Generator().manual_seed(5)
+    A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
+    yp = torch.zeros(NB, H + 2, W + 2, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=yp, out_ld=N,
+             rowmap=ops.ROWMAP_PAD, map_h=H, map_w=W)
+    ref = (A.float() @ B.float().t()).view(NB, H, W, N)
+    assert relerr(yp[:, 1:-1, 1:-1], ref) < TOL_BF16_OP
+    inner = yp[:, 1:-1, 1:-1].float().abs().sum()
+    assert float(yp.float().abs().sum() - inner) == 0.0
+
+
+@pytest.mark.parametrize("case", [(64, 128, 64, 64, 1), (1312, 768, 768, 128, 1), (1000, 256, 192, 64, 1), (333, 136, 72, 64, 1),
+                                  (5000, 256, 256, 128, 7), (640, 128, 128, 64, 100), (32, 8, 1536, 128, 1)])
+def test_wgrad(cuda, case):
+    ops = _ops()
+    P, Mo, No, bn, sk = case
+    g = torch.Generator().manual_seed(6)
+    dY, X = _rnd(g, P, Mo), _rnd(g, P, No)
+    rs = (torch.rand(Mo, generator=g) + 0.5).to(cuda)
+    dW = torch.zeros(Mo, No, device=cuda)
+    ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk, scale=rs,
+             out=dW, out_ld=No, out_fp32=1, block_n=bn)
+    assert relerr(dW, (dY.float().t() @ X.float()) * rs[:, None]) < TOL_FP32_OP
+    # accumulation semantics: a second launch adds
+    ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk, scale=rs,
+             out=dW, out_ld=No, out_fp32=1, block_n=bn)
+    assert relerr(dW, 2 * (dY.float().t() @ X.float()) * rs[:, None]) < TOL_FP32_OP
+
+
+@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 128, 1), (4, 14, 14, 128, 128, 3)])
+def test_wgrad_conv3x3(cuda, dims):
+    ops = _ops()
+    NB, H, W, Cin, Cout, sk = dims
+    g = torch.Generator().manual_seed(7)
+    x, dy = _rnd(g, NB, H, W, Cin), _rnd(g, NB, H, W, Cout)
+    xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
+    dyp = torch.zeros(NB, H + 2, W + 2, Cout, device=cuda, dtype=torch.bfloat16)
+    xp[:, 1:-1, 1:-1], dyp[:, 1:-1, 1:-1] = x, dy
+    P = NB * (H + 2) * (W + 2)
+    dW = torch.zeros(Cout, 9 * Cin, device=cuda)
+    ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Cout, n=Cin, k=P, a=dyp, a_rows=P, a_ld=Cout, b=xp, b_rows=P, b_ld=Cin, ntaps=9, tap_w=W + 2,
+             tap_sign=1, split_k=sk, out=dW, out_ld=9 * Cin, out_fp32=1)
+    wz = torch.zeros(Cout, Cin, 3, 3, device=cuda, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert relerr(dW, wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)) < TOL_FP32_OP
+
+
+def test_gemm_dropout_is_a_pure_function_of_seed_and_index(cuda):
+    ops = _ops()
+    M, N, K = 512, 768, 64
+    g = torch.Generator().manual_seed(8)
+    A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
+    outs = []
+    for bn in (64, 128):
+        C = torch.zeros(M, N, device=cuda)
+        ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N, out_fp32=1,
+                 dropout_p=0.1, dropout_seed=99, block_n=bn)
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1])            # same mask whatever the tiling
+    keep = outs[0] != 0
+    assert abs(float(keep.float().mean()) - 0.9) < 0.01
+    ref = A.float() @ B.float().t()
+    assert relerr(outs[0][keep], ref[keep] / 0.9) < TOL_FP32_OP
+    # the standalone dropout kernel and the LayerNorm-backward mask use the same generator
+    x = torch.ones(M, N, device=cuda, dtype=torch.bfloat16)
+    y = torch.empty_like(x)
+    ops.dropout(x, y, 0.1, 99)
+    assert torch.equal(y != 0, keep)
+
+
+def test_gemm_rejects_bad_arguments(cuda):
+    ops = _ops()
+    A = torch.zeros(16, 12, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.gemm(mode=ops.CB_GEMM_TN, m=16, n=12, k=12, a=A, a_rows=16, a_ld=12, b=A, b_rows=12, b_ld=12, out=A, out_ld=12)
+    with pytest.raises(RuntimeError, match="null"):
+        ops.gemm(mode=ops.CB_GEMM_TN, m=16, n=16, k=16, a=None, a_rows=16, a_ld=16, b=A, b_rows=16, b_ld=16, out=A, out_ld=16)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("M", [1, 5, 1312])
+def test_layernorm_fwd_bwd(cuda, M):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = _rnd(g, M, 768, scale=2.0)
+    gam = (1 + 0.1 * torch.randn(768, generator=g)).to(cuda)
+    bet = (0.1 * torch.randn(768, generator=g)).to(cuda)
+    dy = _rnd(g, M, 768)
+    y = torch.empty_like(x)
+    stats = torch.empty(M, 2, device=cuda)
+    ops.layernorm_fwd(x, gam, bet, y, stats, 1e-12)
+    xr = x.float().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (768,), gr, br, 1e-12)
+    assert relerr(y, ref) < TOL_BF16_OP
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dgam, dbet, dbias = torch.zeros(768, device=cuda), torch.zeros(768, device=cuda), torch.zeros(768, device=cuda)
+    ops.layernorm_bwd(dy, x, stats, gam, dx, None, dgam, dbet, dbias, 0.0, 0)
+    assert relerr(dx, xr.grad) < TOL_BF16_OP
+    assert relerr(dgam, gr.grad) < 1e-4 and relerr(dbet, br.grad) < 1e-4
+    assert relerr(dbias, dx.float().sum(0)) < 1e-4
+    # dropped copy: same mask as the forward GEMM epilogue would have used for (row, col)
+    dxd = torch.empty_like(x)
+    ops.layernorm_bwd(dy, x, stats, gam, dx, dxd, None, None, None, 0.1, 1234)
+    ones = torch.ones(M, 768, device=cuda, dtype=torch.bfloat16)
+    msk = torch.empty_like(ones)
+    ops.dropout(ones, msk, 0.1, 1234)
+    assert relerr(dxd, dx.float() * msk.float()) < TOL_BF16_OP
+
+
+# ------------------------------------------------------------------------------------------------ embeddings
+def test_embed_text_and_visual(cuda):
+    ops = _ops()
+    from oracle import clipbert_ref as R
+    g = torch.Generator().manual_seed(10)
+    nseq, lt, T, gh, gw, n_ex = 6, 12, 2, 3, 3, 2
+    nvid, Lv, L = nseq // n_ex, gh * gw, lt + gh * gw
+    sd = {k: (torch.randn(*s, generator=g) * 0.5) for k, s in {
+        "e.word_embeddings.weight": (500, 768), "e.position_embeddings.weight": (64, 768), "e.token_type_embeddings.weight": (2, 768),
+        "v.row_position_embeddings.weight": (10, 768), "v.col_position_embeddings.weight": (10, 768),
+        "v.token_type_embeddings.weight": (1, 768)}.items()}
+    for p in ("e.", "v."):
+        sd[p + "LayerNorm.weight"] = 1 + 0.1 * torch.randn(768, generator=g)
+        sd[p + "LayerNorm.bias"] = 0.1 * torch.randn(768, generator=g)
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    ids = torch.randint(0, 500, (nseq, lt), generator=g)
+    grid = _rnd(g, nvid, T, gh, gw, 768, dev="cpu").float().requires_grad_(True)
+    te = R.bert_embeddings(ids, sd, "e.", 1e-12)
+    ve = R.visual_embeddings(R.repeat_tensor_rows(grid, [n_ex] * nvid), sd, "v.", 1e-12)
+    ref = torch.cat([te, ve], 1)
+    dh = _rnd(g, nseq, L, 768, dev="cpu")
+    ref.backward(dh.float())
+
+    d = {k: v.detach().to(cuda) for k, v in sd.items()}
+    out = torch.zeros(nseq * L, 768, device=cuda, dtype=torch.bfloat16)
+    st_t, st_v = torch.empty(nseq * lt, 2, device=cuda), torch.empty(nseq * Lv, 2, device=cuda)
+    gridc = grid.detach().to(cuda).to(torch.bfloat16)
+    ops.embed_text_fwd(ids.to(cuda), d["e.word_embeddings.weight"], d["e.position_embeddings.weight"], d["e.token_type_embeddings.weight"],
+                       d["e.LayerNorm.weight"], d["e.LayerNorm.bias"], out, st_t, nseq, lt, L, 1e-12, 0.0, 0)
+    for s2v, starts, nx in [(None, None, n_ex),
+                            (torch.tensor([0, 0, 1, 1, 2, 2], dtype=torch.int32, device=cuda), torch.tensor([0, 2, 4, 6], dtype=torch.int32, device=cuda), 0)]:
+        ops.embed_visual_fwd(gridc, s2v, nx, d["v.row_position_embeddings.weight"], d["v.col_position_embeddings.weight"],
+                             d["v.token_type_embeddings.weight"], d["v.LayerNorm.weight"], d["v.LayerNorm.bias"], out, st_v, nseq, T, gh, gw,
+                             lt, L, 1e-12, 0.0, 0)
+        assert relerr(out.view(nseq, L, 768), ref) < TOL_BF16_OP
+        gz = {k: torch.zeros_like(v) for k, v in d.items()}
+        dhc = dh.to(cuda).view(nseq * L, 768)
+        ops.embed_text_bwd(dhc, ids.to(cuda), d["e.word_embeddings.weight"], d["e.position_embeddings.weight"], d["e.token_type_embeddings.weight"],
+                           d["e.LayerNorm.weight"], st_t, gz["e.word_embeddings.weight"], gz["e.position_embeddings.weight"],
+                           gz["e.token_type_embeddings.weight"][0], gz["e.LayerNorm.weight"], gz["e.LayerNorm.bias"], nseq, lt, L, 0.0, 0)
+        dv_tmp = torch.empty(nseq * Lv, 768, device=cuda)
+        dgrid = torch.empty(nvid, T, gh, gw, 768, device=cuda, dtype=torch.bfloat16)
+        ops.embed_visual_bwd(dhc, gridc, s2v, starts, nx, d["v.row_position_embeddings.weight"], d["v.col_position_embeddings.weight"],
+                             d["v.token_type_embeddings.weight"], d["v.LayerNorm.weight"], st_v, dv_tmp, dgrid,
+                             gz["v.row_position_embeddings.weight"], gz["v.col_position_embeddings.weight"], gz["v.token_type_embeddings.weight"],
+                             gz["v.LayerNorm.weight"], gz["v.LayerNorm.bias"], nseq, nvid, T, gh, gw, lt, L, 0.0, 0)
+        for k in sd:
+            if sd[k].grad is None:
+                continue
+            assert relerr(gz[k], sd[k].grad) < 2e-3, k
+        assert relerr(dgrid, grid.grad) < TOL_BF16_OP
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("dims", [(3, 41, 32), (2, 150, 100), (1, 64, 64), (2, 9, 0)])
+def test_attention_fwd_bwd(cuda, dims):
+    ops = _ops()
+    nseq, L, lt = dims
+    heads = 12
+    g = torch.Generator().manual_seed(11)
+    qkv = _rnd(g, nseq * L, 3 * 768, scale=1.0)
+    mask = torch.ones(nseq, max(lt, 1), dtype=torch.int64)
+    if lt > 4:
+        mask[0, lt - 3:] = 0
+        mask[-1, lt // 2:] = 0
+    mask = mask[:, :lt] if lt > 0 else torch.ones(nseq, 0, dtype=torch.int64)
+    dctx = _rnd(g, nseq * L, 768)
+    ctx = torch.empty(nseq * L, 768, device=cuda, dtype=torch.bfloat16)
+    lse = torch.empty(nseq, heads, L, device=cuda)
+    mask_c = mask.to(cuda) if lt > 0 else torch.ones(nseq, 1, dtype=torch.int64, device=cuda)
+    ops.attention_fwd(qkv, mask_c, ctx, lse, nseq, L, lt, heads, 0.0, 0)
+
+    x = qkv.float().view(nseq, L, 3, heads, 64).requires_grad_(True)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    full = torch.cat([mask.to(cuda), torch.ones(nseq, L - lt, dtype=torch.int64, device=cuda)], 1)
+    ext = (1.0 - full[:, None, None, :].float()) * -10000.0
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + ext, -1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(nseq * L, 768)
+    assert relerr(ctx, ref) < TOL_BF16_OP
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, mask_c, ctx, dctx, lse, dqkv, nseq, L, lt, heads, 0.0, 0)
+    assert relerr(dqkv, x.grad.reshape(nseq * L, 3 * 768)) < 2 * TOL_BF16_OP
+
+
+def test_attention_dropout_consistency(cuda):
+    """With p>0 the backward must regenerate the forward mask: check dV against a finite set of probes."""
+    ops = _ops()
+    nseq, L, lt, heads = 2, 41, 32, 12
+    g = torch.Generator().manual_seed(12)
+    qkv = _rnd(g, nseq * L, 3 * 768, scale=0.5)
+    mask = torch.ones(nseq, lt, dtype=torch.int64, device=cuda)
+    ctx = torch.empty(nseq * L, 768, device=cuda, dtype=torch.bfloat16)
+    lse = torch.empty(nseq, heads, L, device=cuda)
+    ops.attention_fwd(qkv, mask, ctx, lse, nseq, L, lt, heads, 0.1, 77)
+    # recover the dropped probabilities through V = identity-like probes: P_drop = ctx when V = e_j; instead compare
+    # against torch using the mask inferred from a second forward with V := ones (row sums of dropped P)
+    x = qkv.float().view(nseq, L, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+    qkv1 = qkv.clone().view(nseq, L, 3, heads, 64)
+    qkv1[:, :, 2] = 1.0
+    ctx1 = torch.empty_like(ctx)
+    ops.attention_fwd(qkv1.view(nseq * L, -1), mask, ctx1, None, nseq, L, lt, heads, 0.1, 77)
+    rowsum = ctx1.float().view(nseq, L, heads, 64)[..., 0].permute(0, 2, 1)          # sum_j P_ij * keep_ij / 0.9
+    assert abs(float(rowsum.mean()) - 1.0) < 0.02 and float(rowsum.std()) > 1e-3     # dropout really applied, unbiased
+    # linearity in dO of the backward with the same seed (mask regenerated identically)
+    d1, d2 = _rnd(g, nseq * L, 768), _rnd(g, nseq * L, 768)
+    outs = []
+    for d in (d1, d2, (d1.float() + d2.float()).to(torch.bfloat16)):
+        dq = torch.empty_like(qkv)
+        ops.attention_bwd(qkv, mask, ctx, d, lse, dq, nseq, L, lt, heads, 0.1, 77)
+        outs.append(dq.float())
+    assert relerr(outs[2], outs[0] + outs[1]) < 3 * TOL_BF16_OP
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def test_colsum_padcast_castscale(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    x = _rnd(g, 1000, 2304)
+    out = torch.zeros(2304, device=cuda)
+    ops.colsum(x, out, 1000, 2304)
+    assert relerr(out, x.float().sum(0)) < 1e-5
+    src = torch.randn(37, 2, generator=g).to(cuda)
+    dst = torch.full((37, 8), 5.0, device=cuda, dtype=torch.bfloat16)
+    ops.pad_cast(src, dst)
+    assert torch.equal(dst[:, :2], src.to(torch.bfloat16)) and float(dst[:, 2:].abs().sum()) == 0.0
+    w = torch.randn(64 * 147, generator=g).to(cuda)
+    sc = (torch.rand(64, generator=g) + 0.5).to(cuda)
+    o = torch.empty(64 * 147, device=cuda, dtype=torch.bfloat16)
+    ops.cast_scale(w, o, sc, 147)
+    assert torch.equal(o, (w.view(64, 147) * sc[:, None]).to(torch.bfloat16).view(-1))
+    ops.cast_scale(w, o)
+    assert torch.equal(o, w.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ CNN aux ops
+@pytest.mark.parametrize("hw", [(224, 224), (64, 96), (37, 53)])
+def test_stem_im2col_matches_unfold_with_bgr_flip(cuda, hw):
+    ops = _ops()
+    H, W = hw
+    g = torch.Generator().manual_seed(14)
+    u8 = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8)
+    mean = (123.675, 116.28, 103.53)
+    xf = (u8.float() - torch.tensor(mean).view(1, 3, 1, 1)).to(cuda)
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    col = torch.empty(2 * ho * wo, 152, device=cuda, dtype=torch.bfloat16)
+    ops.stem_im2col(xf, col, 2, H, W, 152)
+    bgr = xf[:, [2, 1, 0]]
+    unf = F.unfold(bgr, kernel_size=7, padding=3, stride=2)                         # [N, 3*49, L] ordered (c, r, s)
+    ref = unf.view(2, 3, 49, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, 147)  # -> (r, s, c)
+    assert torch.equal(col[:, :147], ref.to(torch.bfloat16)) and float(col[:, 147:].float().abs().sum()) == 0.0
+    # uint8 input with fused mean subtraction (ImageNorm) gives the same bits
+    col2 = torch.empty_like(col)
+    ops.stem_im2col(u8.to(cuda), col2, 2, H, W, 152, mean)
+    assert torch.equal(col, col2)
+
+
+def test_pool_and_subsample_ops(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(15)
+    N, H, W, C = 2, 13, 12, 64
+    x = _rnd(g, N, H, W, C)
+    nchw = x.float().permute(0, 3, 1, 2)
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(N, ho, wo, C, device=cuda, dtype=torch.bfloat16)
+    ops.maxpool3x3s2(x, y, N, H, W, C)
+    assert torch.equal(y.float(), F.max_pool2d(nchw, 3, 2, 1).permute(0, 2, 3, 1))
+    ops.subsample2(x, y, N, H, W, C)
+    assert torch.equal(y, x[:, ::2, ::2])
+    dsub, act = _rnd(g, N, ho, wo, C), _rnd(g, N, H, W, C)
+    dx = torch.empty_like(x)
+    ops.unsubsample2_mask(dsub, act, dx, N, H, W, C)
+    ref = torch.zeros_like(x)
+    ref[:, ::2, ::2] = dsub
+    assert torch.equal(dx, ref * (act > 0))
+    ops.relu_mask(x, act, dx)
+    assert torch.equal(dx, x * (act > 0))
+    # grid_encoder tail, 7x7 -> 3x3 (floor), backward into the padded layout
+    H = W = 7
+    xg = _rnd(g, N, H, W, C)
+    xr = xg.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.relu(F.max_pool2d(xr, 2, 2))
+    yg = torch.empty(N, 3, 3, C, device=cuda, dtype=torch.bfloat16)
+    ops.maxpool2x2_relu_fwd(xg, yg, N, H, W, C)
+    assert torch.equal(yg.float(), ref.permute(0, 2, 3, 1))
+    dy = _rnd(g, N, 3, 3, C)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dxp = torch.full((N, H + 2, W + 2, C), 9.0, device=cuda, dtype=torch.bfloat16)
+    ops.maxpool2x2_relu_bwd(dy, xg, dxp, N, H, W, C)
+    assert torch.equal(dxp[:, 1:-1, 1:-1].float(), xr.grad.permute(0, 2, 3, 1))
+    assert float(dxp.float().abs().sum() - dxp[:, 1:-1, 1:-1].float().abs().sum()) == 0.0
