@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""clips/sec forward+backward of the ClipBERT hot path on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                      # this repo's sm_100a path
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                                # the reference's CPU path (oracle port)
+
+One "step" = one training iteration of the reference loop (src/tasks/run_video_retrieval.py:379-432)
+on one synthetic batch per GPU: for each of n_clips clips ClipBert.forward (GridFeat ResNet-50 ->
+12-layer cross-modal BERT -> retrieval head), LSE aggregation of the clip logits + CE loss, backward,
+and (N > 1) the data-parallel gradient all-reduce. Dropout is ON (train mode, p = 0.1) as in the
+reference. 1 clip = one (video, clip) unit = T frames through the CNN + n_ex sequences through BERT.
+
+JSON keys beyond the base contract:
+  value     clips/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e       same metric through the public API (ClipBert.forward on a batch dict) with HOST (pinned)
+            uint8 frames / ids / masks / labels copied H2D and the loss copied D2H every step
+  roofline  the tcgen05 GEMM kernel (all convs + linears, fwd/dgrad/wgrad): algorithmic FLOPs per step
+            / summed device time of its launches (CUDA events around every launch, on the launch stream,
+            in an instrumented pass right after the timed region), against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/clipbert_ref.py, a port: kind "port") on this host's cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+IMAGE_MEAN = (123.675, 116.28, 103.53)
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work (BASELINE.md §3 / SURVEY.md §8d): 1 MAC = 2 FLOP, conv / GEMM / attention contractions only
+# ------------------------------------------------------------------------------------------------
+def flops_per_clip(T, L, n_ex, num_labels=2, size=224, backward=True):
+    scale = (size / 224.0) ** 2
+    C, Cf = 4.550e9 * scale, 0.786e9 * scale
+    bert = 12 * (7077888 * L + 1536 * L * L)
+    head = 768 * 768 + 768 * 1536 + 1536 * num_labels
+    if backward:
+        return 2.0 * (T * (3 * C - 2 * Cf) + 3 * n_ex * (bert + head))
+    return 2.0 * (T * C + n_ex * (bert + head))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1464.0), hbm=d.get("hbm_gbs", 6489.9), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def make_host_batch(args, rank):
+    from oracle import synth   # shapes / value ranges of the synthetic inputs only
+    B, frames = args.batch, args.n_clips * args.n_frm
+    u8 = synth.synth_images(B, frames, size=args.size, seed=42 + rank, as_uint8=True)
+    ids, mask = synth.synth_text(B * args.n_ex, args.txt_len, seed=42 + rank)
+    g = torch.Generator().manual_seed(1000 + rank)
+    labels = torch.randint(0, 2, (B * args.n_ex,), generator=g)
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    return dict(visual_inputs=pin(u8), text_input_ids=pin(ids), text_input_mask=pin(mask), labels=pin(labels))
+
+
+def lse_loss(logits_per_clip, labels):
+    """Clip aggregation + loss of the reference loop (run_video_retrieval.py:404-422, pool_method 'lse')."""
+    lg = torch.stack(logits_per_clip).permute(1, 0, 2).contiguous()
+    out = torch.logsumexp(lg.view(lg.shape[0], -1), dim=-1, keepdim=True) - torch.logsumexp(lg, dim=1)
+    return torch.gather(out, -1, labels.view(-1, 1)).mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import clipbert_b200 as cb
+    from clipbert_b200 import ops
+    from util import make_cfg
+
+    torch.manual_seed(42)
+    cfg = make_cfg()                      # base_model.json + retrieval head (num_labels 2, CE)
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", transformer_cls=cb.ClipBertForVideoTextRetrieval)
+    from oracle import synth
+    model.load_state_dict(synth.cnn_state_dict(42), strict=False)     # randomised FrozenBN statistics (random-init weights)
+    model = model.to(dev).train()
+    model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
+
+    host = make_host_batch(args, rank)
+    B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
+    dbuf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def h2d():
+        for k in host:
+            dbuf[k].copy_(host[k], non_blocking=True)
+
+    def fwd_bwd():
+        vis = dbuf["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+        logits = []
+        for c in range(n_clips):
+            mb = dict(visual_inputs=vis[:, c], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
+                      labels=dbuf["labels"], n_examples_list=[n_ex] * B)
+            logits.append(model(mb)["logits"])
+        loss = lse_loss(logits, dbuf["labels"])
+        loss.backward()
+        loss_dev.copy_(loss.detach().reshape(1))
+
+    graph = None
+    captured_launches = 0
+
+    def step_device():
+        model.zero_grad()
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
+        if world > 1:
+            model.allreduce_grads()
+
+    def step_e2e():
+        h2d()
+        step_device()
+        loss_host.copy_(loss_dev, non_blocking=True)
+
+    h2d()
+    torch.cuda.synchronize()
+    # ---- optional whole-step CUDA graph (fwd + bwd of all clips): removes ~900 launch latencies ----
+    if args.graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    model.zero_grad()
+                    fwd_bwd()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            model.zero_grad()
+            lc0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                fwd_bwd()
+            captured_launches = ops.launch_count() - lc0
+            graph = g
+        except Exception as e:      # report, fall back to eager launches (still this repo's kernels)
+            if rank == 0:
+                print("[bench] CUDA graph capture failed (%s: %s); running eager" % (type(e).__name__, e), file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.15)
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, clocks
+
+    ms_dev, launches, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    if graph is not None:          # kernels replayed from the captured graph do not pass through the C-ABI counter
+        launches += captured_launches * args.steps
+
+    clips_per_step = B * n_clips * world
+    L = args.txt_len + (args.size // 32 // 2) ** 2
+    fl_clip = flops_per_clip(T, L, n_ex, 2, args.size)
+    peaks = load_peaks()
+    value = clips_per_step / (ms_dev / args.steps / 1e3)
+    e2e_value = clips_per_step / (ms_e2e / args.steps / 1e3)
+
+    # ---- instrumented pass: device time of every tcgen05 GEMM launch (events on the launch stream) ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        ev = []
+        ops.set_gemm_timing(ev)
+        for _ in range(2):
+            model.zero_grad()
+            fwd_bwd()
+        torch.cuda.synchronize()
+        ops.set_gemm_timing(None)
+        half = len(ev) // 2
+        gemm_ms = sum(a.elapsed_time(b) for a, b in ev[half:])
+        n_gemm = len(ev) - half
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.zero_grad()
+        torch.cuda.synchronize()
+        e0.record()
+        fwd_bwd()
+        e1.record()
+        torch.cuda.synchronize()
+        eager_ms = e0.elapsed_time(e1)
+        algo_tf = fl_clip * B * n_clips / 1e12
+        achieved = algo_tf / (gemm_ms / 1e3)
+        roof = dict(bound="tensor", kernel="cb::gemm_kernel<BN,MODE> (tcgen05, all convs + linears fwd/dgrad/wgrad)",
+                    achieved=round(achieved, 2), peak=peaks["tflops"], unit="TFLOP/s", frac=round(achieved / peaks["tflops"], 4),
+                    peak_source="%s bf16_tflops_sustained" % peaks["src"], traffic=None, launches_per_step=n_gemm,
+                    gemm_ms_per_step=round(gemm_ms, 3), eager_step_ms=round(eager_ms, 3),
+                    gemm_share_of_step=round(gemm_ms / eager_ms, 3),
+                    whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4))
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        out = dict(metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=round(value, 2), unit="clips/s", n_gpus=world,
+                   steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 4), higher_is_better=True,
+                   scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                   config=dict(workload="MSRVTT retrieval train step: %d videos/GPU x %d clips x %d frames %dx%d, %d-token text, n_ex=%d, "
+                               "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
+                               clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
+                               l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
+                               cuda_graph=graph is not None, gflop_per_clip=round(fl_clip / 1e9, 2)),
+                   e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
+                            h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4),
+                   gpu_launches=int(launches), gpu_launches_per_step=int(launches // args.steps), clocks=clocks, roofline=roof,
+                   cpu_baseline=cpu)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_step(sd, batch, n_clips, T, size):
+    from oracle import clipbert_ref as R
+    B = batch["visual_inputs"].shape[0]
+    vis = batch["visual_inputs"].view(B, n_clips, T, 3, size, size)
+    logits = []
+    for c in range(n_clips):
+        mb = dict(batch, visual_inputs=vis[:, c])
+        logits.append(R.clipbert_forward(mb, sd)["logits"])
+    loss = R.aggregate_clip_logits(logits, batch["labels"], "lse")
+    loss.backward()
+    return float(loss)
+
+
+def _cpu_setup(args, b):
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.full_state_dict(42)
+    for k, v in sd.items():
+        if k.endswith((".weight", ".bias")) and ".norm." not in k and not k.startswith(("cnn.feature.backbone.stem", "cnn.feature.backbone.res2")):
+            v.requires_grad_(True)
+    batch = synth.synth_batch(b, args.n_clips * args.n_frm, n_ex=args.n_ex, size=args.size, max_len=args.txt_len)
+    return sd, batch
+
+
+def cpu_baseline(args):
+    """Bounded sample (~10-30 s) of the same workload on the host cores: fp32 eager PyTorch, all threads."""
+    b = args.cpu_batch
+    sd, batch = _cpu_setup(args, b)
+    _cpu_step(sd, batch, args.n_clips, args.n_frm, args.size)          # warm-up
+    best = 1e30
+    for _ in range(2):
+        t0 = time.time()
+        _cpu_step(sd, batch, args.n_clips, args.n_frm, args.size)
+        best = min(best, time.time() - t0)
+    return dict(value=round(b * args.n_clips / best, 3), unit="clips/s", cores=os.cpu_count(), kind="port",
+                sample="%d videos x %d clips x %d frames fwd+bwd, fp32, best of 2 after 1 warm-up (%.2f s/step)" % (b, args.n_clips, args.n_frm, best))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    b = args.cpu_batch
+    sd, batch = _cpu_setup(args, b)
+    for _ in range(max(1, min(args.warmup, 1))):
+        _cpu_step(sd, batch, args.n_clips, args.n_frm, args.size)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.time()
+    for _ in range(steps):
+        _cpu_step(sd, batch, args.n_clips, args.n_frm, args.size)
+    dt = (time.time() - t0) / steps
+    val = round(b * args.n_clips / dt, 3)
+    L = args.txt_len + (args.size // 32 // 2) ** 2
+    out = dict(impl="reference", metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=val, unit="clips/s", n_gpus=args.gpus,
+               steps=steps, warmup=1, ms_per_step=round(dt * 1e3, 2), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+               data="synthetic",
+               config=dict(workload="MSRVTT retrieval train step (bounded CPU sample): %d videos x %d clips x %d frames %dx%d, %d-token text, n_ex=%d"
+                           % (b, args.n_clips, args.n_frm, args.size, args.size, args.txt_len, args.n_ex), seq_len=L,
+                           note="reference path = src/modeling/{modeling,transformers}.py + detectron2 R-50, restated in oracle/ (the Python "
+                                "reference and detectron2 cannot travel to / install on the GPU box)"),
+               cpu_baseline=dict(value=val, unit="clips/s", cores=os.cpu_count(), kind="port",
+                                 sample="%d videos/step, %d timed steps, fp32 eager PyTorch, %d threads" % (b, steps, os.cpu_count())),
+               e2e=dict(value=val, unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="videos per GPU")
+    ap.add_argument("--n_clips", type=int, default=2)
+    ap.add_argument("--n_frm", type=int, default=2)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--txt_len", type=int, default=32)
+    ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--cpu_batch", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

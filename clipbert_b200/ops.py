@@ -71,6 +71,14 @@ def launch_count():
 # tensor-core contraction
 # ------------------------------------------------------------------------------------------------
 _GEMM_PTR_FIELDS = ("a", "b", "scale", "shift", "residual", "aux", "out", "out2")
+_gemm_timing = None
+
+
+def set_gemm_timing(events):
+    """Profiling hook: when ``events`` is a list, every cb_gemm launch is bracketed by CUDA events
+    recorded on the launch stream and the (start, end) pair is appended to it. None disables."""
+    global _gemm_timing
+    _gemm_timing = events
 
 
 def gemm(**kw):
@@ -83,9 +91,15 @@ def gemm(**kw):
         if k in _GEMM_PTR_FIELDS:
             v = _p(v) if isinstance(v, torch.Tensor) else v
         setattr(d, k, v)
+    if _gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = L.lib().cb_gemm(ctypes.byref(d), _s())
     if rc != 0:
         raise RuntimeError("cb_gemm failed (%d): %s" % (rc, L.lib().cb_last_error().decode()))
+    if _gemm_timing is not None:
+        e1.record()
+        _gemm_timing.append((e0, e1))
 
 
 def wgrad_split(m, n, k, ntaps=1, block_n=128):
