@@ -1,11 +1,20 @@
 // tcgen05 tensor-core contraction for every dense op on the ClipBERT path (see cb_gemm in
-// include/clipbert_b200.h). One warp-specialised kernel, two operand modes:
+// include/clipbert_b200.h). One persistent, warp-specialised kernel, three operand modes:
 //   MODE 0 (TN)    : A [rows, K] and B [N, K] both K-major; optional 9-tap row-shifted K loop
-//                    (3x3 conv over a zero-bordered NHWC activation) ; fused epilogue.
+//                    (3x3 conv over a zero-bordered NHWC activation); fused epilogue.
+//   MODE 2 (NN)    : as TN but B [K, ntaps*N] is read MN-major (dgrad straight from the forward weight).
 //   MODE 1 (WGRAD) : dW = dY^T X with both operands read MN-major from the activation layout,
 //                    split over the pixel/token dimension, fp32 red.global accumulation.
-// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
-// (TMEM -> registers -> global). smem ring of STAGES x (A 128x64 | B BNx64) bf16 tiles, 128B swizzle.
+//
+// Structure (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0      TMA producer   : smem ring of STAGES x (A 128x64 | B BNx64) bf16 tiles, 128B swizzle
+//   warp 1      MMA issuer     : tcgen05.mma into one of TWO TMEM accumulator stages (2 x BN columns)
+//   warps 2..9  epilogue       : TMEM -> registers -> fused epilogue, overlapping the next tile's TMA + MMA
+//                                through the tmem_full / tmem_empty barrier pair. Two I/O paths:
+//       EPI 1 (bf16 out, no row re-map): residual / aux tiles are TMA-PREFETCHED two 64-column chunks
+//             ahead into swizzled smem, the output chunk is written to swizzled smem and leaves with a
+//             TMA store (bulk async group), so the memory-bound 1x1 convs keep >= 64 KB in flight per SM;
+//       EPI 0 (row re-map / fp32 / wgrad red.add): per-warp smem staging -> coalesced 128-byte accesses.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -13,7 +22,14 @@ namespace cb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
+constexpr int MAX_STAGES = 8;
+constexpr int CHUNK_BYTES = BM * 128;           // one 128-row x 64-column bf16 chunk (TMA epilogue path)
+constexpr int SMEM_LIMIT = 232448;              // 227 KB opt-in limit per CTA
+constexpr int STG_ROW = 144;                    // staging row pitch in bytes (128 + 16: conflict-free 16 B accesses)
+constexpr int STG_BYTES = 32 * STG_ROW;         // per epilogue warp
 
 struct GemmEpi {
   const float* scale;
@@ -37,63 +53,153 @@ struct GemmEpi {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 64) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages
 };
 
-__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-               "f"(d)
+// fused elementwise epilogue on 32 consecutive columns [nb, nb+32) of one output row
+__device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi, int nb, int N, int64_t orow,
+                                              const uint32_t* res16, const uint32_t* aux16, uint32_t* o2_16) {
+  if (nb >= N) return;
+  if (epi.scale) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (nb + j + 4 <= N) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.scale + nb + j));
+        f[j] *= s4.x; f[j + 1] *= s4.y; f[j + 2] *= s4.z; f[j + 3] *= s4.w;
+      }
+    }
+  }
+  if (epi.shift) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (nb + j + 4 <= N) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
+        f[j] += s4.x; f[j + 1] += s4.y; f[j + 2] += s4.z; f[j + 3] += s4.w;
+      }
+    }
+  }
+  if (epi.drop_thresh) {
+    const uint64_t base = static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= dropout_mult(epi.seed, base + j, epi.drop_thresh, epi.drop_inv_keep);
+  }
+  if (res16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 r2 = unpack_bf16x2(res16[j]);
+      f[2 * j] += r2.x;
+      f[2 * j + 1] += r2.y;
+    }
+  }
+  if (o2_16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o2_16[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+  }
+  if (epi.act == CB_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (epi.act == CB_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  } else if (epi.act == CB_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+  }
+  if (aux16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 a2 = unpack_bf16x2(aux16[j]);
+      if (epi.aux_mode == CB_AUX_RELU_MASK) {
+        f[2 * j] = a2.x > 0.0f ? f[2 * j] : 0.0f;
+        f[2 * j + 1] = a2.y > 0.0f ? f[2 * j + 1] : 0.0f;
+      } else if (epi.aux_mode == CB_AUX_GELU_GRAD) {
+        f[2 * j] *= gelu_erf_grad(a2.x);
+        f[2 * j + 1] *= gelu_erf_grad(a2.y);
+      } else if (epi.aux_mode == CB_AUX_TANH_GRAD) {
+        f[2 * j] *= (1.0f - a2.x * a2.x);
+        f[2 * j + 1] *= (1.0f - a2.y * a2.y);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 
+struct TileInfo {
+  int m0, n0, tap, it_begin, n_iters;
+};
+
+// tile index -> coordinates; n-tiles are fastest so that concurrently running CTAs share the A rows
 template <int BN, int MODE>
+__device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles_n, int K, int ntaps, int iters_per_split) {
+  TileInfo t;
+  const int nt = tile % tiles_n;
+  int r = tile / tiles_n;
+  const int mt = r % tiles_m;
+  r /= tiles_m;
+  t.m0 = mt * BM;
+  t.n0 = nt * BN;
+  const int kc = (K + BK - 1) / BK;
+  if (MODE == 1) {
+    t.tap = r % ntaps;
+    const int split = r / ntaps;
+    t.it_begin = split * iters_per_split;
+    t.n_iters = min(kc, t.it_begin + iters_per_split) - t.it_begin;
+  } else {
+    t.tap = 0;
+    t.it_begin = 0;
+    t.n_iters = ntaps * kc;
+  }
+  return t;
+}
+
+template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                int M, int N, int K, int ntaps, int tap_w, int tap_sign, int iters_per_split,
-                GemmEpi epi) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmX, int M, int N, int K, int ntaps, int tap_w, int tap_sign,
+                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int epi_bytes, GemmEpi epi) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* stg_base = smem + STAGES * Cfg::STAGE_BYTES;     // epilogue region (1024-byte aligned: stage sizes are multiples of 8 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + epi_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator stage ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator stage drained by the epilogue
+  uint64_t* rfull_bar = tempty_bar + 2;          // [2] residual chunk landed (EPI 1)
+  uint64_t* xfull_bar = rfull_bar + 2;           // [2] aux chunk landed (EPI 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-
-  // ---- per-CTA iteration space ----
-  int tap = 0, it_begin = 0, it_end = 0;
-  if (MODE == 0 || MODE == 2) {
-    const int kc = (K + BK - 1) / BK;
-    it_begin = 0;
-    it_end = ntaps * kc;
-  } else {
-    tap = blockIdx.z % ntaps;
-    const int split = blockIdx.z / ntaps;
-    const int total = (K + BK - 1) / BK;
-    it_begin = split * iters_per_split;
-    it_end = min(total, it_begin + iters_per_split);
-  }
-  const int n_iters = it_end - it_begin;  // may be <= 0 for a trailing empty split
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI == 1) {
+      tma_prefetch_desc(&tmC);
+      if (epi.residual) tma_prefetch_desc(&tmR);
+      if (epi.aux) tma_prefetch_desc(&tmX);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
+      mbar_init(&rfull_bar[s], 1);
+      mbar_init(&xfull_bar[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -101,56 +207,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int kc_per_tap = (K + BK - 1) / BK;
 
-  if (n_iters > 0) {
-    if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        const int kc_per_tap = (K + BK - 1) / BK;
-        for (int i = 0; i < n_iters; ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;        // smem ring position / phase, carried across tiles
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        for (int i = 0; i < t.n_iters; ++i) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          const int it = it_begin + i;
-          if (MODE == 0) {
-            const int t = it / kc_per_tap;
-            const int kc = it - t * kc_per_tap;
+          const int kit = t.it_begin + i;
+          if (MODE == 1) {
             int shift = 0;
-            if (ntaps == 9) shift = tap_sign * ((t / 3 - 1) * tap_w + (t % 3 - 1));
-            tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, m0 + shift);
-            tma_load_2d(sb, &tmB, &full_bar[s], t * K + kc * BK, n0);
-          } else if (MODE == 2) {
-            const int t = it / kc_per_tap;
-            const int kc = it - t * kc_per_tap;
-            int shift = 0;
-            if (ntaps == 9) shift = tap_sign * ((t / 3 - 1) * tap_w + (t % 3 - 1));
-            tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, m0 + shift);
+            if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
+            const int p = kit * BK;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], t.m0 + j * 64, p);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], t * N + n0 + j * 64, kc * BK);
+              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], t.n0 + j * 64, p + shift);
           } else {
+            const int tp = kit / kc_per_tap;
+            const int kc = kit - tp * kc_per_tap;
             int shift = 0;
-            if (ntaps == 9) shift = tap_sign * ((tap / 3 - 1) * tap_w + (tap % 3 - 1));
-            const int p = it * BK;
+            if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
+            tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, t.m0 + shift);
+            if (MODE == 0) {
+              tma_load_2d(sb, &tmB, &full_bar[s], tp * K + kc * BK, t.n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + j * 64, p);
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + j * 64, p + shift);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], tp * N + t.n0 + j * 64, kc * BK);
+            }
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == 1, MODE != 0);
-        for (int i = 0; i < n_iters; ++i) {
-          const int s = i % STAGES;
-          const uint32_t ph = (i / STAGES) & 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == 1, MODE != 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i = 0; i < t.n_iters; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -158,162 +271,311 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t ad, bd;
-            if (MODE == 0) {
-              ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-              bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
-            } else if (MODE == 2) {
-              ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-              bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
-            } else {
-              ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
-              bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
-            }
-            umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (MODE == 1) ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
+            else ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            if (MODE == 0) bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            else bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(accum_bar);  // accumulator complete
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
       }
-    } else {
-      // ===================== epilogue warps =====================
-      const int q = warp & 3;  // TMEM lane quarter this warp may access
-      const int m = m0 + q * 32 + lane;
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int grp = ew >> 2;          // two warps share each lane quarter and split the columns
+    int local = 0;
 
-      if (MODE == 1) {
-        const bool row_ok = m < M;
-        const float rs = (row_ok && epi.scale) ? epi.scale[m] : 1.0f;
-        float* orow = reinterpret_cast<float*>(epi.out) + static_cast<int64_t>(m) * epi.out_ld +
-                      static_cast<int64_t>(tap) * N;
+    if (EPI == 1) {
+      // ---------- TMA epilogue: rowmap NONE, bf16 output ----------
+      constexpr int CPT = BN / 64;                      // 64-column chunks per tile
+      uint8_t* cbuf = stg_base;                         // [2][128 x 128 B] output chunks
+      uint8_t* rbuf = cbuf + 2 * CHUNK_BYTES;           // [2] residual chunks (if any)
+      uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
+      const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
+      const bool elected = (ew == 0 && lane == 0);
+      const int row = q * 32 + lane;                    // row inside the 128-row tile
+      const int swz = row & 7;                          // 128B-swizzle XOR of this row
+      const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int total_chunks = my_tiles * CPT;
+      auto prefetch = [&](int g) {                      // elected thread: TMA-load residual / aux of chunk g
+        if (g >= total_chunks) return;
+        const int tile = blockIdx.x + (g / CPT) * gridDim.x;
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int b = g & 1, nc = t.n0 + (g % CPT) * 64;
+        if (has_res) {
+          mbar_expect_tx(&rfull_bar[b], CHUNK_BYTES);
+          tma_load_2d(rbuf + b * CHUNK_BYTES, &tmR, &rfull_bar[b], nc, t.m0);
+        }
+        if (has_aux) {
+          mbar_expect_tx(&xfull_bar[b], CHUNK_BYTES);
+          tma_load_2d(xbuf + b * CHUNK_BYTES, &tmX, &xfull_bar[b], nc, t.m0);
+        }
+      };
+      if (elected) {
+        prefetch(0);
+        prefetch(1);
+      }
+      int g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        const int64_t orow = t.m0 + row;
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < CPT; ++c, ++g) {
+          const int b = g & 1;
+          const uint32_t bph = (g >> 1) & 1;
+          const int nb = t.n0 + c * 64 + grp * 32;      // this thread's 32 columns
           uint32_t v[32];
           __syncwarp();
-          tmem_ld32(trow + c, v);
+          tmem_ld32(trow + c * 64 + grp * 32, v);
           tmem_ld_wait();
-          if (row_ok) {
+          if (c == CPT - 1) {                           // last TMEM read of this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          uint32_t res16[16], aux16[16];
+          if (has_res) {
+            mbar_wait(&rfull_bar[b], bph);
+            const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + c + j;
-              if (n + 4 <= N) {
-                red_add_f32x4(orow + n, __uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
-                              __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rr + (((grp * 4 + j) ^ swz) << 4));
+              res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
             }
           }
-        }
-      } else {
-        bool row_ok = m < M;
-        int64_t orow = m;
-        if (epi.rowmap == CB_ROWMAP_PAD) {
-          const int hw = epi.H * epi.W;
-          const int img = m / hw;
-          const int r = m - img * hw;
-          const int y = r / epi.W, x = r - y * epi.W;
-          orow = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
-        } else if (epi.rowmap == CB_ROWMAP_UNPAD) {
-          const int wp = epi.W + 2, hp = epi.H + 2;
-          const int img = m / (hp * wp);
-          const int r = m - img * (hp * wp);
-          const int y = r / wp, x = r - y * wp;
-          row_ok = row_ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
-          orow = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
-        }
-        const __nv_bfloat16* res_row = epi.residual ? epi.residual + static_cast<int64_t>(m) * epi.res_ld : nullptr;
-        const __nv_bfloat16* aux_row = epi.aux ? epi.aux + static_cast<int64_t>(m) * epi.aux_ld : nullptr;
-        __nv_bfloat16* out2_row = epi.out2 ? epi.out2 + orow * epi.out2_ld : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
+          if (has_aux) {
+            mbar_wait(&xfull_bar[b], bph);
+            const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(xr + (((grp * 4 + j) ^ swz) << 4));
+              aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
+            }
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          epilogue_math(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, nullptr);
+          uint8_t* cr = cbuf + b * CHUNK_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(cr + (((grp * 4 + j) ^ swz) << 4)) =
+                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
+          if (elected) tma_store_wait_read<0>();        // the previous chunk's store has finished reading cbuf[b^1]
           __syncwarp();
-          tmem_ld32(trow + c, v);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-#pragma unroll
-          for (int g = 0; g < 32; g += 8) {
-            const int n = n0 + c + g;
-            if (n + 8 > N) continue;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g + j]);
-            if (epi.scale) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.scale + n));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.scale + n + 4));
-              f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-              f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-            }
-            if (epi.shift) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(epi.shift + n));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(epi.shift + n + 4));
-              f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w;
-              f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
-            }
-            if (epi.drop_thresh) {
-              const uint64_t base = static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + n;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                f[j] *= dropout_mult(epi.seed, base + j, epi.drop_thresh, epi.drop_inv_keep);
-            }
-            if (res_row) {
-              const uint4 r = *reinterpret_cast<const uint4*>(res_row + n);
-              const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), cc = unpack_bf16x2(r.z),
-                           d = unpack_bf16x2(r.w);
-              f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
-              f[4] += cc.x; f[5] += cc.y; f[6] += d.x; f[7] += d.y;
-            }
-            if (out2_row) {
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(out2_row + n) = o;
-            }
-            if (epi.act == CB_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-            } else if (epi.act == CB_ACT_GELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-            } else if (epi.act == CB_ACT_TANH) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
-            }
-            if (aux_row) {
-              const uint4 r = *reinterpret_cast<const uint4*>(aux_row + n);
-              float a[8];
-              float2 t;
-              t = unpack_bf16x2(r.x); a[0] = t.x; a[1] = t.y;
-              t = unpack_bf16x2(r.y); a[2] = t.x; a[3] = t.y;
-              t = unpack_bf16x2(r.z); a[4] = t.x; a[5] = t.y;
-              t = unpack_bf16x2(r.w); a[6] = t.x; a[7] = t.y;
-              if (epi.aux_mode == CB_AUX_RELU_MASK) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = a[j] > 0.0f ? f[j] : 0.0f;
-              } else if (epi.aux_mode == CB_AUX_GELU_GRAD) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gelu_erf_grad(a[j]);
-              } else if (epi.aux_mode == CB_AUX_TANH_GRAD) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= (1.0f - a[j] * a[j]);
-              }
-            }
-            if (epi.out_fp32) {
-              float* o = reinterpret_cast<float*>(epi.out) + orow * epi.out_ld + n;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orow * epi.out_ld + n) = o;
-            }
+          named_bar_sync(1, EPI_THREADS);
+          if (elected) {
+            tma_store_2d(&tmC, cbuf + b * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+            tma_store_commit();
+            prefetch(g + 2);                            // rbuf[b] / xbuf[b] were fully consumed before the barrier
           }
         }
       }
-      tc_fence_before();
+      if (elected) tma_store_wait_all<0>();
+    } else {
+      // ---------- staged epilogue: row re-map, fp32 output, pre-activation stash, wgrad accumulation ----------
+      uint8_t* stg = stg_base + ew * STG_BYTES;
+      uint8_t* my_row = stg + lane * STG_ROW;       // this thread's own row in the staging tile
+      const int srow = lane >> 3;                   // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
+      const int sseg = lane & 7;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        const int m = t.m0 + q * 32 + lane;
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        bool released = false;
+
+        if (MODE == 1) {
+          const bool row_ok = m < M;
+          const float rs = (row_ok && epi.scale) ? epi.scale[m] : 1.0f;
+          float* obase = reinterpret_cast<float*>(epi.out) + static_cast<int64_t>(t.tap) * N;
+          constexpr int NCH = BN / 32;
+#pragma unroll 1
+          for (int cc = grp; cc < NCH; cc += 2) {
+            const int c = cc * 32;
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(trow + c, v);
+            tmem_ld_wait();
+            if (cc + 2 >= NCH) {  // last TMEM read of this warp for this tile
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+              released = true;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(my_row + j * 4) = make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
+                                                                        __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = j * 4 + srow;
+              const int mm = t.m0 + q * 32 + r;
+              const int n = t.n0 + c + sseg * 4;
+              if (mm < M && n + 4 <= N)
+                red_add_f32x4(obase + static_cast<int64_t>(mm) * epi.out_ld + n, *reinterpret_cast<const float4*>(stg + r * STG_ROW + sseg * 16));
+            }
+          }
+        } else {
+          bool row_ok = m < M;
+          int64_t orow = m;
+          if (epi.rowmap == CB_ROWMAP_PAD) {
+            const int hw = epi.H * epi.W;
+            const int img = m / hw;
+            const int r = m - img * hw;
+            const int y = r / epi.W, x = r - y * epi.W;
+            orow = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
+          } else if (epi.rowmap == CB_ROWMAP_UNPAD) {
+            const int wp = epi.W + 2, hp = epi.H + 2;
+            const int img = m / (hp * wp);
+            const int r = m - img * (hp * wp);
+            const int y = r / wp, x = r - y * wp;
+            row_ok = row_ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
+            orow = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
+          }
+          constexpr int NCH = BN / 64;
+#pragma unroll 1
+          for (int cc = grp; cc < NCH; cc += 2) {
+            const int c = cc * 64;
+            const int ncol = t.n0 + c;      // first column of this 64-wide chunk
+            uint32_t res[32], axv[32];      // packed bf16 pairs of this thread's row (64 columns)
+            // ---- coalesced loads of the residual / aux blocks (rows in A-row space) through the staging tile ----
+            if (epi.residual) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + srow;
+                const int mm = t.m0 + q * 32 + r;
+                const int n = ncol + sseg * 8;
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (mm < M && n + 8 <= N) u = *reinterpret_cast<const uint4*>(epi.residual + static_cast<int64_t>(mm) * epi.res_ld + n);
+                *reinterpret_cast<uint4*>(stg + r * STG_ROW + sseg * 16) = u;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(my_row + j * 16);
+                res[4 * j] = u.x; res[4 * j + 1] = u.y; res[4 * j + 2] = u.z; res[4 * j + 3] = u.w;
+              }
+            }
+            if (epi.aux) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + srow;
+                const int mm = t.m0 + q * 32 + r;
+                const int n = ncol + sseg * 8;
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (mm < M && n + 8 <= N) u = *reinterpret_cast<const uint4*>(epi.aux + static_cast<int64_t>(mm) * epi.aux_ld + n);
+                *reinterpret_cast<uint4*>(stg + r * STG_ROW + sseg * 16) = u;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(my_row + j * 16);
+                axv[4 * j] = u.x; axv[4 * j + 1] = u.y; axv[4 * j + 2] = u.z; axv[4 * j + 3] = u.w;
+              }
+            }
+            uint32_t o2[32];                // packed pre-activation (out2), only when requested
+            uint32_t ob[32];                // packed bf16 output (bf16 path)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              __syncwarp();
+              tmem_ld32(trow + c + h * 32, v);
+              tmem_ld_wait();
+              if (cc + 2 >= NCH && h == 1) {  // last TMEM read of this warp for this tile
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                released = true;
+              }
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              const int nb = ncol + h * 32;
+              epilogue_math(f, epi, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
+                            epi.out2 ? o2 + h * 16 : nullptr);
+              if (epi.out_fp32) {
+                // fp32 output: stage 32 columns (128 B per row) and store coalesced right away
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(my_row + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int r = j * 4 + srow;
+                  const int64_t orr = __shfl_sync(0xffffffffu, orow, r);
+                  const int okr = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), r);
+                  const int n = nb + sseg * 4;
+                  if (okr && n + 4 <= N)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(epi.out) + orr * epi.out_ld + n) =
+                        *reinterpret_cast<const float4*>(stg + r * STG_ROW + sseg * 16);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ob[h * 16 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              }
+            }
+            // ---- coalesced bf16 stores: own row -> staging tile -> 4 rows x 128 B per warp instruction ----
+            if (epi.out2) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + j * 16) = make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + srow;
+                const int64_t orr = __shfl_sync(0xffffffffu, orow, r);
+                const int okr = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), r);
+                const int n = ncol + sseg * 8;
+                if (okr && n + 8 <= N)
+                  *reinterpret_cast<uint4*>(epi.out2 + orr * epi.out2_ld + n) = *reinterpret_cast<const uint4*>(stg + r * STG_ROW + sseg * 16);
+              }
+            }
+            if (!epi.out_fp32) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + j * 16) = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + srow;
+                const int64_t orr = __shfl_sync(0xffffffffu, orow, r);
+                const int okr = __shfl_sync(0xffffffffu, static_cast<int>(row_ok), r);
+                const int n = ncol + sseg * 8;
+                if (okr && n + 8 <= N)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orr * epi.out_ld + n) =
+                      *reinterpret_cast<const uint4*>(stg + r * STG_ROW + sseg * 16);
+              }
+            }
+          }
+        }
+        if (!released) {   // this warp had no column chunk in this tile (narrow BN): still hand the stage back, in order
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+      }
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -321,44 +583,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
-template <int BN, int MODE>
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int MODE, int EPI>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE>;
+  auto kern = gemm_kernel<BN, MODE, EPI>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(smem=%d): %s", SMEM_LIMIT, cudaGetErrorString(e));
       return CB_ERR_CUDA;
     }
     attr_set = true;
   }
-  const CUtensorMap *ta, *tb;
-  dim3 grid;
+  const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr;
   int iters_per_split = 0;
+  const int tiles_m = ceil_div(d.m, BM), tiles_n = ceil_div(d.n, BN);
+  int total = tiles_m * tiles_n;
+  int kiters;
   if (MODE == 0) {
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
     tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN);
-    grid = dim3(ceil_div(d.n, BN), ceil_div(d.m, BM), 1);
+    kiters = ceil_div(d.k, BK) * d.ntaps;
   } else if (MODE == 2) {
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
     tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
-    grid = dim3(ceil_div(d.n, BN), ceil_div(d.m, BM), 1);
+    kiters = ceil_div(d.k, BK) * d.ntaps;
   } else {
     ta = get_tmap_2d(d.a, d.m, d.a_rows, d.a_ld, 64, BK);
     tb = get_tmap_2d(d.b, d.n, d.b_rows, d.b_ld, 64, BK);
-    const int total = ceil_div(d.k, BK);
+    const int kc = ceil_div(d.k, BK);
     int splits = d.split_k < 1 ? 1 : d.split_k;
-    if (splits > total) splits = total;
-    iters_per_split = ceil_div(total, splits);
-    splits = ceil_div(total, iters_per_split);
-    grid = dim3(ceil_div(d.n, BN), ceil_div(d.m, BM), splits * d.ntaps);
+    if (splits > kc) splits = kc;
+    iters_per_split = ceil_div(kc, splits);
+    splits = ceil_div(kc, iters_per_split);   // every split is non-empty
+    total *= splits * d.ntaps;
+    kiters = iters_per_split;
   }
   if (!ta || !tb) return CB_ERR_CUDA;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, d.m, d.n, d.k, d.ntaps, d.tap_w,
-                                                         d.tap_sign, iters_per_split, epi);
+  int epi_bytes;
+  if (EPI == 1) {
+    tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
+    if (d.residual) tr = get_tmap_2d(d.residual, d.n, d.m, d.res_ld, 64, BM);
+    if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
+    if (!tc || (d.residual && !tr) || (d.aux && !tx)) return CB_ERR_CUDA;
+    epi_bytes = 2 * CHUNK_BYTES * (1 + (d.residual ? 1 : 0) + (d.aux ? 1 : 0));
+  } else {
+    epi_bytes = EPI_WARPS * STG_BYTES;
+    epi_bytes = (epi_bytes + 1023) & ~1023;
+  }
+  if (!tc) tc = ta;   // unused placeholders (a __grid_constant__ parameter must still be a valid object)
+  if (!tr) tr = ta;
+  if (!tx) tx = ta;
+  int stages = (SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - epi_bytes) / Cfg::STAGE_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > kiters + 1 && kiters + 1 >= 2) stages = kiters + 1 > 2 ? kiters + 1 : 2;   // no point in a ring deeper than the K loop
+  if (stages < 2) {
+    set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B)", BN, epi_bytes);
+    return CB_ERR_INVALID;
+  }
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int smem_bytes = stages * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+                                                    iters_per_split, tiles_m, tiles_n, total, stages, epi_bytes, epi);
   return check_launch("cb_gemm");
+}
+
+// tile width: widest tile that still gives every SM work; small problems prefer more, narrower tiles
+static int choose_bn(int m, int n, int mode) {
+  const int64_t mt = ceil_div(m, BM);
+  const int sms = sm_count();
+  if (mode == CB_GEMM_WGRAD) return n >= 128 ? 128 : 64;
+  if (n >= 256 && mt * ceil_div(n, 256) >= sms) return 256;
+  if (n >= 128 && mt * ceil_div(n, 128) >= sms) return 128;
+  return 64;
 }
 
 }  // namespace cb
@@ -410,32 +720,34 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(!d.residual || d.res_ld % 8 == 0, "cb_gemm(TN): res_ld must be a multiple of 8");
     CB_REQUIRE(!d.aux || d.aux_ld % 8 == 0, "cb_gemm(TN): aux_ld must be a multiple of 8");
     CB_REQUIRE(!d.out2 || d.out2_ld % 8 == 0, "cb_gemm(TN): out2_ld must be a multiple of 8");
+    CB_REQUIRE(!(d.out2 && d.out_fp32), "cb_gemm(TN): out2 requires a bf16 primary output");
     CB_REQUIRE(d.rowmap == CB_ROWMAP_NONE || (d.map_h > 0 && d.map_w > 0), "cb_gemm: rowmap needs map_h/map_w");
     CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: 9-tap mode needs tap_w = W + 2");
-    int bn = d.block_n;
-    if (bn == 0) {
-      // fill the 148 SMs: prefer the widest tile that still yields >= ~1 wave of CTAs
-      const int64_t mt = ceil_div(d.m, BM);
-      if (d.n >= 256 && mt * ceil_div(d.n, 256) >= 148) bn = 256;
-      else if (d.n >= 128 && mt * ceil_div(d.n, 128) >= 120) bn = 128;
-      else bn = (d.n >= 128 && mt * ceil_div(d.n, 64) > 2 * 296) ? 128 : 64;
-    }
+    const int bn = d.block_n ? d.block_n : choose_bn(d.m, d.n, d.mode);
+    // TMA epilogue whenever the output is a plain bf16 matrix (no row re-map, no second output)
+    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && !d.out2 && d.reserved == 0 &&
+                         (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+                         (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
+                         (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
+#define CB_DISPATCH(BN_)                                                                                             \
+  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1>(d, epi, stream) : launch_gemm<BN_, 2, 0>(d, epi, stream))         \
+            : (tma_epi ? launch_gemm<BN_, 0, 1>(d, epi, stream) : launch_gemm<BN_, 0, 0>(d, epi, stream))
     switch (bn) {
-      case 64: return nn ? launch_gemm<64, 2>(d, epi, stream) : launch_gemm<64, 0>(d, epi, stream);
-      case 128: return nn ? launch_gemm<128, 2>(d, epi, stream) : launch_gemm<128, 0>(d, epi, stream);
-      case 256: return nn ? launch_gemm<256, 2>(d, epi, stream) : launch_gemm<256, 0>(d, epi, stream);
+      case 64: CB_DISPATCH(64);
+      case 128: CB_DISPATCH(128);
+      case 256: CB_DISPATCH(256);
       default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
     }
+#undef CB_DISPATCH
   } else {
     CB_REQUIRE(d.out_fp32 == 1, "cb_gemm(WGRAD): output must be fp32");
     CB_REQUIRE(d.m % 8 == 0 && d.n % 8 == 0, "cb_gemm(WGRAD): m, n must be multiples of 8 (got %d, %d)", d.m, d.n);
     CB_REQUIRE(d.out_ld % 4 == 0, "cb_gemm(WGRAD): out_ld must be a multiple of 4");
     CB_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "cb_gemm(WGRAD): out must be 16-byte aligned");
-    int bn = d.block_n;
-    if (bn == 0) bn = (d.n >= 128) ? 128 : 64;
+    const int bn = d.block_n ? d.block_n : choose_bn(d.m, d.n, d.mode);
     switch (bn) {
-      case 64: return launch_gemm<64, 1>(d, epi, stream);
-      case 128: return launch_gemm<128, 1>(d, epi, stream);
+      case 64: return launch_gemm<64, 1, 0>(d, epi, stream);
+      case 128: return launch_gemm<128, 1, 0>(d, epi, stream);
       default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64 or 128 (got %d)", bn);
     }
   }

@@ -57,10 +57,26 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+_op_timing = None
+
+
+def set_op_timing(events):
+    """Profiling hook: when ``events`` is a list, EVERY kernel launch made through this module is bracketed by
+    CUDA events on the launch stream and (label, start, end) is appended. None disables."""
+    global _op_timing
+    _op_timing = events
+
+
 def _call(name, *args):
+    if _op_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _fn(name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, L.lib().cb_last_error().decode()))
+    if _op_timing is not None:
+        e1.record()
+        _op_timing.append((name, e0, e1))
 
 
 def launch_count():
@@ -91,15 +107,19 @@ def gemm(**kw):
         if k in _GEMM_PTR_FIELDS:
             v = _p(v) if isinstance(v, torch.Tensor) else v
         setattr(d, k, v)
-    if _gemm_timing is not None:
+    timing = _gemm_timing is not None or _op_timing is not None
+    if timing:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = L.lib().cb_gemm(ctypes.byref(d), _s())
     if rc != 0:
         raise RuntimeError("cb_gemm failed (%d): %s" % (rc, L.lib().cb_last_error().decode()))
-    if _gemm_timing is not None:
+    if timing:
         e1.record()
-        _gemm_timing.append((e0, e1))
+        if _gemm_timing is not None:
+            _gemm_timing.append((e0, e1))
+        if _op_timing is not None:
+            _op_timing.append(("gemm mode=%d m=%d n=%d k=%d taps=%d" % (d.mode, d.m, d.n, d.k, d.ntaps), e0, e1))
 
 
 def wgrad_split(m, n, k, ntaps=1, block_n=128):

@@ -109,7 +109,7 @@ typedef struct cb_gemm_desc {
   float dropout_p;
   uint64_t dropout_seed;
   int32_t block_n;  /* 0 = let the library choose (64 / 128 / 256) */
-  int32_t reserved;
+  int32_t reserved; /* 1 = force the staged (non-TMA) epilogue; used by tests to cover both paths */
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

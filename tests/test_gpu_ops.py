@@ -43,15 +43,18 @@ def test_gemm_nn_dgrad(cuda, shape):
     assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
 
 
-def test_gemm_epilogues(cuda):
+@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("shape", [(500, 384, 256), (20000, 512, 128), (3000, 64, 64)])
+def test_gemm_epilogues(cuda, staged, shape):
+    """Both epilogue I/O paths (TMA-prefetched / TMA-stored vs. per-warp staged), several tiles per persistent CTA."""
     ops = _ops()
-    M, N, K = 500, 384, 256
+    M, N, K = shape
     g = torch.Generator().manual_seed(3)
     A, B, R, AUX = _rnd(g, M, K), _rnd(g, N, K, scale=0.1), _rnd(g, M, N), _rnd(g, M, N)
     scale = (torch.rand(N, generator=g) + 0.5).to(cuda)
     shift = torch.randn(N, generator=g).to(cuda)
     acc = A.float() @ B.float().t()
-    base = dict(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out_ld=N)
+    base = dict(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out_ld=N, reserved=staged)
     C, C2 = torch.zeros(M, N, device=cuda, dtype=torch.bfloat16), torch.zeros(M, N, device=cuda, dtype=torch.bfloat16)
     ops.gemm(**base, scale=scale, shift=shift, residual=R, res_ld=N, act=ops.ACT_RELU, out=C, out2=C2, out2_ld=N)
     pre = acc * scale + shift + R.float()
@@ -65,6 +68,17 @@ def test_gemm_epilogues(cuda):
     for mode, fac in [(ops.AUX_RELU_MASK, (a > 0).float()), (ops.AUX_GELU_GRAD, gelu_grad), (ops.AUX_TANH_GRAD, 1 - a * a)]:
         ops.gemm(**base, residual=R, res_ld=N, aux=AUX, aux_ld=N, aux_mode=mode, out=C)
         assert relerr(C, (acc + R.float()) * fac) < TOL_BF16_OP
+    # plain bf16 output, aux only, dropout + residual, every tile width
+    for bn in (64, 128, 256):
+        ops.gemm(**base, out=C, block_n=bn)
+        assert relerr(C, acc) < TOL_BF16_OP
+        ops.gemm(**base, aux=AUX, aux_ld=N, aux_mode=ops.AUX_RELU_MASK, out=C, block_n=bn)
+        assert relerr(C, acc * (a > 0)) < TOL_BF16_OP
+    ops.gemm(**base, shift=shift, residual=R, res_ld=N, dropout_p=0.1, dropout_seed=5, out=C)
+    ones = torch.ones(M, N, device=cuda, dtype=torch.bfloat16)
+    msk = torch.empty_like(ones)
+    ops.dropout(ones, msk, 0.1, 5)
+    assert relerr(C, (acc + shift) * msk.float() + R.float()) < TOL_BF16_OP
 
 
 @pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64)])

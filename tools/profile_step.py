@@ -1,0 +1,89 @@
+"""Per-kernel device-time breakdown of one training step (eager launches, CUDA events around every launch).
+Writes gpurun_out/step_breakdown.txt. Usage: python tools/profile_step.py [--batch 32 --n_clips 2 ...]"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--n_clips", type=int, default=2)
+    ap.add_argument("--n_frm", type=int, default=2)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--txt_len", type=int, default=32)
+    ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--out", default="gpurun_out/step_breakdown.txt")
+    args = ap.parse_args()
+    import clipbert_b200 as cb
+    from clipbert_b200 import ops
+    from oracle import synth
+    from util import make_cfg
+    dev = torch.device("cuda:0")
+    torch.manual_seed(42)
+    model = cb.ClipBert(make_cfg(), detectron2_model_cfg="x")
+    model.load_state_dict(synth.cnn_state_dict(42), strict=False)
+    model = model.to(dev).train()
+    model.cnn.pixel_mean = bench.IMAGE_MEAN
+    host = bench.make_host_batch(args, 0)
+    d = {k: v.to(dev) for k, v in host.items()}
+    B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
+
+    def step():
+        model.zero_grad()
+        vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+        logits = []
+        for c in range(n_clips):
+            mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
+                      labels=d["labels"], n_examples_list=[n_ex] * B)
+            logits.append(model(mb)["logits"])
+        bench.lse_loss(logits, d["labels"]).backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ev = []
+    ops.set_op_timing(ev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize()
+    ops.set_op_timing(None)
+    total = e0.elapsed_time(e1)
+    agg = defaultdict(lambda: [0.0, 0])
+    for label, a, b in ev:
+        agg[label][0] += a.elapsed_time(b)
+        agg[label][1] += 1
+    ksum = sum(v[0] for v in agg.values())
+    lines = ["step %.3f ms (eager, with event overhead); sum of kernel times %.3f ms; %d launches" % (total, ksum, len(ev))]
+    fam = defaultdict(float)
+    for label, (ms, cnt) in agg.items():
+        fam[label.split(" ")[0] + (" " + label.split(" ")[1] if label.startswith("gemm") else "")] += ms
+    lines.append("-- by family")
+    for k, v in sorted(fam.items(), key=lambda kv: -kv[1]):
+        lines.append("  %-28s %8.3f ms  %5.1f %%" % (k, v, 100 * v / ksum))
+    lines.append("-- by kernel/shape (total ms, count, avg us, TFLOP/s for gemm)")
+    for label, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        tf = ""
+        if label.startswith("gemm"):
+            f = dict(kv.split("=") for kv in label.split(" ")[1:])
+            m, n, k, taps, mode = int(f["m"]), int(f["n"]), int(f["k"]), int(f["taps"]), int(f["mode"])
+            fl = 2.0 * m * n * k * taps
+            tf = "%7.1f TF/s" % (fl * cnt / (ms / 1e3) / 1e12)
+        lines.append("  %-46s %8.3f ms x%-4d %8.1f us %s" % (label, ms, cnt, 1e3 * ms / cnt, tf))
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    open(args.out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:60]))
+
+
+if __name__ == "__main__":
+    main()
