@@ -632,8 +632,12 @@ int cb_colsum(const void* x, int64_t ld, float* out, int m, int n, void* stream)
   CB_REQUIRE(x && out && m > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "cb_colsum: bad arguments (n, ld must be multiples of 8)");
   const int groups = n / 8;
   const int threads = groups < 128 ? ((groups + 31) / 32) * 32 : 128;
-  const int rows_per_block = 64;
-  dim3 grid(ceil_div(groups, threads), ceil_div(m, rows_per_block));
+  // enough row blocks to cover the 148 SMs a few times over; each thread keeps 8 column sums in registers
+  const int col_blocks = ceil_div(groups, threads);
+  int rows_per_block = ceil_div(static_cast<int64_t>(m) * col_blocks, 148 * 4);
+  if (rows_per_block < 8) rows_per_block = 8;
+  if (rows_per_block > 64) rows_per_block = 64;
+  dim3 grid(col_blocks, ceil_div(m, rows_per_block));
   colsum_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, out, m, n,
                                                                           rows_per_block);
   return check_launch("cb_colsum");

@@ -49,12 +49,17 @@ struct GemmEpi {
   uint32_t drop_thresh;
   float drop_inv_keep;
   uint64_t seed;
+  long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
 };
 
-template <int BN>
+__device__ __forceinline__ void dbg_stamp(const GemmEpi& epi, int slot) {
+  if (epi.dbg && blockIdx.x == 0) epi.dbg[slot] = clock64();
+}
+
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // a CTA pair (CG = 2) splits the B tile: each CTA stages N/2 rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages
@@ -134,19 +139,21 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
 }
 
 struct TileInfo {
-  int m0, n0, tap, it_begin, n_iters;
+  int m0, n0, nb0, tap, it_begin, n_iters;
 };
 
-// tile index -> coordinates; n-tiles are fastest so that concurrently running CTAs share the A rows
-template <int BN, int MODE>
-__device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles_n, int K, int ntaps, int iters_per_split) {
+// tile index -> coordinates; n-tiles are fastest so that concurrently running CTAs share the A rows.
+// With CG = 2 a "tile" is the 256 x BN tile of a CTA pair: m0 is THIS CTA's 128-row half, nb0 its half of the B rows.
+template <int BN, int MODE, int CG>
+__device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles_n, int K, int ntaps, int iters_per_split, int rank) {
   TileInfo t;
   const int nt = tile % tiles_n;
   int r = tile / tiles_n;
   const int mt = r % tiles_m;
   r /= tiles_m;
-  t.m0 = mt * BM;
+  t.m0 = mt * (BM * CG) + rank * BM;
   t.n0 = nt * BN;
+  t.nb0 = t.n0 + rank * (BN / CG);
   const int kc = (K + BK - 1) / BK;
   if (MODE == 1) {
     t.tap = r % ntaps;
@@ -161,13 +168,13 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles
   return t;
 }
 
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, int M, int N, int K, int ntaps, int tap_w, int tap_sign,
-                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int epi_bytes, GemmEpi epi) {
-  using Cfg = GemmCfg<BN>;
+                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int epi_bytes, int n_cbuf, GemmEpi epi) {
+  using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stg_base = smem + STAGES * Cfg::STAGE_BYTES;     // epilogue region (1024-byte aligned: stage sizes are multiples of 8 KB)
@@ -181,6 +188,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader of the CTA pair
+  const int unit = blockIdx.x / CG;                                     // persistent work unit (CTA or CTA pair)
+  const int n_units = gridDim.x / CG;
+  if (threadIdx.x == 0) dbg_stamp(epi, 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -191,73 +202,85 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (epi.aux) tma_prefetch_desc(&tmX);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);            // one arrive.expect_tx per CTA of the pair (only the leader's copy is used)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS);
+      mbar_init(&tempty_bar[s], EPI_WARPS * CG);
       mbar_init(&rfull_bar[s], 1);
       mbar_init(&xfull_bar[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kc_per_tap = (K + BK - 1) / BK;
+  if (threadIdx.x == 0) dbg_stamp(epi, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;        // smem ring position / phase, carried across tiles
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         for (int i = 0; i < t.n_iters; ++i) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          // both CTAs of a pair credit their bytes to the LEADER's full barrier
+          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[s]), 0) : 0u;
+          if (CG == 2) mbar_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
+          else mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (CG == 2) tma_load_2d_2sm(dst, map, fb, c0, c1);
+            else tma_load_2d(dst, map, &full_bar[s], c0, c1);
+          };
           const int kit = t.it_begin + i;
           if (MODE == 1) {
             int shift = 0;
             if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
             const int p = kit * BK;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], t.m0 + j * 64, p);
+            for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmA, t.m0 + j * 64, p);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], t.n0 + j * 64, p + shift);
+            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * (BK * 128), &tmB, t.nb0 + j * 64, p + shift);
           } else {
             const int tp = kit / kc_per_tap;
             const int kc = kit - tp * kc_per_tap;
             int shift = 0;
             if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
-            tma_load_2d(sa, &tmA, &full_bar[s], kc * BK, t.m0 + shift);
+            load(sa, &tmA, kc * BK, t.m0 + shift);
             if (MODE == 0) {
-              tma_load_2d(sb, &tmB, &full_bar[s], tp * K + kc * BK, t.n0);
+              load(sb, &tmB, tp * K + kc * BK, t.nb0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], tp * N + t.n0 + j * 64, kc * BK);
+              for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * (BK * 128), &tmB, tp * N + t.nb0 + j * 64, kc * BK);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (i == 0 && tile == unit) dbg_stamp(epi, 2);
         }
       }
+      dbg_stamp(epi, 3);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == 1, MODE != 0);
+    if (lane == 0 && rank == 0) {              // only the leader CTA of a pair issues MMAs
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, MODE == 1, MODE != 0);
       int s = 0;
       uint32_t ph = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
@@ -266,6 +289,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int i = 0; i < t.n_iters; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (i == 0 && local == 0) dbg_stamp(epi, 4);
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -275,16 +299,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             else ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
             if (MODE == 0) bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
             else bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+          if (CG == 2) umma_commit_2sm(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (CG == 2) umma_commit_2sm(&tfull_bar[acc], 3);   // accumulator complete (both halves)
+        else umma_commit(&tfull_bar[acc]);
+        if (local == 0) dbg_stamp(epi, 5);
       }
+      dbg_stamp(epi, 6);
     }
   } else {
     // ===================== epilogue warps =====================
+    auto release_acc = [&](uint64_t* bar) {   // hand the accumulator stage back to the (leader's) MMA warp
+      if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+      else mbar_arrive(bar);
+    };
     const int ew = warp - 2;          // 0..7
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = ew >> 2;          // two warps share each lane quarter and split the columns
@@ -293,19 +327,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (EPI == 1) {
       // ---------- TMA epilogue: rowmap NONE, bf16 output ----------
       constexpr int CPT = BN / 64;                      // 64-column chunks per tile
-      uint8_t* cbuf = stg_base;                         // [2][128 x 128 B] output chunks
-      uint8_t* rbuf = cbuf + 2 * CHUNK_BYTES;           // [2] residual chunks (if any)
+      uint8_t* cbuf = stg_base;                         // [n_cbuf][128 x 128 B] output chunks (n_cbuf = 2 or 4)
+      uint8_t* rbuf = cbuf + n_cbuf * CHUNK_BYTES;      // [2] residual chunks (if any)
       uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
       const bool elected = (ew == 0 && lane == 0);
       const int row = q * 32 + lane;                    // row inside the 128-row tile
       const int swz = row & 7;                          // 128B-swizzle XOR of this row
-      const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int my_tiles = (total_tiles - unit + n_units - 1) / n_units;
       const int total_chunks = my_tiles * CPT;
       auto prefetch = [&](int g) {                      // elected thread: TMA-load residual / aux of chunk g
         if (g >= total_chunks) return;
-        const int tile = blockIdx.x + (g / CPT) * gridDim.x;
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int tile = unit + (g / CPT) * n_units;
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int b = g & 1, nc = t.n0 + (g % CPT) * 64;
         if (has_res) {
           mbar_expect_tx(&rfull_bar[b], CHUNK_BYTES);
@@ -321,13 +355,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         prefetch(1);
       }
       int g = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         const int64_t orow = t.m0 + row;
         mbar_wait(&tfull_bar[acc], acc_ph);
         tc_fence_after();
+        if (elected && local == 0) dbg_stamp(epi, 7);
         const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++g) {
@@ -341,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (c == CPT - 1) {                           // last TMEM read of this tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc(&tempty_bar[acc]);
           }
           uint32_t res16[16], aux16[16];
           if (has_res) {
@@ -366,37 +401,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           epilogue_math(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, nullptr);
-          uint8_t* cr = cbuf + b * CHUNK_BYTES + row * 128;
+          const int cb = g & (n_cbuf - 1);
+          uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(cr + (((grp * 4 + j) ^ swz) << 4)) =
                 make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
-          if (elected) tma_store_wait_read<0>();        // the previous chunk's store has finished reading cbuf[b^1]
+          if (elected) {                                // the buffer the NEXT chunk writes must be free again
+            if (n_cbuf == 4) tma_store_wait_read<2>();
+            else tma_store_wait_read<0>();
+          }
           __syncwarp();
           named_bar_sync(1, EPI_THREADS);
           if (elected) {
-            tma_store_2d(&tmC, cbuf + b * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+            tma_store_2d(&tmC, cbuf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
             tma_store_commit();
             prefetch(g + 2);                            // rbuf[b] / xbuf[b] were fully consumed before the barrier
           }
         }
       }
+      if (elected) dbg_stamp(epi, 8);
       if (elected) tma_store_wait_all<0>();
+      if (elected) dbg_stamp(epi, 9);
     } else {
       // ---------- staged epilogue: row re-map, fp32 output, pre-activation stash, wgrad accumulation ----------
       uint8_t* stg = stg_base + ew * STG_BYTES;
       uint8_t* my_row = stg + lane * STG_ROW;       // this thread's own row in the staging tile
       const int srow = lane >> 3;                   // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
       const int sseg = lane & 7;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         const int m = t.m0 + q * 32 + lane;
         mbar_wait(&tfull_bar[acc], acc_ph);
         tc_fence_after();
+        if (ew == 0 && lane == 0 && local == 0) dbg_stamp(epi, 7);
         const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         bool released = false;
 
@@ -415,7 +457,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if (cc + 2 >= NCH) {  // last TMEM read of this warp for this tile
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+              if (lane == 0) release_acc(&tempty_bar[acc]);
               released = true;
             }
 #pragma unroll
@@ -503,7 +545,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if (cc + 2 >= NCH && h == 1) {  // last TMEM read of this warp for this tile
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) release_acc(&tempty_bar[acc]);
                 released = true;
               }
               float f[32];
@@ -570,18 +612,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (!released) {   // this warp had no column chunk in this tile (narrow BN): still hand the stage back, in order
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) release_acc(&tempty_bar[acc]);
         }
       }
+      if (ew == 0 && lane == 0) dbg_stamp(epi, 8);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until here
+  if (threadIdx.x == 0) dbg_stamp(epi, 10);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 32) dbg_stamp(epi, 11);
 }
+
+static long long* g_gemm_timeline = nullptr;
 
 static int sm_count() {
   static int n = 0;
@@ -594,11 +643,11 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, int CG>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE, EPI>;
+  auto kern = gemm_kernel<BN, MODE, EPI, CG>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
@@ -609,12 +658,12 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   }
   const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr;
   int iters_per_split = 0;
-  const int tiles_m = ceil_div(d.m, BM), tiles_n = ceil_div(d.n, BN);
+  const int tiles_m = ceil_div(d.m, BM * CG), tiles_n = ceil_div(d.n, BN);
   int total = tiles_m * tiles_n;
   int kiters;
   if (MODE == 0) {
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
-    tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN);
+    tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN / CG);
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else if (MODE == 2) {
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
@@ -632,13 +681,16 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     kiters = iters_per_split;
   }
   if (!ta || !tb) return CB_ERR_CUDA;
-  int epi_bytes;
+  int epi_bytes, n_cbuf = 2;
   if (EPI == 1) {
     tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
     if (d.residual) tr = get_tmap_2d(d.residual, d.n, d.m, d.res_ld, 64, BM);
     if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
     if (!tc || (d.residual && !tr) || (d.aux && !tx)) return CB_ERR_CUDA;
-    epi_bytes = 2 * CHUNK_BYTES * (1 + (d.residual ? 1 : 0) + (d.aux ? 1 : 0));
+    // four output buffers (three TMA stores in flight) unless that would starve the operand ring
+    const int io_bytes = 2 * CHUNK_BYTES * ((d.residual ? 1 : 0) + (d.aux ? 1 : 0));
+    n_cbuf = ((SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - io_bytes - 4 * CHUNK_BYTES) / Cfg::STAGE_BYTES >= 3) ? 4 : 2;
+    epi_bytes = n_cbuf * CHUNK_BYTES + io_bytes;
   } else {
     epi_bytes = EPI_WARPS * STG_BYTES;
     epi_bytes = (epi_bytes + 1023) & ~1023;
@@ -655,23 +707,82 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int smem_bytes = stages * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
-  const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-                                                    iters_per_split, tiles_m, tiles_n, total, stages, epi_bytes, epi);
+  const int units = sm_count() / CG;
+  const int grid = (total < units ? total : units) * CG;
+  if (CG == 1) {
+    kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+                                                      iters_per_split, tiles_m, tiles_n, total, stages, epi_bytes, n_cbuf, epi);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
+                                       tiles_m, tiles_n, total, stages, epi_bytes, n_cbuf, epi);
+    if (e != cudaSuccess) {
+      set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return CB_ERR_CUDA;
+    }
+  }
   return check_launch("cb_gemm");
 }
 
-// tile width: widest tile that still gives every SM work; small problems prefer more, narrower tiles
-static int choose_bn(int m, int n, int mode) {
-  const int64_t mt = ceil_div(m, BM);
+// ------------------------------------------------------------------------------------------------
+// Launch configuration. Measured on B200: one SM ingests ~44 B/clk through TMA whatever the tile, so the main
+// loop of a CTA costs (k-iterations x stage bytes) / 44 cycles and the job is done when the busiest SM is; the
+// model below picks (tile width, CTA pairing, wgrad K-split) that minimises that, plus a per-tile epilogue term.
+// A CTA pair (cta_group::2) stages only half of the B tile per CTA: 256 x 256 pair tiles reach 128 FLOP/B.
+// ------------------------------------------------------------------------------------------------
+struct LaunchCfg {
+  int bn, cg, splits;
+};
+
+static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
   const int sms = sm_count();
-  if (mode == CB_GEMM_WGRAD) return n >= 128 ? 128 : 64;
-  if (n >= 256 && mt * ceil_div(n, 256) >= sms) return 256;
-  if (n >= 128 && mt * ceil_div(n, 128) >= sms) return 128;
-  return 64;
+  const int kc = ceil_div(d.k, BK);
+  const bool wgrad = d.mode == CB_GEMM_WGRAD;
+  static const int cand[5][2] = {{64, 1}, {128, 1}, {256, 1}, {128, 2}, {256, 2}};
+  LaunchCfg best = {64, 1, 1};
+  double best_cost = 1e30;
+  for (int c = 0; c < 5; ++c) {
+    const int bn = cand[c][0], cg = cand[c][1];
+    if (force_cg && cg != force_cg) continue;
+    if (d.block_n && bn != d.block_n) continue;
+    if (wgrad && bn == 256 && cg == 1) continue;          // not instantiated
+    if (bn > 64 && d.n <= bn / 2) continue;               // mostly padding
+    if (cg == 2 && d.m <= BM) continue;
+    const int units = sms / cg;
+    const int64_t base = static_cast<int64_t>(ceil_div(d.m, BM * cg)) * ceil_div(d.n, bn) * (wgrad ? d.ntaps : 1);
+    const double stage = 16384.0 + bn * 128.0 / cg;
+    const int max_split = wgrad ? (d.split_k > 0 ? d.split_k : (kc < 32 ? kc : 32)) : 1;
+    for (int sp = (wgrad && d.split_k > 0) ? d.split_k : 1; sp <= max_split; ++sp) {
+      const int ips = ceil_div(wgrad ? kc : kc * d.ntaps, sp);
+      const int real_sp = wgrad ? ceil_div(kc, ips) : 1;
+      const int64_t tiles = base * real_sp;
+      const double rounds = static_cast<double>((tiles + units - 1) / units);
+      const double epi = wgrad ? bn * 24.0 : bn * 10.0;    // cycles per tile: fp32 red.add vs bf16 store path
+      const double cost = rounds * (ips * stage / 44.0 + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = {bn, cg, real_sp};
+      }
+    }
+  }
+  return best;
 }
 
 }  // namespace cb
+
+/* bring-up / tuning hook (not part of the public header): device buffer of >= 16 int64 receiving clock64() stamps of CTA 0 */
+extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline = static_cast<long long*>(device_buf); }
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;
@@ -702,6 +813,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.H = d.map_h;
   epi.W = d.map_w;
   epi.seed = d.dropout_seed;
+  epi.dbg = g_gemm_timeline;
   if (d.dropout_p > 0.0f) {
     double t = static_cast<double>(d.dropout_p) * 4294967296.0;
     epi.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
@@ -723,20 +835,25 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(!(d.out2 && d.out_fp32), "cb_gemm(TN): out2 requires a bf16 primary output");
     CB_REQUIRE(d.rowmap == CB_ROWMAP_NONE || (d.map_h > 0 && d.map_w > 0), "cb_gemm: rowmap needs map_h/map_w");
     CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: 9-tap mode needs tap_w = W + 2");
-    const int bn = d.block_n ? d.block_n : choose_bn(d.m, d.n, d.mode);
+    const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
+    const LaunchCfg lc = choose_config(d, force_cg);
     // TMA epilogue whenever the output is a plain bf16 matrix (no row re-map, no second output)
-    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && !d.out2 && d.reserved == 0 &&
+    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && !d.out2 && (d.reserved & 1) == 0 &&
                          (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
-#define CB_DISPATCH(BN_)                                                                                             \
-  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1>(d, epi, stream) : launch_gemm<BN_, 2, 0>(d, epi, stream))         \
-            : (tma_epi ? launch_gemm<BN_, 0, 1>(d, epi, stream) : launch_gemm<BN_, 0, 0>(d, epi, stream))
-    switch (bn) {
-      case 64: CB_DISPATCH(64);
-      case 128: CB_DISPATCH(128);
-      case 256: CB_DISPATCH(256);
-      default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
+#define CB_DISPATCH(BN_, CG_)                                                                                                \
+  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))         \
+            : (tma_epi ? launch_gemm<BN_, 0, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 0, 0, CG_>(d, epi, stream))
+    if (lc.cg == 2) {
+      if (lc.bn == 128) { CB_DISPATCH(128, 2); }
+      CB_DISPATCH(256, 2);
+    }
+    switch (lc.bn) {
+      case 64: CB_DISPATCH(64, 1);
+      case 128: CB_DISPATCH(128, 1);
+      case 256: CB_DISPATCH(256, 1);
+      default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", lc.bn);
     }
 #undef CB_DISPATCH
   } else {
@@ -744,11 +861,18 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(d.m % 8 == 0 && d.n % 8 == 0, "cb_gemm(WGRAD): m, n must be multiples of 8 (got %d, %d)", d.m, d.n);
     CB_REQUIRE(d.out_ld % 4 == 0, "cb_gemm(WGRAD): out_ld must be a multiple of 4");
     CB_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "cb_gemm(WGRAD): out must be 16-byte aligned");
-    const int bn = d.block_n ? d.block_n : choose_bn(d.m, d.n, d.mode);
-    switch (bn) {
-      case 64: return launch_gemm<64, 1, 0>(d, epi, stream);
-      case 128: return launch_gemm<128, 1, 0>(d, epi, stream);
-      default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64 or 128 (got %d)", bn);
+    const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
+    const LaunchCfg lc = choose_config(d, force_cg);
+    cb_gemm_desc d2 = d;
+    d2.split_k = lc.splits;
+    if (lc.cg == 2) {
+      if (lc.bn == 128) return launch_gemm<128, 1, 0, 2>(d2, epi, stream);
+      return launch_gemm<256, 1, 0, 2>(d2, epi, stream);
+    }
+    switch (lc.bn) {
+      case 64: return launch_gemm<64, 1, 0, 1>(d2, epi, stream);
+      case 128: return launch_gemm<128, 1, 0, 1>(d2, epi, stream);
+      default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64, 128 (or 256 paired) (got %d)", lc.bn);
     }
   }
   return CB_ERR_INVALID;

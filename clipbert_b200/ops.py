@@ -102,7 +102,7 @@ def gemm(**kw):
     d = L.GemmDesc()
     d.ntaps = 1
     d.tap_sign = 1
-    d.split_k = 1
+    d.split_k = 0
     for k, v in kw.items():
         if k in _GEMM_PTR_FIELDS:
             v = _p(v) if isinstance(v, torch.Tensor) else v
@@ -123,12 +123,8 @@ def gemm(**kw):
 
 
 def wgrad_split(m, n, k, ntaps=1, block_n=128):
-    """Number of K-splits so that a wgrad launch fills the 148 SMs about twice."""
-    bn = block_n if n >= 128 else 64
-    tiles = -(-m // 128) * -(-n // bn) * ntaps
-    iters = -(-k // 64)
-    want = max(1, -(-296 // tiles))
-    return max(1, min(want, iters))
+    """0 = the library's launch-configuration model picks tile width, CTA pairing and the K-split."""
+    return 0
 
 
 # ------------------------------------------------------------------------------------------------

@@ -90,7 +90,7 @@ typedef struct cb_gemm_desc {
   const void* b;
   int64_t b_rows, b_ld;
   int32_t ntaps, tap_w, tap_sign; /* tap_w = W + 2 (padded row pitch in pixels) */
-  int32_t split_k;                /* WGRAD only; >= 1 */
+  int32_t split_k;                /* WGRAD only; 0 = let the library choose, else the number of K splits */
   /* epilogue */
   const float* scale;
   const float* shift;
@@ -109,7 +109,7 @@ typedef struct cb_gemm_desc {
   float dropout_p;
   uint64_t dropout_seed;
   int32_t block_n;  /* 0 = let the library choose (64 / 128 / 256) */
-  int32_t reserved; /* 1 = force the staged (non-TMA) epilogue; used by tests to cover both paths */
+  int32_t reserved; /* test knobs: bit0 force the staged (non-TMA) epilogue, bit1 force single-CTA tiles, bit2 force CTA pairs */
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

@@ -20,30 +20,37 @@ def _rnd(g, *shape, scale=1.0, dev="cuda"):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("bn", [64, 128, 256])
-@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (1312, 768, 768), (77, 264, 1096)])
-def test_gemm_tn_fp32_out(cuda, bn, shape):
+PAIR, SINGLE, STAGED = 4, 2, 1      # cb_gemm_desc.reserved test knobs
+
+
+@pytest.mark.parametrize("cfg", [(64, SINGLE), (128, SINGLE), (256, SINGLE), (128, PAIR), (256, PAIR)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (1312, 768, 768), (77, 264, 1096), (40000, 256, 64)])
+def test_gemm_tn_fp32_out(cuda, cfg, shape):
+    """Every tile width, single CTAs and CTA pairs (cta_group::2), ragged M / N / K, several tiles per persistent CTA."""
     ops = _ops()
     M, N, K = shape
+    bn, knob = cfg
     g = torch.Generator().manual_seed(1)
     A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
     C = torch.full((M, N), 7.0, device=cuda)
-    ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N, out_fp32=1, block_n=bn)
+    ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N, out_fp32=1, block_n=bn,
+             reserved=knob)
     assert relerr(C, A.float() @ B.float().t()) < TOL_FP32_OP
 
 
+@pytest.mark.parametrize("knob", [SINGLE, PAIR])
 @pytest.mark.parametrize("shape", [(500, 384, 256), (1312, 2304, 768), (64, 768, 3072)])
-def test_gemm_nn_dgrad(cuda, shape):
+def test_gemm_nn_dgrad(cuda, shape, knob):
     ops = _ops()
     M, N, K = shape     # out [M, N] = A [M, K] @ B [K, N]
     g = torch.Generator().manual_seed(2)
     A, B = _rnd(g, M, K), _rnd(g, K, N, scale=0.1)
     C = torch.zeros(M, N, device=cuda)
-    ops.gemm(mode=ops.CB_GEMM_NN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=K, b_ld=N, out=C, out_ld=N, out_fp32=1)
+    ops.gemm(mode=ops.CB_GEMM_NN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=K, b_ld=N, out=C, out_ld=N, out_fp32=1, reserved=knob)
     assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
 
 
-@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("staged", [0, STAGED, PAIR, PAIR | STAGED])
 @pytest.mark.parametrize("shape", [(500, 384, 256), (20000, 512, 128), (3000, 64, 64)])
 def test_gemm_epilogues(cuda, staged, shape):
     """Both epilogue I/O paths (TMA-prefetched / TMA-stored vs. per-warp staged), several tiles per persistent CTA."""
@@ -81,8 +88,9 @@ def test_gemm_epilogues(cuda, staged, shape):
     assert relerr(C, (acc + shift) * msk.float() + R.float()) < TOL_BF16_OP
 
 
+@pytest.mark.parametrize("knob", [SINGLE, PAIR])
 @pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64)])
-def test_conv3x3_fwd_and_dgrad(cuda, dims):
+def test_conv3x3_fwd_and_dgrad(cuda, dims, knob):
     ops = _ops()
     NB, H, W, Cin, Cout = dims
     g = torch.Generator().manual_seed(4)
@@ -94,14 +102,14 @@ def test_conv3x3_fwd_and_dgrad(cuda, dims):
     y = torch.zeros(NB * H * W, Cout, device=cuda, dtype=torch.bfloat16)
     wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
     ops.gemm(mode=ops.CB_GEMM_TN, m=P, n=Cout, k=Cin, a=xp, a_rows=P, a_ld=Cin, b=wk, b_rows=Cout, b_ld=9 * Cin, ntaps=9,
-             tap_w=W + 2, tap_sign=1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W)
+             tap_w=W + 2, tap_sign=1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W, reserved=knob)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     assert relerr(y, ref) < TOL_BF16_OP
     # dgrad of a conv whose forward weight is wf [Cin(out), Cout(in), 3, 3] stored KRSC: x plays dY
     wf = _rnd(g, Cin, Cout, 3, 3, scale=0.05)
     wfk = wf.permute(0, 2, 3, 1).contiguous().view(Cin, 9 * Cout)         # [out_f, (r,s,in_f)] = forward layout
     ops.gemm(mode=ops.CB_GEMM_NN, m=P, n=Cout, k=Cin, a=xp, a_rows=P, a_ld=Cin, b=wfk, b_rows=Cin, b_ld=9 * Cout, ntaps=9,
-             tap_w=W + 2, tap_sign=-1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W)
+             tap_w=W + 2, tap_sign=-1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W, reserved=knob)
     ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wf.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     assert relerr(y, ref) < TOL_BF16_OP
 
@@ -121,28 +129,30 @@ def test_rowmap_pad_keeps_border_zero(cuda):
     assert float(yp.float().abs().sum() - inner) == 0.0
 
 
-@pytest.mark.parametrize("case", [(64, 128, 64, 64, 1), (1312, 768, 768, 128, 1), (1000, 256, 192, 64, 1), (333, 136, 72, 64, 1),
-                                  (5000, 256, 256, 128, 7), (640, 128, 128, 64, 100), (32, 8, 1536, 128, 1)])
+@pytest.mark.parametrize("case", [(64, 128, 64, 64, 1, SINGLE), (1312, 768, 768, 128, 1, SINGLE), (1000, 256, 192, 64, 1, SINGLE),
+                                  (333, 136, 72, 64, 1, SINGLE), (5000, 256, 256, 128, 7, SINGLE), (640, 128, 128, 64, 100, SINGLE),
+                                  (32, 8, 1536, 128, 1, SINGLE), (1312, 768, 3072, 256, 0, PAIR), (5000, 512, 256, 128, 3, PAIR),
+                                  (1312, 2304, 768, 0, 0, 0), (50176, 512, 128, 0, 0, 0)])
 def test_wgrad(cuda, case):
     ops = _ops()
-    P, Mo, No, bn, sk = case
+    P, Mo, No, bn, sk, knob = case
     g = torch.Generator().manual_seed(6)
     dY, X = _rnd(g, P, Mo), _rnd(g, P, No)
     rs = (torch.rand(Mo, generator=g) + 0.5).to(cuda)
     dW = torch.zeros(Mo, No, device=cuda)
     ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk, scale=rs,
-             out=dW, out_ld=No, out_fp32=1, block_n=bn)
+             out=dW, out_ld=No, out_fp32=1, block_n=bn, reserved=knob)
     assert relerr(dW, (dY.float().t() @ X.float()) * rs[:, None]) < TOL_FP32_OP
     # accumulation semantics: a second launch adds
     ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk, scale=rs,
-             out=dW, out_ld=No, out_fp32=1, block_n=bn)
+             out=dW, out_ld=No, out_fp32=1, block_n=bn, reserved=knob)
     assert relerr(dW, 2 * (dY.float().t() @ X.float()) * rs[:, None]) < TOL_FP32_OP
 
 
-@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 128, 1), (4, 14, 14, 128, 128, 3)])
+@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 128, 1, SINGLE), (4, 14, 14, 128, 128, 3, SINGLE), (4, 14, 14, 256, 256, 0, PAIR)])
 def test_wgrad_conv3x3(cuda, dims):
     ops = _ops()
-    NB, H, W, Cin, Cout, sk = dims
+    NB, H, W, Cin, Cout, sk, knob = dims
     g = torch.Generator().manual_seed(7)
     x, dy = _rnd(g, NB, H, W, Cin), _rnd(g, NB, H, W, Cout)
     xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
@@ -151,7 +161,7 @@ def test_wgrad_conv3x3(cuda, dims):
     P = NB * (H + 2) * (W + 2)
     dW = torch.zeros(Cout, 9 * Cin, device=cuda)
     ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Cout, n=Cin, k=P, a=dyp, a_rows=P, a_ld=Cout, b=xp, b_rows=P, b_ld=Cin, ntaps=9, tap_w=W + 2,
-             tap_sign=1, split_k=sk, out=dW, out_ld=9 * Cin, out_fp32=1)
+             tap_sign=1, split_k=sk, out=dW, out_ld=9 * Cin, out_fp32=1, reserved=knob)
     wz = torch.zeros(Cout, Cin, 3, 3, device=cuda, requires_grad=True)
     F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(dy.float().permute(0, 3, 1, 2))
     assert relerr(dW, wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)) < TOL_FP32_OP

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--txt_len", type=int, default=32)
     ap.add_argument("--n_ex", type=int, default=1)
     ap.add_argument("--out", default="gpurun_out/step_breakdown.txt")
+    ap.add_argument("--ncu", type=int, default=0, help="1: bracket ONE step with cudaProfilerStart/Stop for "
+                    "`ncu --profile-from-start off` instead of timing with events")
     args = ap.parse_args()
     import clipbert_b200 as cb
     from clipbert_b200 import ops
@@ -50,6 +52,12 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    if args.ncu:
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     ev = []
     ops.set_op_timing(ev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
