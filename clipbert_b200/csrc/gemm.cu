@@ -736,10 +736,13 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
 }
 
 // ------------------------------------------------------------------------------------------------
-// Launch configuration. Measured on B200: one SM ingests ~44 B/clk through TMA whatever the tile, so the main
-// loop of a CTA costs (k-iterations x stage bytes) / 44 cycles and the job is done when the busiest SM is; the
-// model below picks (tile width, CTA pairing, wgrad K-split) that minimises that, plus a per-tile epilogue term.
-// A CTA pair (cta_group::2) stages only half of the B tile per CTA: 256 x 256 pair tiles reach 128 FLOP/B.
+// Launch configuration. Measured on B200 (tools/probe_gemm_timeline.py, profiles/r01_gemm_timeline.txt): a
+// persistent CTA sustains ~60-70 B/clk of TMA ingest, so its main loop costs about (k-iterations x stage bytes)
+// / 60 cycles and the launch is done when the busiest SM is. The model picks the tile width (and the wgrad
+// K-split) minimising that plus a per-tile epilogue term. 128 x 256 single-CTA tiles reach 1.27 PFLOP/s on
+// 8192^2 x 2048 (87 % of the measured sustained cuBLAS figure). The cta_group::2 CTA-pair path is functionally
+// complete and unit-tested but measured ~2x SLOWER than single CTAs in round 1 (cause not yet found), so it is
+// only used when a caller forces it (cb_gemm_desc.reserved bit 2).
 // ------------------------------------------------------------------------------------------------
 struct LaunchCfg {
   int bn, cg, splits;
@@ -754,9 +757,8 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
   double best_cost = 1e30;
   for (int c = 0; c < 5; ++c) {
     const int bn = cand[c][0], cg = cand[c][1];
-    if (force_cg && cg != force_cg) continue;
+    if (cg != (force_cg ? force_cg : 1)) continue;
     if (d.block_n && bn != d.block_n) continue;
-    if (wgrad && bn == 256 && cg == 1) continue;          // not instantiated
     if (bn > 64 && d.n <= bn / 2) continue;               // mostly padding
     if (cg == 2 && d.m <= BM) continue;
     const int units = sms / cg;
@@ -769,7 +771,7 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
       const int64_t tiles = base * real_sp;
       const double rounds = static_cast<double>((tiles + units - 1) / units);
       const double epi = wgrad ? bn * 24.0 : bn * 10.0;    // cycles per tile: fp32 red.add vs bf16 store path
-      const double cost = rounds * (ips * stage / 44.0 + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
+      const double cost = rounds * (ips * (stage / 60.0 + 64.0) + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
       if (cost < best_cost) {
         best_cost = cost;
         best = {bn, cg, real_sp};
@@ -872,6 +874,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     switch (lc.bn) {
       case 64: return launch_gemm<64, 1, 0, 1>(d2, epi, stream);
       case 128: return launch_gemm<128, 1, 0, 1>(d2, epi, stream);
+      case 256: return launch_gemm<256, 1, 0, 1>(d2, epi, stream);
       default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64, 128 (or 256 paired) (got %d)", lc.bn);
     }
   }

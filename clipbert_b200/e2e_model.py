@@ -13,6 +13,23 @@ from .modeling import (ClipBertForMultipleChoice, ClipBertForSequenceClassificat
                        ClipBertForVideoTextRetrieval)
 
 
+def allreduce_flat(grads, group=None, average=True, async_op=False):
+    """Sum (or average) a list of flat gradient buffers over the data-parallel group, in place.
+
+    The B200 replacement of ``hvd.DistributedOptimizer``'s per-parameter allreduce + ``synchronize()``
+    (src/tasks/run_video_retrieval.py:299-301,432): two flat fp32 buffers, one NCCL all-reduce each.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return []
+    ws = dist.get_world_size(group)
+    works = []
+    for g in grads:
+        if average:
+            g.mul_(1.0 / ws)
+        works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+    return works
+
+
 class ClipBert(nn.Module):
     def __init__(self, config, input_format="BGR", detectron2_model_cfg=None, transformer_cls=ClipBertForVideoTextRetrieval,
                  freeze_at=2):
@@ -72,12 +89,4 @@ class ClipBert(nn.Module):
 
     def allreduce_grads(self, group=None, average=True, async_op=False):
         """Sum (average) the two flat fp32 gradient buffers over the data-parallel group (NCCL)."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return []
-        ws = dist.get_world_size(group)
-        works = []
-        for g in self.flat_grads():
-            if average:
-                g.mul_(1.0 / ws)
-            works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
-        return works
+        return allreduce_flat(self.flat_grads(), group, average, async_op)

@@ -289,7 +289,11 @@ class _ClipBertHeadModel(nn.Module):
             repeat = (1, None, None)
         else:
             assert len(repeat_counts) == nvid and sum(repeat_counts) == nseq
-            if len(set(repeat_counts)) == 1:
+            if sum(repeat_counts) == len(repeat_counts):
+                # repeat_tensor_rows returns its input untouched in this case, even for counts like [2, 0, 1]
+                # (src/datasets/data_utils.py:351) - follow the reference
+                repeat = (1, None, None)
+            elif len(set(repeat_counts)) == 1:
                 repeat = (int(repeat_counts[0]), None, None)
             else:
                 s2v = torch.tensor([i for i, r in enumerate(repeat_counts) for _ in range(r)], dtype=torch.int32)

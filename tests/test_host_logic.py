@@ -1,0 +1,111 @@
+"""CPU tests of the host-side logic around the kernels: flat parameter storage, state_dict contract,
+the world_size-2 gradient exchange (gloo), synthetic-workload and FLOP accounting helpers."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import make_cfg
+
+
+def test_state_dict_keys_match_the_reference_contract():
+    import clipbert_b200 as cb
+    from oracle import synth
+    model = cb.ClipBert(make_cfg(), detectron2_model_cfg="R-50-grid.yaml")
+    sd = synth.full_state_dict(42)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    res = model.load_state_dict(sd)
+    assert not res.missing_keys
+    names = [n for n, _ in model.named_parameters()]
+    assert all(n.startswith(("cnn.", "transformer.")) for n in names) and any("grid_encoder" in n for n in names)
+    # d2 FREEZE_AT=2: stem + res2 frozen, res3-5 + grid_encoder + transformer trainable
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert frozen and all(("stem" in n) or ("res2" in n) for n in frozen)
+    n_tr = sum(p.numel() for n, p in model.named_parameters() if p.requires_grad)
+    assert abs(n_tr - 148.6e6) < 0.3e6                                   # SURVEY.md §8d allreduce payload
+    assert "FREEZE_AT: 2" in model.cnn.config_file
+    model.freeze_cnn_backbone()
+    assert [n for n, p in model.cnn.named_parameters() if p.requires_grad] == ["grid_encoder.0.weight"]
+
+
+def test_flat_group_views_grads_and_conv_layout():
+    from clipbert_b200.params import FlatGroup
+    lin = torch.nn.Linear(24, 40)
+    conv = torch.nn.Conv2d(8, 16, 3, bias=False)
+    w0, c0 = lin.weight.detach().clone(), conv.weight.detach().clone()
+    fg = FlatGroup(torch.device("cpu"))
+    e_l = fg.add("lin.w", lin.weight)
+    fg.add("lin.b", lin.bias)
+    e_c = fg.add("conv.w", conv.weight, kind="conv")
+    fg.materialize()
+    assert torch.equal(lin.weight, w0) and torch.equal(conv.weight, c0)            # values preserved
+    # conv master is stored KRSC (channels_last): element (o, c, r, s) lives at ((o*3 + r)*3 + s)*8 + c
+    flat = fg.master[e_c["offset"]: e_c["offset"] + e_c["numel"]].view(16, 3, 3, 8)
+    assert torch.equal(flat.permute(0, 3, 1, 2), c0)
+    assert e_l["offset"] % 64 == 0 and e_c["offset"] % 64 == 0
+    # grads are views of one buffer: writing the flat buffer is visible through p.grad, in the KRSC order
+    fg.grad.zero_()
+    fg.grad[e_c["offset"] + 5] = 3.0                                                # (o=0, r=0, s=0, c=5)
+    assert float(conv.weight.grad[0, 5, 0, 0]) == 3.0
+    for prm in (lin.weight, lin.bias, conv.weight):                                 # optimizer.zero_grad(set_to_none=True)
+        prm.grad = None
+    fg.grad.fill_(7.0)
+    fg.attach_grads()
+    assert conv.weight.grad is not None and float(fg.grad.abs().sum()) == 0.0       # re-attached and zeroed
+    assert fg.is_current()
+    lin.weight.data = lin.weight.data.clone()
+    assert not fg.is_current()
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from clipbert_b200.e2e_model import allreduce_flat
+    a = torch.full((1000,), float(rank + 1))
+    b = torch.arange(10.0) * (rank + 1)
+    works = allreduce_flat([a, b], average=True, async_op=True)
+    for w in works:
+        w.wait()
+    q.put((rank, float(a[0]), b.tolist()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, a0, b in res:
+        assert a0 == pytest.approx(1.5)                                   # mean of (1, 2)
+        assert b == pytest.approx([1.5 * i for i in range(10)])
+
+
+def test_flop_accounting_matches_baseline_md():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    assert bench.flops_per_clip(2, 41, 1) / 1e9 == pytest.approx(69.40, abs=0.05)       # BASELINE.md §3, C2 / headline
+    assert bench.flops_per_clip(2, 41, 2) / 1e9 == pytest.approx(90.49, abs=0.05)
+    assert bench.flops_per_clip(1, 41, 5) / 1e9 == pytest.approx(129.61, abs=0.1)
+    assert bench.flops_per_clip(2, 41, 1, backward=False) / 1e9 == pytest.approx(25.23, abs=0.05)
+    assert bench.flops_per_clip(1, 521, 1, backward=False) / 1e9 == pytest.approx(107.61, abs=0.1)
+
+
+def test_synthetic_text_follows_the_survey_recipe():
+    from oracle import synth
+    ids, mask = synth.synth_text(16, 32, seed=1)
+    assert ids.shape == (16, 32) and (ids[:, 0] == 101).all()
+    lens = mask.sum(1)
+    assert int(lens.min()) >= 8 and int(lens.max()) <= 32
+    for i in range(16):
+        n = int(lens[i])
+        assert int(ids[i, n - 1]) == 102 and (ids[i, n:] == 0).all() and (mask[i, :n] == 1).all()

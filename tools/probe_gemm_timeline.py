@@ -56,32 +56,10 @@ def rnd(*shape):
     return torch.randn(*shape, device=dev).to(torch.bfloat16)
 
 
-for (M, N, K) in [(32, 768, 768), (1312, 768, 768), (1312, 3072, 768), (1312, 768, 3072), (12544, 1024, 256)]:
-    A, B = rnd(M, K), rnd(N, K)
+import sys as _sys
+for (M, N, K, taps) in [(1312, 3072, 768, 1), (12544, 1024, 256, 1), (16384, 256, 256, 9), (5184, 2048, 768, 9), (8192, 8192, 2048, 1)]:
+    A, B = rnd(M + 64, K), rnd(N, K * taps)
     C = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-    base = dict(mode=0, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N)
-    run("TN %dx%dx%d tma-epi" % (M, N, K), **base)
-    run("TN %dx%dx%d staged-epi" % (M, N, K), reserved=1, **base)
-    R = rnd(M, N)
-    run("TN %dx%dx%d tma-epi +res+relu" % (M, N, K), residual=R, res_ld=N, act=1, **base)
-P, Mo, No = 1312, 768, 3072
-dY, X = rnd(P, Mo), rnd(P, No)
-dW = torch.zeros(Mo, No, device=dev)
-for sk in (1, 3):
-    run("WGRAD %dx%dx%d split %d" % (Mo, No, P, sk), mode=1, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk,
-        out=dW, out_ld=No, out_fp32=1)
-# reference point: an empty-ish kernel of our own (LayerNorm over 32 rows)
-x = rnd(32, 768)
-y = torch.empty_like(x)
-st = torch.empty(32, 2, device=dev)
-g = torch.ones(768, device=dev)
-for _ in range(5):
-    ops.layernorm_fwd(x, g, g, y, st, 1e-12)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(200):
-    ops.layernorm_fwd(x, g, g, y, st, 1e-12)
-e1.record()
-torch.cuda.synchronize()
-print("layernorm 32 rows: stream %.2f us/launch" % (1e3 * e0.elapsed_time(e1) / 200))
+    base = dict(mode=0, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K * taps, out=C, out_ld=N, ntaps=taps, tap_w=30, tap_sign=1)
+    for bn, knob, lab in [(128, 2, "single bn128"), (256, 2, "single bn256"), (128, 4, "pair bn128"), (256, 4, "pair bn256")]:
+        run("TN %dx%dx%d t%d %s" % (M, N, K, taps, lab), block_n=bn, reserved=knob, **base)
