@@ -6,5 +6,5 @@ host-side mirrors of the reference module interface (``ClipBert``, ``GridFeatBac
 """
 from .e2e_model import ClipBert  # noqa: F401
 from .grid_feat import GridFeatBackbone  # noqa: F401
-from .modeling import (ClipBertForMultipleChoice, ClipBertForSequenceClassification,  # noqa: F401
+from .modeling import (ClipBertForMultipleChoice, ClipBertForPreTraining, ClipBertForSequenceClassification,  # noqa: F401
                        ClipBertForVideoTextRetrieval)

@@ -506,6 +506,22 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
   *reinterpret_cast<uint4*>(y + i) = o;
 }
 
+// dx = dy * gelu'(u)  (backward of the MLM-head transform activation, transformers.py:486-495)
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
+                                __nv_bfloat16* __restrict__ dx, int64_t n8) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n8) return;
+  const uint4 a = reinterpret_cast<const uint4*>(dy)[t], b = reinterpret_cast<const uint4*>(u)[t];
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 g = unpack_bf16x2(av[j]), x = unpack_bf16x2(bv[j]);
+    o[j] = pack_bf16x2(g.x * gelu_erf_grad(x.x), g.y * gelu_erf_grad(x.y));
+  }
+  reinterpret_cast<uint4*>(dx)[t] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // out[r, 0:cpad] (bf16) = in[r, 0:c] (fp32) zero-padded ; used for dlogits -> padded classifier grad
 __global__ void pad_cast_kernel(const float* __restrict__ in, int64_t in_ld, __nv_bfloat16* __restrict__ out, int rows,
                                 int c, int cpad) {
@@ -648,6 +664,13 @@ int cb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* 
   dropout_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, make_drop(p, seed));
   return check_launch("cb_dropout");
+}
+
+int cb_gelu_bwd(const void* dy, const void* u, void* dx, int64_t n, void* stream) {
+  CB_REQUIRE(dy && u && dx && n > 0 && n % 8 == 0, "cb_gelu_bwd: n must be a positive multiple of 8");
+  gelu_bwd_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(dx), n / 8);
+  return check_launch("cb_gelu_bwd");
 }
 
 int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int cpad, void* stream) {

@@ -150,9 +150,9 @@ class _TransformerFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, *douts):
         stash, ctx.stash = ctx.stash, None
-        dgrid = ctx.module._backward_impl(stash, dout, ctx.grid_needs_grad)
+        dgrid = ctx.module._backward_impl(stash, douts if len(douts) > 1 else douts[0], ctx.grid_needs_grad)
         return None, dgrid, None, None, None, None
 
 
@@ -223,12 +223,15 @@ class _ClipBertHeadModel(nn.Module):
         emb, vis = bert.embeddings, bert.visual_embeddings
         self._spec["emb.ln"] = (flat.add("emb.ln.w", emb.LayerNorm.weight), flat.add("emb.ln.b", emb.LayerNorm.bias))
         self._spec["vis.ln"] = (flat.add("vis.ln.w", vis.LayerNorm.weight), flat.add("vis.ln.b", vis.LayerNorm.bias))
-        for key, mod in (("emb.word", emb.word_embeddings), ("emb.pos", emb.position_embeddings), ("emb.type", emb.token_type_embeddings),
+        # the word table gets room for 8-row padding: the tied MLM decoder reads / accumulates it as a [vocab_pad, 768] operand
+        vocab_pad = (emb.word_embeddings.weight.shape[0] + 7) // 8 * 8
+        self._spec["emb.word"] = flat.add("emb.word", emb.word_embeddings.weight, slot_numel=vocab_pad * emb.word_embeddings.weight.shape[1])
+        for key, mod in (("emb.pos", emb.position_embeddings), ("emb.type", emb.token_type_embeddings),
                          ("vis.pos", vis.position_embeddings), ("vis.row", vis.row_position_embeddings),
                          ("vis.col", vis.col_position_embeddings), ("vis.type", vis.token_type_embeddings)):
             self._spec[key] = flat.add(key, mod.weight)
-        for name, p in self._extra_params():
-            self._spec[name] = flat.add(name, p)
+        for name, p, slot in self._extra_params():
+            self._spec[name] = flat.add(name, p, slot_numel=slot)
         flat.materialize()
         self._flat = flat
         # resolve views
@@ -444,7 +447,7 @@ class _ClipBertHeadModel(nn.Module):
 
     def _backward_impl(self, st, dout, grid_needs_grad):
         self._flat.attach_grads()
-        dev = dout.device
+        dev = st["x_last"].device
         cfg = self.config
         H = _cfg(cfg, "hidden_size")
         heads = _cfg(cfg, "num_attention_heads")
@@ -640,3 +643,162 @@ class ClipBertForMultipleChoice(_MlpHeadMixin, _ClipBertHeadModel):
         else:
             raise ValueError("Invalid option for config.loss_type")
         return logits, loss
+
+
+class BertPredictionHeadTransform(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        h = _cfg(config, "hidden_size")
+        self.dense = nn.Linear(h, h)
+        self.LayerNorm = nn.LayerNorm(h, eps=_cfg(config, "layer_norm_eps"))
+
+
+class BertLMPredictionHead(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        self.decoder = nn.Linear(_cfg(config, "hidden_size"), _cfg(config, "vocab_size"), bias=False)
+        self.bias = nn.Parameter(torch.zeros(_cfg(config, "vocab_size")))
+        self.decoder.bias = self.bias          # hf 2.11 link (transformers.py:503-507)
+
+
+class BertPreTrainingHeads(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.predictions = BertLMPredictionHead(config)
+        self.seq_relationship = nn.Linear(_cfg(config, "hidden_size"), 2)
+
+
+class ClipBertForPreTraining(_ClipBertHeadModel):
+    """src/modeling/modeling.py:241-307 — MLM head on the text positions (tied decoder, vocab 30522) + ITM head.
+
+    Head kernels: strided gather of the text rows, cb_gemm(+bias, GELU, stash) -> cb_layernorm_fwd ->
+    cb_gemm against the bf16 copy of the word table (N padded 30522 -> 30528, fp32 logits) ; ITM = cb_gemm on
+    the pooled output. The per-token CE (ignore_index -100) stays torch glue on the returned logits.
+    """
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.cls = BertPreTrainingHeads(config)
+        _init_bert_weights(self, _cfg(config, "initializer_range", 0.02))
+        self.cls.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight      # tied (get_output_embeddings)
+        self._word_bf16 = None
+
+    def _head_linears(self):
+        return [("itm", self.cls.seq_relationship), ("mlm_t", self.cls.predictions.transform.dense)]
+
+    def _extra_layernorms(self):
+        return [("mlm_ln", self.cls.predictions.transform.LayerNorm)]
+
+    def _extra_params(self):
+        v = self.cls.predictions.bias.shape[0]
+        return [("mlm_bias", self.cls.predictions.bias, (v + 7) // 8 * 8)]
+
+    def _num_head_outputs(self):
+        return 2
+
+    def named_parameters(self, *a, **k):            # the tied decoder weight must not be listed twice
+        return super().named_parameters(*a, **k)
+
+    @torch.no_grad()
+    def _repack(self):
+        super()._repack()
+        e = self._spec["emb.word"]
+        v, h = e["param"].shape
+        vp = (v + 7) // 8 * 8
+        if self._word_bf16 is None or self._word_bf16.device != self._flat.master.device:
+            self._word_bf16 = torch.zeros(vp, h, dtype=torch.bfloat16, device=self._flat.master.device)
+        ops.cast_scale(self._flat.master[e["offset"]: e["offset"] + v * h], self._word_bf16.view(-1)[: v * h])
+
+    def _head_forward(self, pooled, st, nseq, p_h, seed, need_backward):
+        dev = pooled.device
+        H = pooled.shape[1]
+        nseq_, nvid, T, gh, gw, lt, L = st["dims"]
+        bf16 = torch.bfloat16
+        itm_l, t_l = self._lin["itm"], self._lin["mlm_t"]
+        itm = torch.empty(nseq, itm_l.n, dtype=torch.float32, device=dev)
+        self._gemm_fwd(pooled, nseq, itm_l, itm, out_fp32=1)
+        # text rows of the final sequence output (sequence_output[:, :txt_len], modeling.py:283-285)
+        R = nseq * lt
+        xt = st["x_last"].view(nseq, L, H)[:, :lt].contiguous().view(R, H)
+        u = torch.empty(R, H, dtype=bf16, device=dev)
+        t1 = torch.empty(R, H, dtype=bf16, device=dev)
+        self._gemm_fwd(xt, R, t_l, t1, act=ops.ACT_GELU, out2=u, out2_ld=H)
+        g, b, _, _ = self._ln("mlm_ln")
+        t2 = torch.empty(R, H, dtype=bf16, device=dev)
+        stats = torch.empty(R, 2, dtype=torch.float32, device=dev)
+        ops.layernorm_fwd(t1, g, b, t2, stats, float(_cfg(self.config, "layer_norm_eps")))
+        e = self._spec["mlm_bias"]
+        vp = self._word_bf16.shape[0]
+        bias = self._flat.master[e["offset"]: e["offset"] + vp]
+        scores = torch.empty(R, vp, dtype=torch.float32, device=dev)
+        ops.gemm(mode=ops.CB_GEMM_TN, m=R, n=vp, k=H, a=t2, a_rows=R, a_ld=H, b=self._word_bf16, b_rows=vp, b_ld=H, shift=bias,
+                 out=scores, out_ld=vp, out_fp32=1)
+        st.update(xt=xt, mlm_u=u, mlm_t1=t1, mlm_t2=t2, mlm_stats=stats)
+        v = _cfg(self.config, "vocab_size")
+        return itm[:, :2], scores.view(nseq, lt, vp)[:, :, :v]
+
+    def _head_backward(self, st, douts, nseq, H):
+        ditm, dscores = douts
+        dev = st["x_last"].device
+        bf16 = torch.bfloat16
+        nseq_, nvid, T, gh, gw, lt, L = st["dims"]
+        R = nseq * lt
+        itm_l, t_l = self._lin["itm"], self._lin["mlm_t"]
+        dpre = torch.zeros(nseq, H, dtype=bf16, device=dev)
+        if ditm is not None:
+            dl = torch.empty(nseq, itm_l.n, dtype=bf16, device=dev)
+            ops.pad_cast(ditm.float().contiguous(), dl)
+            self._wgrad(itm_l, dl, st["pooled"], nseq)
+            ops.colsum(dl, itm_l.gb, nseq, itm_l.n)
+            self._dgrad(itm_l, dl, nseq, dpre, aux=st["pooled"], aux_ld=H, aux_mode=ops.AUX_TANH_GRAD)
+        st["mlm_dx"] = None
+        if dscores is not None:
+            vp = self._word_bf16.shape[0]
+            v = _cfg(self.config, "vocab_size")
+            ds = torch.empty(R, vp, dtype=bf16, device=dev)
+            ops.pad_cast(dscores.reshape(R, v).float().contiguous(), ds)
+            e = self._spec["emb.word"]
+            gword = self._flat.grad[e["offset"]: e["offset"] + vp * H].view(vp, H)
+            eb = self._spec["mlm_bias"]
+            ops.gemm(mode=ops.CB_GEMM_WGRAD, m=vp, n=H, k=R, a=ds, a_rows=R, a_ld=vp, b=st["mlm_t2"], b_rows=R, b_ld=H, split_k=0, out=gword,
+                     out_ld=H, out_fp32=1)
+            ops.colsum(ds, self._flat.grad[eb["offset"]: eb["offset"] + vp], R, vp)
+            dt2 = torch.empty(R, H, dtype=bf16, device=dev)
+            ops.gemm(mode=ops.CB_GEMM_NN, m=R, n=H, k=vp, a=ds, a_rows=R, a_ld=vp, b=self._word_bf16, b_rows=vp, b_ld=H, out=dt2, out_ld=H)
+            g, _, dg, db = self._ln("mlm_ln")
+            dt1 = torch.empty(R, H, dtype=bf16, device=dev)
+            ops.layernorm_bwd(dt2, st["mlm_t1"], st["mlm_stats"], g, dt1, None, dg, db, None, 0.0, 0)
+            # d(pre-GELU) = dt1 * gelu'(u): a dgrad-style epilogue needs a GEMM, so fold it into the dgrad of transform.dense
+            # by first masking dt1 (relu_mask has no gelu form) -> use the NN GEMM of the *identity-free* path below
+            du = torch.empty(R, H, dtype=bf16, device=dev)
+            _gelu_bwd(dt1, st["mlm_u"], du)
+            self._wgrad(t_l, du, st["xt"], R)
+            ops.colsum(du, t_l.gb, R, H)
+            dxt = torch.empty(R, H, dtype=bf16, device=dev)
+            self._dgrad(t_l, du, R, dxt)
+            st["mlm_dx"] = dxt
+        return dpre
+
+    def _extra_sequence_grad(self, st):
+        dxt = st.get("mlm_dx")
+        if dxt is None:
+            return None
+        nseq, nvid, T, gh, gw, lt, L = st["dims"]
+        H = dxt.shape[1]
+        full = torch.zeros(nseq, L, H, dtype=dxt.dtype, device=dxt.device)
+        full[:, :lt] = dxt.view(nseq, lt, H)
+        return full.view(nseq * L, H)
+
+    def forward(self, text_input_ids, visual_inputs, text_input_mask, mlm_labels=None, itm_labels=None, _repeat_counts=None, **_unused):
+        itm_scores, mlm_scores = self._run(text_input_ids, visual_inputs, text_input_mask, _repeat_counts)
+        v = _cfg(self.config, "vocab_size")
+        mlm_loss = F.cross_entropy(mlm_scores.reshape(-1, v), mlm_labels.view(-1), reduction="none") if mlm_labels is not None else 0
+        itm_loss = F.cross_entropy(itm_scores.view(-1, 2), itm_labels.view(-1), reduction="none") if itm_labels is not None else 0
+        return dict(mlm_scores=mlm_scores, mlm_loss=mlm_loss, mlm_labels=mlm_labels, itm_scores=itm_scores, itm_loss=itm_loss,
+                    itm_labels=itm_labels)
+
+
+def _gelu_bwd(dy, u, out):
+    """out = dy * gelu'(u) via the GEMM epilogue machinery is overkill for one [R,768] tensor: reuse cb_layernorm-free path."""
+    ops.gelu_bwd(dy, u, out)

@@ -24,6 +24,7 @@ _SIGS = {
     "cb_embed_visual_bwd": [_vp, _vp, _vp, _vp, _i] + [_vp] * 12 + [_i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_colsum": [_vp, _i64, _vp, _i, _i, _vp],
     "cb_dropout": [_vp, _vp, _i64, _f, _u64, _vp],
+    "cb_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
     "cb_attention_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp],
@@ -168,6 +169,10 @@ def colsum(x, out, m, n, ld=None):
 
 def dropout(x, y, p, seed):
     _call("cb_dropout", _p(x), _p(y), x.numel(), p, seed, _s())
+
+
+def gelu_bwd(dy, u, dx):
+    _call("cb_gelu_bwd", _p(dy), _p(u), _p(dx), dy.numel(), _s())
 
 
 def pad_cast(src, dst):

@@ -183,6 +183,8 @@ int cb_attention_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
  * ------------------------------------------------------------------------------------------ */
 int cb_colsum(const void* x, int64_t ld, float* out, int m, int n, void* stream);
 int cb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream);
+/* dx = dy * gelu'(u): backward of BertPredictionHeadTransform's activation (transformers.py:486-495) */
+int cb_gelu_bwd(const void* dy, const void* u, void* dx, int64_t n, void* stream);
 int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int cpad, void* stream);
 int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void* out, int64_t n, void* stream);
 
