@@ -552,6 +552,31 @@ __global__ void cast_scale_kernel(const float* __restrict__ in, const float* __r
   }
 }
 
+// all conv weights of the backbone in ONE launch: segment g (blockIdx.y) = one conv's KRSC block, scaled per output row
+__global__ void cast_scale_segments_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
+                                           const int64_t* __restrict__ seg /*[nseg][4]: offset, numel, row_len, scale_off (-1: none)*/,
+                                           const float* __restrict__ scales) {
+  const int64_t* sg = seg + 4 * blockIdx.y;
+  const int64_t off = sg[0], n = sg[1], row_len = sg[2], soff = sg[3];
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(master + off + i);
+      float s0 = 1.f, s1 = 1.f, s2 = 1.f, s3 = 1.f;
+      if (soff >= 0) {
+        s0 = scales[soff + i / row_len]; s1 = scales[soff + (i + 1) / row_len];
+        s2 = scales[soff + (i + 2) / row_len]; s3 = scales[soff + (i + 3) / row_len];
+      }
+      uint2 o;
+      o.x = pack_bf16x2(v.x * s0, v.y * s1);
+      o.y = pack_bf16x2(v.z * s2, v.w * s3);
+      *reinterpret_cast<uint2*>(packed + off + i) = o;
+    } else {
+      for (int64_t k = i; k < n; ++k) packed[off + k] = __float2bfloat16(master[off + k] * (soff >= 0 ? scales[soff + k / row_len] : 1.f));
+    }
+  }
+}
+
 }  // namespace cb
 
 // ================================================================================================
@@ -678,6 +703,14 @@ int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int 
   pad_cast_kernel<<<ceil_div(static_cast<int64_t>(rows) * cpad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, in_ld, static_cast<__nv_bfloat16*>(out), rows, c, cpad);
   return check_launch("cb_pad_cast");
+}
+
+int cb_cast_scale_segments(const float* master, void* packed, const int64_t* segments, int nseg, const float* scales, void* stream) {
+  CB_REQUIRE(master && packed && segments && nseg > 0, "cb_cast_scale_segments: bad arguments");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(master) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0, "cb_cast_scale_segments: misaligned");
+  dim3 grid(64, nseg);
+  cast_scale_segments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(master, static_cast<__nv_bfloat16*>(packed), segments, scales);
+  return check_launch("cb_cast_scale_segments");
 }
 
 int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void* out, int64_t n, void* stream) {

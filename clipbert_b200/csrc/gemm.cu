@@ -173,11 +173,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, int M, int N, int K, int ntaps, int tap_w, int tap_sign,
-                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int epi_bytes, int n_cbuf, GemmEpi epi) {
+                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, GemmEpi epi) {
   using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* stg_base = smem + STAGES * Cfg::STAGE_BYTES;     // epilogue region (1024-byte aligned: stage sizes are multiples of 8 KB)
+  const int stage_bytes = KCH * Cfg::STAGE_BYTES;           // a stage holds KCH consecutive 64-deep k-chunks (one barrier round trip)
+  uint8_t* stg_base = smem + STAGES * stage_bytes;          // epilogue region (1024-byte aligned: chunk sizes are multiples of 8 KB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + epi_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator stage ready for the epilogue
@@ -227,43 +228,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // One elected lane owns the barriers and issues the TMA boxes of a stage (KCH chunks x {A boxes, B boxes}).
+    // (Issuing the boxes from several lanes of one instruction was measured 2x SLOWER: UTMALDG takes uniform
+    // operands, so divergent per-lane operands are serialised through a per-lane uniform-register loop.)
     if (lane == 0) {
+      constexpr int A_BOXES = (MODE == 1) ? BM / 64 : 1;
+      constexpr int B_BOXES = (MODE == 0) ? 1 : BN / CG / 64;
       int s = 0;        // smem ring position / phase, carried across tiles
       uint32_t ph = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
-        for (int i = 0; i < t.n_iters; ++i) {
+        for (int i = 0; i < t.n_iters; i += KCH) {
+          const int nch = min(KCH, t.n_iters - i);
+          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[s]), 0) : 0u;   // pair: bytes are credited to the LEADER
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          // both CTAs of a pair credit their bytes to the LEADER's full barrier
-          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[s]), 0) : 0u;
-          if (CG == 2) mbar_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
-          else mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (CG == 2) mbar_expect_tx_cluster(fb, nch * Cfg::STAGE_BYTES);
+          else mbar_expect_tx(&full_bar[s], nch * Cfg::STAGE_BYTES);
           auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
             if (CG == 2) tma_load_2d_2sm(dst, map, fb, c0, c1);
             else tma_load_2d(dst, map, &full_bar[s], c0, c1);
           };
-          const int kit = t.it_begin + i;
-          if (MODE == 1) {
-            int shift = 0;
-            if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
-            const int p = kit * BK;
+          // the producer thread is issue-bound: per-chunk index math is done once, box loops are fully unrolled
+          int kit = t.it_begin + i;
+          int tp = 0, kc = kit;
+          if (MODE != 1 && ntaps > 1) { tp = kit / kc_per_tap; kc = kit - tp * kc_per_tap; }
+          for (int ch = 0; ch < nch; ++ch, ++kit) {
+            uint8_t* sa = smem + s * stage_bytes + ch * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            if (MODE == 1) {
+              int shift = 0;
+              if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
+              const int p = kit * BK;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmA, t.m0 + j * 64, p);
+              for (int j = 0; j < A_BOXES; ++j) load(sa + j * (BK * 128), &tmA, t.m0 + j * 64, p);
 #pragma unroll
-            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * (BK * 128), &tmB, t.nb0 + j * 64, p + shift);
-          } else {
-            const int tp = kit / kc_per_tap;
-            const int kc = kit - tp * kc_per_tap;
-            int shift = 0;
-            if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
-            load(sa, &tmA, kc * BK, t.m0 + shift);
-            if (MODE == 0) {
-              load(sb, &tmB, tp * K + kc * BK, t.nb0);
+              for (int j = 0; j < B_BOXES; ++j) load(sb + j * (BK * 128), &tmB, t.nb0 + j * 64, p + shift);
             } else {
+              int shift = 0;
+              if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
+              load(sa, &tmA, kc * BK, t.m0 + shift);
+              if (MODE == 0) {
+                load(sb, &tmB, tp * K + kc * BK, t.nb0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * (BK * 128), &tmB, tp * N + t.nb0 + j * 64, kc * BK);
+                for (int j = 0; j < B_BOXES; ++j) load(sb + j * (BK * 128), &tmB, tp * N + t.nb0 + j * 64, kc * BK);
+              }
+              if (++kc == kc_per_tap) { kc = 0; ++tp; }
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -286,21 +296,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int i = 0; i < t.n_iters; ++i) {
+        for (int i = 0; i < t.n_iters; i += KCH) {
+          const int nch = min(KCH, t.n_iters - i);
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (i == 0 && local == 0) dbg_stamp(epi, 4);
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes + ch * Cfg::STAGE_BYTES);
+            const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t ad, bd;
-            if (MODE == 1) ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
-            else ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-            if (MODE == 0) bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
-            else bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
-            if (CG == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              uint64_t ad, bd;
+              if (MODE == 1) ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
+              else ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+              if (MODE == 0) bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+              else bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
+              const uint32_t accum = (i > 0 || ch > 0 || k > 0) ? 1u : 0u;
+              if (CG == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
+              else umma_bf16(d_tmem, ad, bd, idesc, accum);
+            }
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
           if (CG == 2) umma_commit_2sm(&empty_bar[s], 3);
@@ -631,6 +645,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 }
 
 static long long* g_gemm_timeline = nullptr;
+static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
+static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
 
 static int sm_count() {
   static int n = 0;
@@ -689,7 +705,8 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     if (!tc || (d.residual && !tr) || (d.aux && !tx)) return CB_ERR_CUDA;
     // four output buffers (three TMA stores in flight) unless that would starve the operand ring
     const int io_bytes = 2 * CHUNK_BYTES * ((d.residual ? 1 : 0) + (d.aux ? 1 : 0));
-    n_cbuf = ((SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - io_bytes - 4 * CHUNK_BYTES) / Cfg::STAGE_BYTES >= 3) ? 4 : 2;
+    // two output buffers: measured equal to four (profiles/r01_gemm_kch_probe.txt), and the operand ring needs the room
+    n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
     epi_bytes = n_cbuf * CHUNK_BYTES + io_bytes;
   } else {
     epi_bytes = EPI_WARPS * STG_BYTES;
@@ -698,20 +715,30 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   if (!tc) tc = ta;   // unused placeholders (a __grid_constant__ parameter must still be a valid object)
   if (!tr) tr = ta;
   if (!tx) tx = ta;
-  int stages = (SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - epi_bytes) / Cfg::STAGE_BYTES;
+  // chunks (64-deep k slices) that fit beside the epilogue buffers; a stage groups KCH of them under one barrier
+  // round trip (fewer, larger transactions for deep K loops), keeping >= 3 stages in flight
+  const int chunks_fit = (SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - epi_bytes) / Cfg::STAGE_BYTES;
+  // Measured (profiles/r01_gemm_kch_probe.txt): each stage costs a ~400-cycle barrier round trip whatever its size,
+  // so deep stages beat many stages: 1312x768x3072 takes 26.5 / 18.3 / 15.8 us with 1 / 2 / 4 chunks per stage.
+  int kch = 1;
+  if (g_force_kch > 0) kch = g_force_kch;
+  else if (kiters >= 4 && chunks_fit >= 8) kch = 4;
+  else if (kiters >= 2 && chunks_fit >= 4) kch = 2;
+  if (kch > kiters) kch = kiters;
+  int stages = chunks_fit / kch;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > kiters + 1 && kiters + 1 >= 2) stages = kiters + 1 > 2 ? kiters + 1 : 2;   // no point in a ring deeper than the K loop
+  const int stage_iters = ceil_div(kiters, kch);
+  if (stages > stage_iters + 1) stages = stage_iters + 1 > 2 ? stage_iters + 1 : 2;   // no point in a ring deeper than the K loop
   if (stages < 2) {
     set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B)", BN, epi_bytes);
     return CB_ERR_INVALID;
   }
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  const int smem_bytes = stages * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
+  const int smem_bytes = stages * kch * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
   const int units = sm_count() / CG;
   const int grid = (total < units ? total : units) * CG;
   if (CG == 1) {
     kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-                                                      iters_per_split, tiles_m, tiles_n, total, stages, epi_bytes, n_cbuf, epi);
+                                                      iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -726,7 +753,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
-                                       tiles_m, tiles_n, total, stages, epi_bytes, n_cbuf, epi);
+                                       tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
     if (e != cudaSuccess) {
       set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return CB_ERR_CUDA;
@@ -785,6 +812,8 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
 
 /* bring-up / tuning hook (not part of the public header): device buffer of >= 16 int64 receiving clock64() stamps of CTA 0 */
 extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline = static_cast<long long*>(device_buf); }
+extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
+extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;

@@ -22,11 +22,15 @@ def allreduce_flat(grads, group=None, average=True, async_op=False):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return []
     ws = dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
     works = []
     for g in grads:
-        if average:
-            g.mul_(1.0 / ws)
-        works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+        if average and nccl:
+            works.append(dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group, async_op=async_op))   # one pass, 1/N inside NCCL
+        else:
+            if average:
+                g.mul_(1.0 / ws)
+            works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
     return works
 
 
@@ -87,6 +91,28 @@ class ClipBert(nn.Module):
             if m._flat is not None and m._flat.grad is not None:
                 m._flat.grad.zero_()
 
+    def enable_overlapped_allreduce(self, group=None, average=True):
+        """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
+        outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
+        (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
+        the CNN buffer and joins. Safe inside CUDA-graph capture (ProcessGroupNCCL forks/joins its stream)."""
+        self._dp = dict(group=group, average=average, works=[])
+
+        def hook(flat_grad):
+            self._dp["works"] += allreduce_flat([flat_grad], group, average, async_op=True)
+        self.transformer._grad_ready_hook = hook
+
     def allreduce_grads(self, group=None, average=True, async_op=False):
-        """Sum (average) the two flat fp32 gradient buffers over the data-parallel group (NCCL)."""
-        return allreduce_flat(self.flat_grads(), group, average, async_op)
+        """Average the flat fp32 gradient buffers over the data-parallel group (NCCL) - the replacement of
+        ``optimizer.synchronize()`` (src/tasks/run_video_retrieval.py:432)."""
+        dp = getattr(self, "_dp", None)
+        if dp is None:
+            return allreduce_flat(self.flat_grads(), group, average, async_op)
+        works, dp["works"] = dp["works"], []
+        if not works:                      # hook did not fire (e.g. transformer frozen): exchange everything now
+            works = allreduce_flat(self.flat_grads(), dp["group"], dp["average"], async_op=True)
+        elif self.cnn._flat is not None and self.cnn._flat.grad is not None:
+            works += allreduce_flat([self.cnn._flat.grad], dp["group"], dp["average"], async_op=True)
+        for w in works:
+            w.wait()
+        return []

@@ -138,6 +138,8 @@ class GridFeatBackbone(nn.Module):
         self._bn = None
         self._dirty = True
         self._capture = None     # tests set this to a dict to receive per-stage activations
+        self._segments = None
+        self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
         # d2 FREEZE_AT: stem (1) and res2 (2) get no gradient
         bb = self.feature.backbone
@@ -213,6 +215,8 @@ class GridFeatBackbone(nn.Module):
             self._bn_scale = torch.empty(ctot, dtype=torch.float32, device=device)
             self._bn_shift = torch.empty(ctot, dtype=torch.float32, device=device)
             self._stem_w = torch.zeros(64, STEM_KP, dtype=torch.bfloat16, device=device)
+            self._segments = None
+            self._pad_pool = {}
             self._dirty = True
         if self._dirty or self._flat.needs_repack():
             self._repack()
@@ -227,22 +231,37 @@ class GridFeatBackbone(nn.Module):
         self._bn_scale.mul_(b["weight"])
         torch.addcmul(b["bias"], b["running_mean"], self._bn_scale, value=-1.0, out=self._bn_shift)
         flat = self._flat
+        if self._segments is None:
+            rows = []
+            for name, m in self._convs():
+                e = m._e
+                rows.append([e["offset"], e["numel"], m.k * m.k * m.cin, m._bn_off if hasattr(m, "norm") else -1])
+            self._segments = torch.tensor(rows, dtype=torch.int64, device=flat.master.device)
+        ops.cast_scale_segments(flat.master, flat.packed, self._segments, self._bn_scale)     # all 54 convs, one launch
         for name, m in self._convs():
             e = m._e
             n = e["numel"]
             row_len = m.k * m.k * m.cin
             if hasattr(m, "norm"):
-                sc = self._bn_scale[m._bn_off: m._bn_off + m.cout]
-                m._scale, m._shift = sc, self._bn_shift[m._bn_off: m._bn_off + m.cout]
+                m._scale, m._shift = self._bn_scale[m._bn_off: m._bn_off + m.cout], self._bn_shift[m._bn_off: m._bn_off + m.cout]
             else:
-                sc = None
                 m._scale = m._shift = None
-            ops.cast_scale(flat.master[e["offset"]: e["offset"] + n], flat.packed[e["offset"]: e["offset"] + n], sc, row_len)
             m._w = flat.packed[e["offset"]: e["offset"] + n].view(m.cout, row_len)
             m._gw = flat.grad[e["offset"]: e["offset"] + n].view(m.cout, row_len)
         stem = self.feature.backbone.stem.conv1
         self._stem_w[:, :147] = stem._w      # [64, (r,s,c)] -> row pitch 152
         stem._w = self._stem_w
+
+    # ---- zero-bordered buffers --------------------------------------------------------------------
+    # Only interior rows of a padded activation are ever written (CB_ROWMAP_PAD epilogues), so a buffer that was
+    # zeroed once keeps a valid zero border for its whole life: recycle instead of re-zeroing every step.
+    def _pad_get(self, rows, ch, device):
+        lst = self._pad_pool.setdefault((rows, ch), [])
+        return lst.pop() if lst else torch.zeros(rows, ch, dtype=torch.bfloat16, device=device)
+
+    def _pad_put(self, t):
+        if t is not None:
+            self._pad_pool.setdefault((t.shape[0], t.shape[1]), []).append(t)
 
     # ---- forward ----------------------------------------------------------------------------------
     def forward(self, x):
@@ -322,15 +341,17 @@ class GridFeatBackbone(nn.Module):
                     xs = x_in
                 rows = n * hh * ww
                 sc = self._conv1x1(blk.shortcut, xs, rows, ops.ACT_NONE) if blk.has_shortcut else xs
-                a_pad = torch.zeros(n * (hh + 2) * (ww + 2), blk.mid, dtype=bf16, device=dev)
+                a_pad = self._pad_get(n * (hh + 2) * (ww + 2), blk.mid, dev)
                 self._conv1x1(blk.conv1, xs, rows, ops.ACT_RELU, rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=a_pad)
                 b = self._conv3x3(blk.conv2, a_pad, n, hh, ww, ops.ACT_RELU)
                 if last:
-                    y = torch.zeros(n * (hh + 2) * (ww + 2), blk.cout, dtype=bf16, device=dev)
+                    y = self._pad_get(n * (hh + 2) * (ww + 2), blk.cout, dev)
                     self._conv1x1(blk.conv3, b, rows, ops.ACT_RELU, residual=sc, rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=y)
                 else:
                     y = self._conv1x1(blk.conv3, b, rows, ops.ACT_RELU, residual=sc)
                 trainable = blk.conv1.weight.requires_grad
+                if not (need_backward and trainable):
+                    self._pad_put(a_pad)            # consumed by conv2 above; stream order makes the reuse safe
                 if need_backward and trainable:
                     blocks.append(dict(name="%s.%d" % (name, bi), blk=blk, x_in=x_in, xs=xs, a_pad=a_pad, b=b, y=y, h=hh, w=ww, h_in=h_in, w_in=w_in,
                                        first_trainable=not blocks))
@@ -344,6 +365,8 @@ class GridFeatBackbone(nn.Module):
         grid = torch.empty(bsz, n_frms, gh, gw, ge.cout, dtype=bf16, device=dev)
         ops.maxpool2x2_relu_fwd(gconv, grid, n, hh, ww, ge.cout)
         stash = None
+        if not need_backward:
+            self._pad_put(cur)                      # res5 output (padded), consumed by the grid_encoder conv
         if need_backward:
             stash = dict(n=n, h=hh, w=ww, res5_pad=cur, gconv=gconv, blocks=blocks)
             if self._capture is not None:
@@ -394,21 +417,24 @@ class GridFeatBackbone(nn.Module):
             self._wgrad(ge, dg_pad, stash["res5_pad"], p, ntaps=9, tap_w=w + 2)
         blocks = stash["blocks"]
         if not blocks:
+            self._pad_put(stash["res5_pad"])
             self._dirty = True
             return
         # grad w.r.t. the pre-ReLU output of the last block, compact
         g = self._dgrad3x3(ge, dg_pad, n, h, w, stash["res5_pad"])
         del dg_pad
+        self._pad_put(stash["res5_pad"])
         for st in reversed(blocks):
             blk, hh, ww = st["blk"], st["h"], st["w"]
             rows = n * hh * ww
             pp = n * (hh + 2) * (ww + 2)
             self._wgrad(blk.conv3, g, st["b"], rows)
-            db_pad = torch.zeros(pp, blk.mid, dtype=bf16, device=dev)
+            db_pad = self._pad_get(pp, blk.mid, dev)
             self._dgrad1x1(blk.conv3, g, rows, aux=st["b"], rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=db_pad)
             self._wgrad(blk.conv2, db_pad, st["a_pad"], pp, ntaps=9, tap_w=ww + 2)
             da = self._dgrad3x3(blk.conv2, db_pad, n, hh, ww, st["a_pad"])
-            del db_pad
+            self._pad_put(db_pad)
+            self._pad_put(st["a_pad"])
             self._wgrad(blk.conv1, da, st["xs"], rows)
             if blk.has_shortcut:
                 self._wgrad(blk.shortcut, g, st["xs"], rows)

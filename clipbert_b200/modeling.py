@@ -145,6 +145,7 @@ class _TransformerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, grid, anchor, ids, mask, repeat):
         out, stash = module._forward_impl(ids, grid, mask, repeat, need_backward=True)
+        module._pending_backward += 1
         ctx.module, ctx.stash = module, stash
         ctx.grid_needs_grad = grid.requires_grad
         return out
@@ -152,7 +153,11 @@ class _TransformerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *douts):
         stash, ctx.stash = ctx.stash, None
-        dgrid = ctx.module._backward_impl(stash, douts if len(douts) > 1 else douts[0], ctx.grid_needs_grad)
+        m = ctx.module
+        dgrid = m._backward_impl(stash, douts if len(douts) > 1 else douts[0], ctx.grid_needs_grad)
+        m._pending_backward = max(0, m._pending_backward - 1)
+        if m._pending_backward == 0 and m._grad_ready_hook is not None:
+            m._grad_ready_hook(m._flat.grad)          # every clip's contribution is in: the exchange may start
         return None, dgrid, None, None, None, None
 
 
@@ -169,6 +174,8 @@ class _ClipBertHeadModel(nn.Module):
         self._call_count = 0
         self._seed_base = None
         self._capture = None     # tests set this to a dict to receive per-layer activations
+        self._pending_backward = 0
+        self._grad_ready_hook = None
 
     # ---- flat parameter storage -------------------------------------------------------------------
     def _head_linears(self):

@@ -27,6 +27,7 @@ _SIGS = {
     "cb_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "cb_cast_scale_segments": [_vp, _vp, _vp, _i, _vp, _vp],
     "cb_attention_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_stem_im2col": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
@@ -181,6 +182,10 @@ def pad_cast(src, dst):
 
 def cast_scale(src, dst, rowscale=None, row_len=1):
     _call("cb_cast_scale", _p(src), _p(rowscale), row_len, _p(dst), src.numel(), _s())
+
+
+def cast_scale_segments(master, packed, segments, scales):
+    _call("cb_cast_scale_segments", _p(master), _p(packed), _p(segments), segments.shape[0], _p(scales), _s())
 
 
 def attention_fwd(qkv, text_mask, ctx, lse, nseq, l, lt, heads, p, seed):
