@@ -466,23 +466,37 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_reduce_kernel(const floa
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients): db[n] += sum_m dY[m, n]
 // ------------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int M, int N,
-                              int rows_per_block) {
-  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 columns
-  if (c8 * 8 >= N) return;
-  const int m0 = blockIdx.y * rows_per_block;
-  const int m1 = min(M, m0 + rows_per_block);
+// block = 8 warps x 32 lanes: a lane owns 8 columns (one 128-bit load per row), warps stride the rows of a
+// 128-row slab; partials are combined across warps in smem so that each block issues ONE atomic per column
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int M,
+                                                     int N) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int m0 = blockIdx.y * 128;
+  const int m1 = min(M, m0 + 128);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int m = m0; m < m1; ++m) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + c8 * 8);
-    float2 t;
-    t = unpack_bf16x2(u.x); acc[0] += t.x; acc[1] += t.y;
-    t = unpack_bf16x2(u.y); acc[2] += t.x; acc[3] += t.y;
-    t = unpack_bf16x2(u.z); acc[4] += t.x; acc[5] += t.y;
-    t = unpack_bf16x2(u.w); acc[6] += t.x; acc[7] += t.y;
+  if (col < N) {
+#pragma unroll 4
+    for (int m = m0 + warp; m < m1; m += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + col);
+      float2 t;
+      t = unpack_bf16x2(u.x); acc[0] += t.x; acc[1] += t.y;
+      t = unpack_bf16x2(u.y); acc[2] += t.x; acc[3] += t.y;
+      t = unpack_bf16x2(u.z); acc[4] += t.x; acc[5] += t.y;
+      t = unpack_bf16x2(u.w); acc[6] += t.x; acc[7] += t.y;
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + c8 * 8 + j, acc[j]);
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;           // 256 threads <-> 256 columns
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,7 +614,8 @@ int cb_layernorm_bwd(const void* dy, const void* x, const float* stats, const fl
                      uint64_t dropout_seed, void* stream) {
   CB_REQUIRE(hidden == HID, "cb_layernorm_bwd: hidden size %d unsupported", hidden);
   CB_REQUIRE(dy && x && stats && gamma && dx && m > 0, "cb_layernorm_bwd: bad arguments");
-  const int blocks = min(ceil_div(m, ROWS_PER_BLOCK), 148 * 4);
+  // the dgamma / dbeta / dbias atomics contend once per block and column: a few rows per warp, not one
+  const int blocks = max(1, min(ceil_div(m, ROWS_PER_BLOCK), 148 * 2));
   ln_bwd_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), stats, gamma,
       static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, dbias_drop, m,
@@ -671,16 +686,8 @@ int cb_embed_visual_bwd(const void* dh, const void* grid, const int32_t* seq2vid
 
 int cb_colsum(const void* x, int64_t ld, float* out, int m, int n, void* stream) {
   CB_REQUIRE(x && out && m > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "cb_colsum: bad arguments (n, ld must be multiples of 8)");
-  const int groups = n / 8;
-  const int threads = groups < 128 ? ((groups + 31) / 32) * 32 : 128;
-  // enough row blocks to cover the 148 SMs a few times over; each thread keeps 8 column sums in registers
-  const int col_blocks = ceil_div(groups, threads);
-  int rows_per_block = ceil_div(static_cast<int64_t>(m) * col_blocks, 148 * 4);
-  if (rows_per_block < 8) rows_per_block = 8;
-  if (rows_per_block > 64) rows_per_block = 64;
-  dim3 grid(col_blocks, ceil_div(m, rows_per_block));
-  colsum_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, out, m, n,
-                                                                          rows_per_block);
+  dim3 grid(ceil_div(n, 256), ceil_div(m, 128));
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, out, m, n);
   return check_launch("cb_colsum");
 }
 

@@ -26,35 +26,43 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // 7x7/s2/p3 patches, K index = (r*7 + s)*3 + c with c in BGR order (the x[:, [2,1,0]] flip of
 // grid_feat.py:92-94 is folded into the gather). KP = 152 (147 zero-padded to a multiple of 8).
 // ------------------------------------------------------------------------------------------------
+// One block per (image, output row): the 7 input rows x 3 planes it needs are staged once in shared memory
+// (coalesced row reads, mean subtraction + bf16 rounding applied there, zero padding materialised), then the
+// 19 x Wo 128-bit patch chunks of that output row are written fully coalesced.
 template <typename TIn>
-__global__ void stem_im2col_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Ho,
-                                   int Wo, int KP, float m0, float m1, float m2) {
-  const int chunks = KP / 8;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * chunks;
-  if (t >= total) return;
-  const int chunk = static_cast<int>(t % chunks);
-  const int64_t pix = t / chunks;
-  const int ox = static_cast<int>(pix % Wo);
-  const int oy = static_cast<int>((pix / Wo) % Ho);
-  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wo) * Ho));
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+                                                          int Ho, int Wo, int KP, float m0, float m1, float m2) {
+  extern __shared__ __nv_bfloat16 srow[];          // [7 rows][3 planes][W + 6]
+  const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int WP = W + 6;
   const float mean_rgb[3] = {m0, m1, m2};
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = chunk * 8 + j;
-    float val = 0.f;
-    if (k < 147) {
-      const int c = k % 3, rs = k / 3, s = rs % 7, r = rs / 7;
-      const int iy = oy * 2 - 3 + r, ix = ox * 2 - 3 + s;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        const int cin = 2 - c;  // BGR channel c reads RGB channel 2-c
-        val = static_cast<float>(x[((static_cast<int64_t>(n) * 3 + cin) * H + iy) * W + ix]) - mean_rgb[cin];
-      }
-    }
-    f[j] = val;
+  for (int i = threadIdx.x; i < 21 * WP; i += blockDim.x) {
+    const int xp = i % WP, rp = i / WP;            // rp = r * 3 + plane
+    const int plane = rp % 3, r = rp / 3;
+    const int iy = oy * 2 - 3 + r, ix = xp - 3;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = static_cast<float>(x[((static_cast<int64_t>(n) * 3 + plane) * H + iy) * W + ix]) - mean_rgb[plane];
+    srow[i] = __float2bfloat16(v);
   }
-  *reinterpret_cast<uint4*>(out + pix * KP + chunk * 8) = pack8(f);
+  __syncthreads();
+  const int chunks = KP / 8;
+  __nv_bfloat16* orow = out + (static_cast<int64_t>(n) * Ho + oy) * Wo * KP;
+  for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
+    const int chunk = i % chunks, ox = i / chunks;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = chunk * 8 + j;
+      __nv_bfloat16 val = __float2bfloat16(0.f);
+      if (k < 147) {
+        const int c = k % 3, rs = k / 3, sx = rs % 7, r = rs / 7;
+        val = srow[(r * 3 + (2 - c)) * WP + ox * 2 + sx];     // BGR channel c reads RGB plane 2-c
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<uint4*>(orow + static_cast<int64_t>(ox) * KP + chunk * 8) = *reinterpret_cast<const uint4*>(v);
+  }
 }
 
 // 3x3 stride-2 pad-1 max pool, NHWC
@@ -217,14 +225,15 @@ int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, 
   CB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "cb_stem_im2col: bad arguments");
   CB_REQUIRE(kp >= 152 && kp % 8 == 0, "cb_stem_im2col: kp must be a multiple of 8 and >= 152");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
-  const int64_t total = static_cast<int64_t>(n) * ho * wo * (kp / 8);
+  const int smem = 21 * (w + 6) * 2;
+  CB_REQUIRE(smem <= 48 * 1024, "cb_stem_im2col: frame width %d too large for the row staging buffer", w);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0)
-    stem_im2col_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n,
-                                                                    h, w, ho, wo, kp, mean_r, mean_g, mean_b);
+    stem_im2col_kernel<float><<<n * ho, 256, smem, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo, kp,
+                                                         mean_r, mean_g, mean_b);
   else if (in_dtype == 1)
-    stem_im2col_kernel<uint8_t><<<ceil_div(total, 256), 256, 0, st>>>(static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out),
-                                                                      n, h, w, ho, wo, kp, mean_r, mean_g, mean_b);
+    stem_im2col_kernel<uint8_t><<<n * ho, 256, smem, st>>>(static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo,
+                                                           kp, mean_r, mean_g, mean_b);
   else
     CB_REQUIRE(false, "cb_stem_im2col: in_dtype must be 0 (fp32) or 1 (uint8)");
   return check_launch("cb_stem_im2col");
