@@ -407,11 +407,21 @@ static int set_smem(K kern, int bytes) {
   return CB_OK;
 }
 
+// tensor-core fast path for l <= 64 (attention_tc.cu)
+int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,
+                     int heads, float dropout_p, uint64_t seed, cudaStream_t stream);
+int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
+                     const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
+                     cudaStream_t stream);
+int g_attention_force_general = 0;   // test knob: 1 = always use the general (any L) kernels
+
 }  // namespace cb
 
 using namespace cb;
 
 extern "C" {
+
+void cb_debug_attention_general(int on) { cb::g_attention_force_general = on; }
 
 /* qkv: bf16 [nseq*L, 3*heads*64] (Q | K | V); text_mask: int64 [nseq, Lt]; ctx: bf16 [nseq*L, heads*64];
  * lse: fp32 [nseq, heads, L] (saved for the backward; may be NULL for inference). */
@@ -420,6 +430,8 @@ int cb_attention_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   CB_REQUIRE(head_dim == HD, "cb_attention_fwd: head_dim %d unsupported (built for 64)", head_dim);
   CB_REQUIRE(qkv && text_mask && ctx && nseq > 0 && l > 0 && lt >= 0 && lt <= l && heads > 0, "cb_attention_fwd: bad arguments");
   CB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0, "cb_attention_fwd: row pitches must be multiples of 8");
+  if (l <= 64 && !g_attention_force_general)
+    return attention_tc_fwd(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, static_cast<cudaStream_t>(stream));
   static bool once = false;
   const int smem = 4 * TILE_FLOATS * sizeof(float);
   if (!once) {
@@ -442,6 +454,9 @@ int cb_attention_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   CB_REQUIRE(head_dim == HD, "cb_attention_bwd: head_dim %d unsupported (built for 64)", head_dim);
   CB_REQUIRE(qkv && text_mask && ctx && dctx && lse && dqkv && nseq > 0 && l > 0, "cb_attention_bwd: bad arguments");
   CB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0 && ld_dqkv % 8 == 0, "cb_attention_bwd: row pitches must be multiples of 8");
+  if (l <= 64 && !g_attention_force_general)
+    return attention_tc_bwd(qkv, ld_qkv, text_mask, ctx, dctx, ld_ctx, lse, dqkv, ld_dqkv, nseq, l, lt, heads, dropout_p, seed,
+                            static_cast<cudaStream_t>(stream));
   static bool once = false;
   const int smem_kv = (6 * TILE_FLOATS + 2 * TS) * sizeof(float);
   const int smem_q = (5 * TILE_FLOATS + 2 * TS) * sizeof(float);

@@ -1,0 +1,369 @@
+// Tensor-core fast path of the fused self-attention for short sequences (L <= 64: every ClipBERT training
+// configuration at 224 px, L = Lt + 9). One CTA = one (sequence, head); 4 warps x 16 query rows; Q, K, V (and dO)
+// tiles live in shared memory as bf16, the 64x64x64 products run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate)
+// with ldmatrix operand fetches, softmax / dropout / dS stay in the accumulator registers (the S accumulator
+// layout is reused as the A operand of the next product). Same math, masks, dropout stream and lse convention as
+// csrc/attention.cu, which remains the path for L > 64 (448 px frames, 512-token inference).
+//
+// Why mma.sync and not tcgen05 here: a (sequence, head) problem is 41x41x64 - 0.9 % of the layer FLOPs; it is
+// latency-bound, and a tcgen05 pipeline (TMEM allocation, 128-row UMMA tiles, mbarrier hand-offs) costs more than
+// the whole product. All GEMM-shaped work of the path runs on tcgen05 (csrc/gemm.cu).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace cb {
+
+constexpr int TC_LD = 72;                 // bf16 elements per smem row (144 B: 16 B aligned, conflict-free ldmatrix)
+constexpr int TC_TILE = 64 * TC_LD;       // elements per 64-row tile
+constexpr int TC_THREADS = 128;
+
+struct TcDrop {
+  uint32_t thresh;
+  float inv_keep;
+  uint64_t seed;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// global [rows, 64] bf16 (row pitch ld) -> smem tile [64][TC_LD], rows >= nrows zero-filled
+__device__ __forceinline__ void tc_load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nrows) {
+  for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < nrows) u = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * TC_LD + c) = u;
+  }
+}
+__device__ __forceinline__ void tc_store_tile(const __nv_bfloat16* src, __nv_bfloat16* dst, int64_t ld, int nrows) {
+  for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    if (r < nrows) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * ld + c) = *reinterpret_cast<const uint4*>(src + r * TC_LD + c);
+  }
+}
+
+// acc[j][4] (j = 8-wide column tile) = A(16 x 64 rows r0.. of As) * B^T where B rows are the OUTPUT columns
+// (B stored [n][k] row-major, e.g. S = Q K^T with Bs = K, or dP = dO V^T with Bs = V)
+__device__ __forceinline__ void tc_mm_abt(float (&acc)[8][4], const __nv_bfloat16* As, const __nv_bfloat16* Bs, int r0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, As + (r0 + (lane & 15)) * TC_LD + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {     // two 8-column tiles per ldmatrix.x4
+      uint32_t b[4];
+      ldsm_x4(b, Bs + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * TC_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma16816(acc[2 * jp], a, b[0], b[1]);
+      mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+}
+// acc += A(16 x 64, given as register fragments afrag[ks]) * B where B is stored [k][n] row-major (e.g. O = P V, dQ = dS K)
+__device__ __forceinline__ void tc_mm_ab_reg(float (&acc)[8][4], const uint32_t (&afrag)[4][4], const __nv_bfloat16* Bs, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t b[4];
+      ldsm_x4_t(b, Bs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * TC_LD + jp * 16 + (lane >> 4) * 8);
+      mma16816(acc[2 * jp], afrag[ks], b[0], b[1]);
+      mma16816(acc[2 * jp + 1], afrag[ks], b[2], b[3]);
+    }
+  }
+}
+// acc = A^T-stored (As holds [k][m]: out rows m0.. come from As COLUMNS) * B ([k][n] row-major): dV = Pd^T dO, dK = dS^T Q
+__device__ __forceinline__ void tc_mm_atb(float (&acc)[8][4], const __nv_bfloat16* As, const __nv_bfloat16* Bs, int m0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    const int mi = lane >> 3;
+    ldsm_x4_t(a, As + (ks * 16 + (lane & 7) + (mi >> 1) * 8) * TC_LD + m0 + (mi & 1) * 8);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t b[4];
+      ldsm_x4_t(b, Bs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * TC_LD + jp * 16 + (lane >> 4) * 8);
+      mma16816(acc[2 * jp], a, b[0], b[1]);
+      mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+}
+// write a 16 x 64 accumulator (rows r0 + lane/4, +8) as bf16 into a smem tile
+__device__ __forceinline__ void tc_acc_to_smem(const float (&acc)[8][4], __nv_bfloat16* dst, int r0, int lane, float mul) {
+  const int r = r0 + (lane >> 2), c = 2 * (lane & 3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(dst + r * TC_LD + j * 8 + c) = pack_bf16x2(acc[j][0] * mul, acc[j][1] * mul);
+    *reinterpret_cast<uint32_t*>(dst + (r + 8) * TC_LD + j * 8 + c) = pack_bf16x2(acc[j][2] * mul, acc[j][3] * mul);
+  }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                 const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
+                                                                 const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
+                                                                 int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
+                                                                 TcDrop dc) {
+  extern __shared__ __align__(16) uint8_t tc_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* Ks = Qs + TC_TILE;
+  __nv_bfloat16* Vs = Ks + TC_TILE;
+  float* madd = reinterpret_cast<float*>(Vs + TC_TILE);     // [64] additive key mask (-inf beyond L)
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = static_cast<int64_t>(b) * L;
+  tc_load_tile(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
+  if (threadIdx.x < 64) {
+    const int j = threadIdx.x;
+    float m = -INFINITY;
+    if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
+    madd[j] = m;
+  }
+  __syncthreads();
+  const int r0 = warp * 16;
+  float s[8][4];
+  tc_mm_abt(s, Qs, Ks, r0, lane);
+  const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m0 = madd[j * 8 + cq], m1 = madd[j * 8 + cq + 1];
+    s[j][0] = s[j][0] * scale + m0; s[j][1] = s[j][1] * scale + m1;
+    s[j][2] = s[j][2] * scale + m0; s[j][3] = s[j][3] * scale + m1;
+    mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+  }
+  mx0 = quad_max(mx0);
+  mx1 = quad_max(mx1);
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pf[4][4];     // P as A fragments for the P V product
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float p0 = __expf(s[j][0] - mx0), p1 = __expf(s[j][1] - mx0), p2 = __expf(s[j][2] - mx1), p3 = __expf(s[j][3] - mx1);
+    sum0 += p0 + p1;
+    sum1 += p2 + p3;
+    if (dc.thresh) {
+      const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + rq) * L + j * 8 + cq;
+      const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
+      p0 *= dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
+      p1 *= dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
+      p2 *= dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
+      p3 *= dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+    }
+    pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+    pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  sum0 = quad_sum(sum0);
+  sum1 = quad_sum(sum1);
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+  tc_mm_ab_reg(o, pf, Vs, lane);
+  const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] *= i0; o[j][1] *= i0; o[j][2] *= i1; o[j][3] *= i1; }
+  if (lse && (lane & 3) == 0) {
+    float* lrow = lse + (static_cast<int64_t>(b) * H + h) * L;
+    if (rq < L) lrow[rq] = mx0 + __logf(sum0);
+    if (rq + 8 < L) lrow[rq + 8] = mx1 + __logf(sum1);
+  }
+  __syncthreads();                       // everyone is done reading Qs: reuse it to stage the output
+  tc_acc_to_smem(o, Qs, r0, lane, 1.0f);
+  __syncthreads();
+  tc_store_tile(Qs, ctx + row0 * ld_ctx + h * 64, ld_ctx, L);
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                 const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
+                                                                 const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
+                                                                 const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx,
+                                                                 const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
+                                                                 __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv,
+                                                                 int L, int Lt, int H, float scale, TcDrop dc) {
+  extern __shared__ __align__(16) uint8_t tc_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* Ks = Qs + TC_TILE;
+  __nv_bfloat16* Vs = Ks + TC_TILE;
+  __nv_bfloat16* dOs = Vs + TC_TILE;
+  __nv_bfloat16* Ps = dOs + TC_TILE;     // dropped probabilities [query][key]
+  __nv_bfloat16* dSs = Ps + TC_TILE;     // dS [query][key]
+  float* madd = reinterpret_cast<float*>(dSs + TC_TILE);
+  float* Dv = madd + 64;                 // D_i = sum_d dO[i][d] O[i][d]
+  float* lses = Dv + 64;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = static_cast<int64_t>(b) * L;
+  tc_load_tile(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile(dOs, dctx + row0 * ld_ctx + h * 64, ld_ctx, L);
+  if (threadIdx.x < 64) {
+    const int j = threadIdx.x;
+    float m = -INFINITY;
+    if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
+    madd[j] = m;
+    lses[j] = j < L ? lse[(static_cast<int64_t>(b) * H + h) * L + j] : 0.f;
+  }
+  // D_i: 8 threads per row, 16 rows per pass
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 16 + (threadIdx.x >> 3), c = (threadIdx.x & 7) * 8;
+    float acc = 0.f;
+    if (r < L) {
+      const uint4 uo = *reinterpret_cast<const uint4*>(ctx + (row0 + r) * ld_ctx + h * 64 + c);
+      const uint4 ud = *reinterpret_cast<const uint4*>(dctx + (row0 + r) * ld_ctx + h * 64 + c);
+      const uint32_t ov[4] = {uo.x, uo.y, uo.z, uo.w}, dvv[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack_bf16x2(ov[e]), d = unpack_bf16x2(dvv[e]);
+        acc += a.x * d.x + a.y * d.y;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((threadIdx.x & 7) == 0) Dv[r] = acc;
+  }
+  __syncthreads();
+  // ---- phase 1: this warp's 16 query rows: S, P, dP, dS, dQ ----
+  const int r0 = warp * 16;
+  const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
+  float s[8][4], dp[8][4];
+  tc_mm_abt(s, Qs, Ks, r0, lane);
+  tc_mm_abt(dp, dOs, Vs, r0, lane);
+  const float l0 = lses[rq], l1 = lses[rq + 8], D0 = Dv[rq], D1 = Dv[rq + 8];
+  const bool ok0 = rq < L, ok1 = rq + 8 < L;
+  uint32_t dsf[4][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m0 = madd[j * 8 + cq], m1 = madd[j * 8 + cq + 1];
+    float p0 = ok0 ? __expf(s[j][0] * scale + m0 - l0) : 0.f, p1 = ok0 ? __expf(s[j][1] * scale + m1 - l0) : 0.f;
+    float p2 = ok1 ? __expf(s[j][2] * scale + m0 - l1) : 0.f, p3 = ok1 ? __expf(s[j][3] * scale + m1 - l1) : 0.f;
+    float r_0 = 1.f, r_1 = 1.f, r_2 = 1.f, r_3 = 1.f;
+    if (dc.thresh) {
+      const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + rq) * L + j * 8 + cq;
+      const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
+      r_0 = dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
+      r_1 = dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
+      r_2 = dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
+      r_3 = dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+    }
+    const float ds0 = p0 * (dp[j][0] * r_0 - D0), ds1 = p1 * (dp[j][1] * r_1 - D0);
+    const float ds2 = p2 * (dp[j][2] * r_2 - D1), ds3 = p3 * (dp[j][3] * r_3 - D1);
+    *reinterpret_cast<uint32_t*>(Ps + rq * TC_LD + j * 8 + cq) = pack_bf16x2(p0 * r_0, p1 * r_1);
+    *reinterpret_cast<uint32_t*>(Ps + (rq + 8) * TC_LD + j * 8 + cq) = pack_bf16x2(p2 * r_2, p3 * r_3);
+    const uint32_t d01 = pack_bf16x2(ds0, ds1), d23 = pack_bf16x2(ds2, ds3);
+    *reinterpret_cast<uint32_t*>(dSs + rq * TC_LD + j * 8 + cq) = d01;
+    *reinterpret_cast<uint32_t*>(dSs + (rq + 8) * TC_LD + j * 8 + cq) = d23;
+    dsf[j >> 1][(j & 1) * 2] = d01;
+    dsf[j >> 1][(j & 1) * 2 + 1] = d23;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  tc_mm_ab_reg(acc, dsf, Ks, lane);                  // dQ = dS K
+  __syncthreads();                                   // Ps / dSs complete; every warp is done reading Vs (dP) -> Vs is free
+  tc_acc_to_smem(acc, Vs, r0, lane, scale);          // stage dQ in the V tile
+  // ---- phase 2: this warp's 16 key rows: dV = Pd^T dO, dK = dS^T Q ----
+  float dvacc[8][4], dkacc[8][4];
+  tc_mm_atb(dvacc, Ps, dOs, r0, lane);
+  tc_mm_atb(dkacc, dSs, Qs, r0, lane);
+  __syncthreads();                                   // dQ staged by all warps; Ps / dSs fully consumed
+  tc_store_tile(Vs, dq + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_acc_to_smem(dvacc, Ps, r0, lane, 1.0f);
+  tc_acc_to_smem(dkacc, dSs, r0, lane, scale);
+  __syncthreads();
+  tc_store_tile(Ps, dv + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_store_tile(dSs, dk + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+}
+
+static TcDrop make_tc_drop(float p, uint64_t seed) {
+  TcDrop d;
+  d.seed = seed;
+  if (p > 0.0f) {
+    double t = static_cast<double>(p) * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+    if (d.thresh == 0) d.thresh = 1;
+    d.inv_keep = 1.0f / (1.0f - p);
+  } else {
+    d.thresh = 0;
+    d.inv_keep = 1.0f;
+  }
+  return d;
+}
+
+// called from cb_attention_fwd / cb_attention_bwd (attention.cu) when l <= 64
+int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,
+                     int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  const int smem = 3 * TC_TILE * 2 + 64 * 4;
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("attention_tc_fwd smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    once = true;
+  }
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  const int hid = heads * 64;
+  attn_tc_fwd_kernel<<<dim3(heads, nseq), TC_THREADS, smem, stream>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+                                                                       static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f,
+                                                                       make_tc_drop(dropout_p, seed));
+  return check_launch("cb_attention_fwd(tc)");
+}
+
+int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
+                     const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
+                     cudaStream_t stream) {
+  const int smem = 6 * TC_TILE * 2 + 3 * 64 * 4;
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("attention_tc_bwd smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    once = true;
+  }
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* dbase = static_cast<__nv_bfloat16*>(dqkv);
+  const int hid = heads * 64;
+  attn_tc_bwd_kernel<<<dim3(heads, nseq), TC_THREADS, smem, stream>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+                                                                       static_cast<const __nv_bfloat16*>(ctx),
+                                                                       static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase, dbase + hid,
+                                                                       dbase + 2 * hid, ld_dqkv, l, lt, heads, 0.125f,
+                                                                       make_tc_drop(dropout_p, seed));
+  return check_launch("cb_attention_bwd(tc)");
+}
+
+}  // namespace cb

@@ -172,7 +172,8 @@ template <int BN, int MODE, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                const __grid_constant__ CUtensorMap tmX, int M, int N, int K, int ntaps, int tap_w, int tap_sign,
+                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
+                int tap_w, int tap_sign,
                 int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, GemmEpi epi) {
   using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&tmB);
     if (EPI == 1) {
       tma_prefetch_desc(&tmC);
+      if (epi.out2) tma_prefetch_desc(&tmC2);
       if (epi.residual) tma_prefetch_desc(&tmR);
       if (epi.aux) tma_prefetch_desc(&tmX);
     }
@@ -342,7 +344,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // ---------- TMA epilogue: rowmap NONE, bf16 output ----------
       constexpr int CPT = BN / 64;                      // 64-column chunks per tile
       uint8_t* cbuf = stg_base;                         // [n_cbuf][128 x 128 B] output chunks (n_cbuf = 2 or 4)
-      uint8_t* rbuf = cbuf + n_cbuf * CHUNK_BYTES;      // [2] residual chunks (if any)
+      const bool has_out2 = epi.out2 != nullptr;        // pre-activation stash: a second set of output chunks
+      uint8_t* c2buf = cbuf + n_cbuf * CHUNK_BYTES;
+      uint8_t* rbuf = c2buf + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [2] residual chunks (if any)
       uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
       const bool elected = (ew == 0 && lane == 0);
@@ -414,9 +418,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          epilogue_math(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, nullptr);
+          uint32_t o2_16[16];
+          epilogue_math(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
           const int cb = g & (n_cbuf - 1);
           uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
+          if (has_out2) {
+            uint8_t* c2r = c2buf + cb * CHUNK_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(c2r + (((grp * 4 + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(cr + (((grp * 4 + j) ^ swz) << 4)) =
@@ -431,6 +442,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           named_bar_sync(1, EPI_THREADS);
           if (elected) {
             tma_store_2d(&tmC, cbuf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+            if (has_out2) tma_store_2d(&tmC2, c2buf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
             tma_store_commit();
             prefetch(g + 2);                            // rbuf[b] / xbuf[b] were fully consumed before the barrier
           }
@@ -672,7 +684,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     }
     attr_set = true;
   }
-  const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr;
+  const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr, *tc2 = nullptr;
   int iters_per_split = 0;
   const int tiles_m = ceil_div(d.m, BM * CG), tiles_n = ceil_div(d.n, BN);
   int total = tiles_m * tiles_n;
@@ -702,12 +714,13 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
     if (d.residual) tr = get_tmap_2d(d.residual, d.n, d.m, d.res_ld, 64, BM);
     if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
-    if (!tc || (d.residual && !tr) || (d.aux && !tx)) return CB_ERR_CUDA;
+    if (d.out2) tc2 = get_tmap_2d(d.out2, d.n, d.m, d.out2_ld, 64, BM);
+    if (!tc || (d.residual && !tr) || (d.aux && !tx) || (d.out2 && !tc2)) return CB_ERR_CUDA;
     // four output buffers (three TMA stores in flight) unless that would starve the operand ring
     const int io_bytes = 2 * CHUNK_BYTES * ((d.residual ? 1 : 0) + (d.aux ? 1 : 0));
     // two output buffers: measured equal to four (profiles/r01_gemm_kch_probe.txt), and the operand ring needs the room
     n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
-    epi_bytes = n_cbuf * CHUNK_BYTES + io_bytes;
+    epi_bytes = n_cbuf * CHUNK_BYTES * (d.out2 ? 2 : 1) + io_bytes;
   } else {
     epi_bytes = EPI_WARPS * STG_BYTES;
     epi_bytes = (epi_bytes + 1023) & ~1023;
@@ -715,6 +728,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   if (!tc) tc = ta;   // unused placeholders (a __grid_constant__ parameter must still be a valid object)
   if (!tr) tr = ta;
   if (!tx) tx = ta;
+  if (!tc2) tc2 = ta;
   // chunks (64-deep k slices) that fit beside the epilogue buffers; a stage groups KCH of them under one barrier
   // round trip (fewer, larger transactions for deep K loops), keeping >= 3 stages in flight
   const int chunks_fit = (SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - epi_bytes) / Cfg::STAGE_BYTES;
@@ -737,7 +751,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   const int units = sm_count() / CG;
   const int grid = (total < units ? total : units) * CG;
   if (CG == 1) {
-    kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+    kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
                                                       iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -752,7 +766,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
                                        tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
     if (e != cudaSuccess) {
       set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
@@ -869,8 +883,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
     const LaunchCfg lc = choose_config(d, force_cg);
     // TMA epilogue whenever the output is a plain bf16 matrix (no row re-map, no second output)
-    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && !d.out2 && (d.reserved & 1) == 0 &&
-                         (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && (d.reserved & 1) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (!d.out2 || (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0) &&
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
 #define CB_DISPATCH(BN_, CG_)                                                                                                \

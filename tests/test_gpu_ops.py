@@ -316,6 +316,31 @@ def test_attention_fwd_bwd(cuda, dims):
     assert relerr(dqkv, x.grad.reshape(nseq * L, 3 * 768)) < 2 * TOL_BF16_OP
 
 
+def test_attention_tensor_core_path_matches_general_path(cuda):
+    """L <= 64 runs on the mma.sync kernels, longer sequences on the general kernels: same results, same dropout stream."""
+    import ctypes
+    from clipbert_b200 import _lib
+    ops = _ops()
+    nseq, L, lt, heads = 4, 41, 32, 12
+    g = torch.Generator().manual_seed(21)
+    qkv, dctx = _rnd(g, nseq * L, 3 * 768), _rnd(g, nseq * L, 768)
+    mask = torch.ones(nseq, lt, dtype=torch.int64, device=cuda)
+    mask[1, 20:] = 0
+    outs = []
+    for general in (0, 1):
+        _lib.lib().cb_debug_attention_general(ctypes.c_int(general))
+        ctx = torch.empty(nseq * L, 768, device=cuda, dtype=torch.bfloat16)
+        lse = torch.empty(nseq, heads, L, device=cuda)
+        dqkv = torch.empty_like(qkv)
+        for p, seed in ((0.0, 0), (0.1, 5)):
+            ops.attention_fwd(qkv, mask, ctx, lse, nseq, L, lt, heads, p, seed)
+            ops.attention_bwd(qkv, mask, ctx, dctx, lse, dqkv, nseq, L, lt, heads, p, seed)
+            outs.append((ctx.clone(), lse.clone(), dqkv.clone()))
+    _lib.lib().cb_debug_attention_general(ctypes.c_int(0))
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        assert relerr(a[0], b[0]) < 2 * TOL_BF16_OP and relerr(a[1], b[1]) < 1e-4 and relerr(a[2], b[2]) < 3 * TOL_BF16_OP
+
+
 def test_attention_dropout_consistency(cuda):
     """With p>0 the backward must regenerate the forward mask: check dV against a finite set of probes."""
     ops = _ops()
