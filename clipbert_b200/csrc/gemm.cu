@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == 1) {
-      tma_prefetch_desc(&tmC);
+      if (epi.rowmap == CB_ROWMAP_NONE) tma_prefetch_desc(&tmC);
       if (epi.out2) tma_prefetch_desc(&tmC2);
       if (epi.residual) tma_prefetch_desc(&tmR);
       if (epi.aux) tma_prefetch_desc(&tmX);
@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint8_t* rbuf = c2buf + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [2] residual chunks (if any)
       uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
+      const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: cooperative coalesced stores instead of TMA
+      const int etid = threadIdx.x - 64;                // 0..255 among the epilogue threads
       const bool elected = (ew == 0 && lane == 0);
       const int row = q * 32 + lane;                    // row inside the 128-row tile
       const int swz = row & 7;                          // 128B-swizzle XOR of this row
@@ -433,18 +435,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             *reinterpret_cast<uint4*>(cr + (((grp * 4 + j) ^ swz) << 4)) =
                 make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
-          if (elected) {                                // the buffer the NEXT chunk writes must be free again
-            if (n_cbuf == 4) tma_store_wait_read<2>();
-            else tma_store_wait_read<0>();
+          if (!remap) {
+            fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the TMA store
+            if (elected) {                              // the buffer the NEXT chunk writes must be free again
+              if (n_cbuf == 4) tma_store_wait_read<2>();
+              else tma_store_wait_read<0>();
+            }
           }
           __syncwarp();
           named_bar_sync(1, EPI_THREADS);
           if (elected) {
-            tma_store_2d(&tmC, cbuf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
-            if (has_out2) tma_store_2d(&tmC2, c2buf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
-            tma_store_commit();
+            if (!remap) {
+              tma_store_2d(&tmC, cbuf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+              if (has_out2) tma_store_2d(&tmC2, c2buf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+              tma_store_commit();
+            }
             prefetch(g + 2);                            // rbuf[b] / xbuf[b] were fully consumed before the barrier
+          }
+          if (remap) {
+            // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment,
+            // 32 rows per pass; the buffer is rewritten two chunks later, after the next named barrier
+            const int seg = etid & 7;
+            const int n = t.n0 + c * 64 + seg * 8;
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const int r = (etid >> 3) + pass * 32;
+              const int mm = t.m0 + r;
+              bool ok = mm < M && n + 8 <= N;
+              int64_t orr = mm;
+              if (epi.rowmap == CB_ROWMAP_PAD) {
+                const int hw = epi.H * epi.W;
+                const int img = mm / hw;
+                const int rr = mm - img * hw;
+                const int y = rr / epi.W, x = rr - y * epi.W;
+                orr = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
+              } else {
+                const int wp = epi.W + 2, hp = epi.H + 2;
+                const int img = mm / (hp * wp);
+                const int rr = mm - img * (hp * wp);
+                const int y = rr / wp, x = rr - y * wp;
+                ok = ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
+                orr = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
+              }
+              if (ok)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orr * epi.out_ld + n) =
+                    *reinterpret_cast<const uint4*>(cbuf + cb * CHUNK_BYTES + r * 128 + ((seg ^ (r & 7)) << 4));
+            }
           }
         }
       }
@@ -711,7 +747,8 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   if (!ta || !tb) return CB_ERR_CUDA;
   int epi_bytes, n_cbuf = 2;
   if (EPI == 1) {
-    tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
+    if (d.rowmap == CB_ROWMAP_NONE) tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
+    else tc = ta;
     if (d.residual) tr = get_tmap_2d(d.residual, d.n, d.m, d.res_ld, 64, BM);
     if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
     if (d.out2) tc2 = get_tmap_2d(d.out2, d.n, d.m, d.out2_ld, 64, BM);
@@ -883,7 +920,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
     const LaunchCfg lc = choose_config(d, force_cg);
     // TMA epilogue whenever the output is a plain bf16 matrix (no row re-map, no second output)
-    const bool tma_epi = d.rowmap == CB_ROWMAP_NONE && !d.out_fp32 && (d.reserved & 1) == 0 &&
+    const bool tma_epi = !d.out_fp32 && (d.reserved & 1) == 0 && !(d.rowmap != CB_ROWMAP_NONE && (d.out2 || d.dropout_p > 0.0f)) &&
                          (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (!d.out2 || (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0) &&
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);

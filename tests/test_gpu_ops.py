@@ -88,8 +88,8 @@ def test_gemm_epilogues(cuda, staged, shape):
     assert relerr(C, (acc + shift) * msk.float() + R.float()) < TOL_BF16_OP
 
 
-@pytest.mark.parametrize("knob", [SINGLE, PAIR])
-@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64)])
+@pytest.mark.parametrize("knob", [SINGLE, PAIR, SINGLE | STAGED])
+@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64), (64, 14, 14, 256, 256)])
 def test_conv3x3_fwd_and_dgrad(cuda, dims, knob):
     ops = _ops()
     NB, H, W, Cin, Cout = dims
@@ -114,19 +114,22 @@ def test_conv3x3_fwd_and_dgrad(cuda, dims, knob):
     assert relerr(y, ref) < TOL_BF16_OP
 
 
-def test_rowmap_pad_keeps_border_zero(cuda):
+@pytest.mark.parametrize("knob", [0, STAGED])
+@pytest.mark.parametrize("dims", [(3, 5, 6, 64, 64), (40, 28, 28, 256, 128)])
+def test_rowmap_pad_keeps_border_zero(cuda, dims, knob):
     ops = _ops()
-    NB, H, W, K, N = 3, 5, 6, 64, 64
+    NB, H, W, K, N = dims
     M = NB * H * W
     g = torch.Generator().manual_seed(5)
-    A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
+    A, B, AUX = _rnd(g, M, K), _rnd(g, N, K, scale=0.1), _rnd(g, M, N)
     yp = torch.zeros(NB, H + 2, W + 2, N, device=cuda, dtype=torch.bfloat16)
     ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=yp, out_ld=N,
-             rowmap=ops.ROWMAP_PAD, map_h=H, map_w=W)
-    ref = (A.float() @ B.float().t()).view(NB, H, W, N)
+             rowmap=ops.ROWMAP_PAD, map_h=H, map_w=W, aux=AUX, aux_ld=N, aux_mode=ops.AUX_RELU_MASK, reserved=knob)
+    ref = ((A.float() @ B.float().t()) * (AUX.float() > 0)).view(NB, H, W, N)
     assert relerr(yp[:, 1:-1, 1:-1], ref) < TOL_BF16_OP
-    inner = yp[:, 1:-1, 1:-1].float().abs().sum()
-    assert float(yp.float().abs().sum() - inner) == 0.0
+    border = yp.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert float(border.float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("case", [(64, 128, 64, 64, 1, SINGLE), (1312, 768, 768, 128, 1, SINGLE), (1000, 256, 192, 64, 1, SINGLE),
