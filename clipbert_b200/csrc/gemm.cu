@@ -692,10 +692,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (threadIdx.x == 32) dbg_stamp(epi, 11);
 }
 
-static long long* g_gemm_timeline = nullptr;
-static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
-static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
-
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -705,6 +701,37 @@ static int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+static long long* g_gemm_timeline = nullptr;
+static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
+static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
+
+// Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
+// stage. Measured (profiles/r01_gemm_kch_probe.txt, r01_gemm_staged_probe.txt): every stage costs a ~450-cycle barrier
+// round trip whatever its size, so deep stages beat many stages (1312x768x3072: 26.5 / 18.3 / 15.8 us with 1 / 2 / 4
+// chunks per stage); two output buffers perform like four.
+struct SmemPlan {
+  int epi_bytes, n_cbuf, kch, stages, chunk_bytes;
+};
+static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0) {
+  SmemPlan p;
+  p.chunk_bytes = BM * BK * 2 + (bn / cg) * BK * 2;
+  p.n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
+  if (tma_epi) p.epi_bytes = p.n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + 2 * CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
+  else p.epi_bytes = (EPI_WARPS * STG_BYTES + 1023) & ~1023;
+  const int chunks_fit = (SMEM_LIMIT - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
+  p.kch = 1;
+  if (force_kch > 0) p.kch = force_kch;
+  else if (g_force_kch > 0) p.kch = g_force_kch;
+  else if (kiters >= 4 && chunks_fit >= 8) p.kch = 4;
+  else if (kiters >= 2 && chunks_fit >= 4) p.kch = 2;
+  if (p.kch > kiters) p.kch = kiters;
+  p.stages = chunks_fit / p.kch;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const int stage_iters = ceil_div(kiters, p.kch);
+  if (p.stages > stage_iters + 1) p.stages = stage_iters + 1 > 2 ? stage_iters + 1 : 2;   // no ring deeper than the K loop
+  return p;
 }
 
 template <int BN, int MODE, int EPI, int CG>
@@ -745,7 +772,6 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     kiters = iters_per_split;
   }
   if (!ta || !tb) return CB_ERR_CUDA;
-  int epi_bytes, n_cbuf = 2;
   if (EPI == 1) {
     if (d.rowmap == CB_ROWMAP_NONE) tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
     else tc = ta;
@@ -753,33 +779,13 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
     if (d.out2) tc2 = get_tmap_2d(d.out2, d.n, d.m, d.out2_ld, 64, BM);
     if (!tc || (d.residual && !tr) || (d.aux && !tx) || (d.out2 && !tc2)) return CB_ERR_CUDA;
-    // four output buffers (three TMA stores in flight) unless that would starve the operand ring
-    const int io_bytes = 2 * CHUNK_BYTES * ((d.residual ? 1 : 0) + (d.aux ? 1 : 0));
-    // two output buffers: measured equal to four (profiles/r01_gemm_kch_probe.txt), and the operand ring needs the room
-    n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
-    epi_bytes = n_cbuf * CHUNK_BYTES * (d.out2 ? 2 : 1) + io_bytes;
-  } else {
-    epi_bytes = EPI_WARPS * STG_BYTES;
-    epi_bytes = (epi_bytes + 1023) & ~1023;
   }
   if (!tc) tc = ta;   // unused placeholders (a __grid_constant__ parameter must still be a valid object)
   if (!tr) tr = ta;
   if (!tx) tx = ta;
   if (!tc2) tc2 = ta;
-  // chunks (64-deep k slices) that fit beside the epilogue buffers; a stage groups KCH of them under one barrier
-  // round trip (fewer, larger transactions for deep K loops), keeping >= 3 stages in flight
-  const int chunks_fit = (SMEM_LIMIT - 1024 - Cfg::BAR_BYTES - epi_bytes) / Cfg::STAGE_BYTES;
-  // Measured (profiles/r01_gemm_kch_probe.txt): each stage costs a ~400-cycle barrier round trip whatever its size,
-  // so deep stages beat many stages: 1312x768x3072 takes 26.5 / 18.3 / 15.8 us with 1 / 2 / 4 chunks per stage.
-  int kch = 1;
-  if (g_force_kch > 0) kch = g_force_kch;
-  else if (kiters >= 4 && chunks_fit >= 8) kch = 4;
-  else if (kiters >= 2 && chunks_fit >= 4) kch = 2;
-  if (kch > kiters) kch = kiters;
-  int stages = chunks_fit / kch;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  const int stage_iters = ceil_div(kiters, kch);
-  if (stages > stage_iters + 1) stages = stage_iters + 1 > 2 ? stage_iters + 1 : 2;   // no point in a ring deeper than the K loop
+  const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15);
+  const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
     set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B)", BN, epi_bytes);
     return CB_ERR_INVALID;
@@ -826,7 +832,7 @@ struct LaunchCfg {
   int bn, cg, splits;
 };
 
-static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
+static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi) {
   const int sms = sm_count();
   const int kc = ceil_div(d.k, BK);
   const bool wgrad = d.mode == CB_GEMM_WGRAD;
@@ -841,15 +847,18 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg) {
     if (cg == 2 && d.m <= BM) continue;
     const int units = sms / cg;
     const int64_t base = static_cast<int64_t>(ceil_div(d.m, BM * cg)) * ceil_div(d.n, bn) * (wgrad ? d.ntaps : 1);
-    const double stage = 16384.0 + bn * 128.0 / cg;
     const int max_split = wgrad ? (d.split_k > 0 ? d.split_k : (kc < 32 ? kc : 32)) : 1;
     for (int sp = (wgrad && d.split_k > 0) ? d.split_k : 1; sp <= max_split; ++sp) {
       const int ips = ceil_div(wgrad ? kc : kc * d.ntaps, sp);
       const int real_sp = wgrad ? ceil_div(kc, ips) : 1;
       const int64_t tiles = base * real_sp;
       const double rounds = static_cast<double>((tiles + units - 1) / units);
-      const double epi = wgrad ? bn * 24.0 : bn * 10.0;    // cycles per tile: fp32 red.add vs bf16 store path
-      const double cost = rounds * (ips * (stage / 60.0 + 64.0) + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
+      const SmemPlan pl = plan_smem(bn, cg, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15);
+      if (pl.stages < 2) continue;
+      // per stage: ~450-cycle barrier round trip + bytes at ~60 B/clk; per tile: epilogue (fp32 red.add / staged bf16 / TMA bf16)
+      const double stage_cost = 450.0 + pl.kch * pl.chunk_bytes / 60.0;
+      const double epi = wgrad ? bn * 24.0 : (tma_epi ? bn * 12.0 : bn * 30.0);
+      const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
       if (cost < best_cost) {
         best_cost = cost;
         best = {bn, cg, real_sp};
@@ -918,12 +927,13 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(d.rowmap == CB_ROWMAP_NONE || (d.map_h > 0 && d.map_w > 0), "cb_gemm: rowmap needs map_h/map_w");
     CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: 9-tap mode needs tap_w = W + 2");
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
-    const LaunchCfg lc = choose_config(d, force_cg);
-    // TMA epilogue whenever the output is a plain bf16 matrix (no row re-map, no second output)
+    // TMA-prefetch epilogue whenever the output is bf16 (residual / aux tiles arrive by TMA; the output leaves by TMA store
+    // or, when rows are re-mapped, by cooperative coalesced stores)
     const bool tma_epi = !d.out_fp32 && (d.reserved & 1) == 0 && !(d.rowmap != CB_ROWMAP_NONE && (d.out2 || d.dropout_p > 0.0f)) &&
                          (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (!d.out2 || (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0) &&
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
+    const LaunchCfg lc = choose_config(d, force_cg, tma_epi);
 #define CB_DISPATCH(BN_, CG_)                                                                                                \
   return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))         \
             : (tma_epi ? launch_gemm<BN_, 0, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 0, 0, CG_>(d, epi, stream))
@@ -944,7 +954,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(d.out_ld % 4 == 0, "cb_gemm(WGRAD): out_ld must be a multiple of 4");
     CB_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "cb_gemm(WGRAD): out must be 16-byte aligned");
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
-    const LaunchCfg lc = choose_config(d, force_cg);
+    const LaunchCfg lc = choose_config(d, force_cg, false);
     cb_gemm_desc d2 = d;
     d2.split_k = lc.splits;
     if (lc.cg == 2) {

@@ -99,8 +99,42 @@ def set_gemm_timing(events):
     _gemm_timing = events
 
 
+# Measured launch configurations (tools/autotune_gemm.py on a B200 -> clipbert_b200/gemm_tuning.json): for each GEMM
+# shape of the workload the fastest (tile width, wgrad K-split, k-chunks per stage). Shapes that are not in the table use
+# the library's analytic model (choose_config in csrc/gemm.cu).
+_tuning = None
+_gemm_record = None
+
+
+def gemm_key(kw):
+    return "m%d n%d k%d mode%d t%d r%d a%d o%d f%d rm%d act%d" % (
+        kw["m"], kw["n"], kw["k"], kw.get("mode", 0), kw.get("ntaps", 1), kw.get("residual") is not None, kw.get("aux") is not None,
+        kw.get("out2") is not None, kw.get("out_fp32", 0), kw.get("rowmap", 0), kw.get("act", 0))
+
+
+def _load_tuning():
+    global _tuning
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuning.json")
+    _tuning = {}
+    if os.path.exists(path) and not os.environ.get("CB_NO_TUNING"):
+        try:
+            _tuning = json.load(open(path)).get("configs", {})
+        except Exception:
+            _tuning = {}
+
+
 def gemm(**kw):
     """cb_gemm with keyword fields of cb_gemm_desc; tensor-valued fields are converted to pointers."""
+    if _tuning is None:
+        _load_tuning()
+    if _gemm_record is not None:
+        _gemm_record.append(dict(kw))
+    if _tuning and "block_n" not in kw and "reserved" not in kw:
+        t = _tuning.get(gemm_key(kw))
+        if t is not None:
+            kw = dict(kw, block_n=t[0], split_k=t[1], reserved=t[2] << 8)
     d = L.GemmDesc()
     d.ntaps = 1
     d.tap_sign = 1

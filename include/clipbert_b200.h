@@ -109,7 +109,8 @@ typedef struct cb_gemm_desc {
   float dropout_p;
   uint64_t dropout_seed;
   int32_t block_n;  /* 0 = let the library choose (64 / 128 / 256) */
-  int32_t reserved; /* test knobs: bit0 force the staged (non-TMA) epilogue, bit1 force single-CTA tiles, bit2 force CTA pairs */
+  int32_t reserved; /* tuning / test knobs: bit0 force the staged (non-TMA) epilogue, bit1 force single-CTA tiles,
+                       bit2 force CTA pairs, bits 8-11 k-chunks per pipeline stage (0 = automatic) */
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

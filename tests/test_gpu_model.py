@@ -306,3 +306,38 @@ def test_pretraining_heads_mlm_itm(cuda, weights):
         if not (e < TOL_GRAD and c > 0.999):
             bad.append((name, e, c))
     assert not bad, bad[:10]
+
+
+def test_native_resolution_448_and_long_text(cuda, weights):
+    """The reference's native MSRVTT setting is 448 px (7x7 = 49 visual tokens, the paper's grid) and its
+    paragraph-retrieval inference uses long captions: L = 20 + 49 = 69 and L = 512 + 9 = 521 both take the general
+    (multi-tile) attention kernels."""
+    from oracle import clipbert_ref as R, synth
+    model = _build("ClipBertForVideoTextRetrieval", weights, cuda).train()
+    # ---- 448 px, 1 video x 2 frames, 2 captions of 20 tokens: forward + backward ----
+    batch = synth.synth_batch(1, 2, n_ex=2, size=448, max_len=20, seed=13)
+    mb = {k: (v.to(cuda) if torch.is_tensor(v) else list(v)) for k, v in batch.items()}
+    model.cnn._capture, model.transformer._capture = {}, {}
+    out = model(mb)
+    assert mb["visual_inputs"].shape == (1, 2, 7, 7, 768)
+    pat = cnn_patterns(model.cnn._capture["stash"], mb["visual_inputs"])
+    pat.relu_masks["transformer.classifier.relu"] = (model.transformer._capture["c1"] > 0).cpu()
+    model.cnn._capture = model.transformer._capture = None
+    sd = {k: (v.clone().requires_grad_(True) if k in ("cnn.grid_encoder.0.weight", "transformer.bert.encoder.layer.0.attention.self.query.weight",
+                                                       "cnn.feature.backbone.res4.0.conv2.weight") else v) for k, v in weights.items()}
+    ref = R.clipbert_forward(dict(batch), sd, rnd=pat)
+    assert relerr(out["logits"], ref["logits"]) < TOL_LOGITS
+    out["loss"].mean().backward()
+    ref["loss"].mean().backward()
+    named = dict(model.named_parameters())
+    for k in ("cnn.grid_encoder.0.weight", "transformer.bert.encoder.layer.0.attention.self.query.weight", "cnn.feature.backbone.res4.0.conv2.weight"):
+        assert cosine(named[k].grad, sd[k].grad) > 0.995, (k, cosine(named[k].grad, sd[k].grad))
+    # ---- 512-token captions at 224 px (C5-style inference, L = 521) ----
+    model.eval()
+    g = torch.Generator().manual_seed(17)
+    grid = (torch.randn(1, 1, 3, 3, 768, generator=g).abs()).to(torch.bfloat16).float()
+    ids, mask = synth.synth_text(2, 512, seed=19)
+    with torch.no_grad():
+        ref = R.video_text_retrieval(ids, R.repeat_tensor_rows(grid, [2]), mask, weights, rnd=R.Rounding.bf16())
+        got = model.transformer(ids.to(cuda), grid.to(cuda), mask.to(cuda), _repeat_counts=[2])
+    assert relerr(got["logits"], ref["logits"]) < TOL_LOGITS
