@@ -121,7 +121,7 @@ def make_host_batch(args, rank):
 
 def lse_loss(logits_per_clip, labels):
     """Clip aggregation + loss of the reference loop (run_video_retrieval.py:404-422, pool_method 'lse')."""
-    lg = torch.stack(logits_per_clip).permute(1, 0, 2).contiguous()
+    lg = (logits_per_clip if torch.is_tensor(logits_per_clip) else torch.stack(logits_per_clip)).permute(1, 0, 2).contiguous()
     out = torch.logsumexp(lg.view(lg.shape[0], -1), dim=-1, keepdim=True) - torch.logsumexp(lg, dim=1)
     return torch.gather(out, -1, labels.view(-1, 1)).mean()
 
@@ -152,6 +152,7 @@ def run_b200(args):
     if world > 1:
         model.enable_overlapped_allreduce()
 
+    ops.set_pdl(args.pdl)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
     dbuf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
@@ -163,12 +164,17 @@ def run_b200(args):
             dbuf[k].copy_(host[k], non_blocking=True)
 
     def fwd_bwd():
-        vis = dbuf["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
-        logits = []
-        for c in range(n_clips):
-            mb = dict(visual_inputs=vis[:, c], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
+        if args.clip_batching:     # the n_clips passes of the reference loop as ONE pass over B*n_clips units
+            mb = dict(visual_inputs=dbuf["visual_inputs"], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
                       labels=dbuf["labels"], n_examples_list=[n_ex] * B)
-            logits.append(model(mb)["logits"])
+            logits = model.forward_clips(mb, n_clips)["logits"]
+        else:                      # the reference loop as written (run_video_retrieval.py:396-401)
+            vis = dbuf["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+            logits = []
+            for c in range(n_clips):
+                mb = dict(visual_inputs=vis[:, c], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
+                          labels=dbuf["labels"], n_examples_list=[n_ex] * B)
+                logits.append(model(mb)["logits"])
         loss = lse_loss(logits, dbuf["labels"])
         loss.backward()
         if world > 1:
@@ -262,12 +268,14 @@ def run_b200(args):
     cpu = None
     if True:      # every rank runs the instrumented pass (it contains the collectives); rank 0 reports
         ev = []
+        ops.set_pdl(0)               # per-launch durations: no overlap of a kernel's prologue with its predecessor's tail
         ops.set_gemm_timing(ev)
         for _ in range(2):
             model.zero_grad()
             fwd_bwd()
         torch.cuda.synchronize()
         ops.set_gemm_timing(None)
+        ops.set_pdl(args.pdl)
         half = len(ev) // 2
         gemm_ms = sum(a.elapsed_time(b) for a, b in ev[half:])
         n_gemm = len(ev) - half
@@ -297,7 +305,8 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, gflop_per_clip=round(fl_clip / 1e9, 2)),
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl),
+                               gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4),
                    gpu_launches=int(launches), gpu_launches_per_step=int(launches // args.steps), clocks=clocks, roofline=roof,
@@ -402,6 +411,8 @@ def main():
     ap.add_argument("--txt_len", type=int, default=32)
     ap.add_argument("--n_ex", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch between the library's kernels")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

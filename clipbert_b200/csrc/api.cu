@@ -1,4 +1,5 @@
 // C-ABI plumbing: error strings, version, launch counter, TMA tensor-map cache.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -10,6 +11,11 @@ namespace cb {
 
 static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+static int pdl_default() {
+  const char* e = getenv("CB_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+std::atomic<int> g_pdl{pdl_default()};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -104,4 +110,5 @@ const char* cb_last_error(void) { return cb::t_err; }
 int cb_version(void) { return 100; }
 int cb_sm_arch(void) { return 100; }
 int64_t cb_launch_count(void) { return cb::g_launches.load(std::memory_order_relaxed); }
+int cb_set_pdl(int enable) { return cb::g_pdl.exchange(enable ? 1 : 0, std::memory_order_relaxed); }
 }

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
                                                                __nv_bfloat16* __restrict__ ctx, int64_t ld_ctx,
                                                                float* __restrict__ lse, int L, int Lt, int H, float scale,
                                                                AttnDrop dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + TILE_FLOATS;
@@ -289,6 +291,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kv_kernel(
     int64_t ld_qkv, const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
     const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dk,
     __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Ks = sm;
   float* Vs = Ks + TILE_FLOATS;
@@ -342,6 +346,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_q_kernel(
     int64_t ld_qkv, const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
     const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
     int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* dOs = Qs + TILE_FLOATS;
@@ -442,7 +448,7 @@ int cb_attention_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   const int hid = heads * HD;
   dim3 grid(ceil_div(l, TS), heads, nseq);
-  attn_fwd_kernel<<<grid, ATT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(attn_fwd_kernel, grid, ATT_THREADS, smem, static_cast<cudaStream_t>(stream), 
       base, base + hid, base + 2 * hid, ld_qkv, text_mask, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads,
       0.125f, make_attn_drop(dropout_p, seed));
   return check_launch("cb_attention_fwd");
@@ -473,13 +479,13 @@ int cb_attention_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   const AttnDrop dc = make_attn_drop(dropout_p, seed);
   dim3 grid(ceil_div(l, TS), heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  attn_bwd_kv_kernel<<<grid, ATT_THREADS, smem_kv, st>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+  launch_k(attn_bwd_kv_kernel, grid, ATT_THREADS, smem_kv, st, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
                                                          static_cast<const __nv_bfloat16*>(ctx),
                                                          static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase + hid,
                                                          dbase + 2 * hid, ld_dqkv, l, lt, heads, 0.125f, dc);
   int rc = check_launch("cb_attention_bwd(kv)");
   if (rc) return rc;
-  attn_bwd_q_kernel<<<grid, ATT_THREADS, smem_q, st>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+  launch_k(attn_bwd_q_kernel, grid, ATT_THREADS, smem_q, st, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
                                                        static_cast<const __nv_bfloat16*>(ctx),
                                                        static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase, ld_dqkv, l,
                                                        lt, heads, 0.125f, dc);

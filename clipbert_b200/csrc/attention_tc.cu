@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
                                                                  const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
                                                                  int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
                                                                  TcDrop dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
   __nv_bfloat16* Ks = Qs + TC_TILE;
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
                                                                  const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
                                                                  __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv,
                                                                  int L, int Lt, int H, float scale, TcDrop dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
   __nv_bfloat16* Ks = Qs + TC_TILE;
@@ -339,7 +343,7 @@ int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   }
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   const int hid = heads * 64;
-  attn_tc_fwd_kernel<<<dim3(heads, nseq), TC_THREADS, smem, stream>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+  launch_k(attn_tc_fwd_kernel, dim3(heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
                                                                        static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f,
                                                                        make_tc_drop(dropout_p, seed));
   return check_launch("cb_attention_fwd(tc)");
@@ -358,7 +362,7 @@ int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* dbase = static_cast<__nv_bfloat16*>(dqkv);
   const int hid = heads * 64;
-  attn_tc_bwd_kernel<<<dim3(heads, nseq), TC_THREADS, smem, stream>>>(base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+  launch_k(attn_tc_bwd_kernel, dim3(heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
                                                                        static_cast<const __nv_bfloat16*>(ctx),
                                                                        static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase, dbase + hid,
                                                                        dbase + 2 * hid, ld_dqkv, l, lt, heads, 0.125f,

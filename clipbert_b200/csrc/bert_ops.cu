@@ -149,6 +149,8 @@ __device__ __forceinline__ void block_accumulate(float (&acc)[CH][8], float* sme
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* gamma,
                                                      const float* beta, __nv_bfloat16* __restrict__ y,
                                                      float* __restrict__ stats, int M, float eps) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp;
   if (m >= M) return;
@@ -169,6 +171,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ stats, const float* gamma,
                                                      __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
                                                      float* dgamma, float* dbeta, float* dbias_drop, int M, DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[CH][8];
@@ -226,6 +230,8 @@ __global__ void __launch_bounds__(128) embed_text_fwd_kernel(const int64_t* __re
                                                              const float* gamma, const float* beta,
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
                                                              int nseq, int Lt, int L, int vocab, float eps, DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp;
   if (r >= static_cast<int64_t>(nseq) * Lt) return;
@@ -257,6 +263,8 @@ __global__ void __launch_bounds__(128) embed_text_bwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ stats, float* dword, float* dpos,
                                                              float* dtype0, float* dgamma, float* dbeta, int nseq, int Lt,
                                                              int L, int vocab, DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[CH][8];
@@ -319,6 +327,8 @@ __global__ void __launch_bounds__(128) embed_visual_fwd_kernel(const __nv_bfloat
                                                                __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
                                                                int nseq, int T, int gh, int gw, int Lt, int L, float eps,
                                                                DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lv = gh * gw;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp;
@@ -368,6 +378,8 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_kernel(const __nv_bfloat
                                                                float* drow, float* dcol, float* dtype0, float* dgamma,
                                                                float* dbeta, int nseq, int T, int gh, int gw, int Lt, int L,
                                                                DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lv = gh * gw;
@@ -436,6 +448,8 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_reduce_kernel(const floa
                                                                       const int32_t* __restrict__ vid_start, int n_ex,
                                                                       __nv_bfloat16* __restrict__ dgrid, int nvid, int T,
                                                                       int Lv) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp;
   if (r >= static_cast<int64_t>(nvid) * Lv) return;
@@ -470,6 +484,8 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_reduce_kernel(const floa
 // 128-row slab; partials are combined across warps in smem so that each block issues ONE atomic per column
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int M,
                                                      int N) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -503,6 +519,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 // small elementwise helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, DropCfg dc) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   const uint4 u = *reinterpret_cast<const uint4*>(x + i);
@@ -523,6 +541,8 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 // dx = dy * gelu'(u)  (backward of the MLM-head transform activation, transformers.py:486-495)
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
                                 __nv_bfloat16* __restrict__ dx, int64_t n8) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= n8) return;
   const uint4 a = reinterpret_cast<const uint4*>(dy)[t], b = reinterpret_cast<const uint4*>(u)[t];
@@ -539,6 +559,8 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 // out[r, 0:cpad] (bf16) = in[r, 0:c] (fp32) zero-padded ; used for dlogits -> padded classifier grad
 __global__ void pad_cast_kernel(const float* __restrict__ in, int64_t in_ld, __nv_bfloat16* __restrict__ out, int rows,
                                 int c, int cpad) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(rows) * cpad) return;
   const int r = static_cast<int>(i / cpad), j = static_cast<int>(i - static_cast<int64_t>(r) * cpad);
@@ -548,6 +570,8 @@ __global__ void pad_cast_kernel(const float* __restrict__ in, int64_t in_ld, __n
 // fp32 -> bf16 (weight packing), optional per-row scale (FrozenBN fold: row = element / row_len)
 __global__ void cast_scale_kernel(const float* __restrict__ in, const float* __restrict__ rowscale, int64_t row_len,
                                   __nv_bfloat16* __restrict__ out, int64_t n) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 4 <= n) {
@@ -570,6 +594,8 @@ __global__ void cast_scale_kernel(const float* __restrict__ in, const float* __r
 __global__ void cast_scale_segments_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
                                            const int64_t* __restrict__ seg /*[nseg][4]: offset, numel, row_len, scale_off (-1: none)*/,
                                            const float* __restrict__ scales) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t* sg = seg + 4 * blockIdx.y;
   const int64_t off = sg[0], n = sg[1], row_len = sg[2], soff = sg[3];
   for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
@@ -604,7 +630,7 @@ int cb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
                      float eps, void* stream) {
   CB_REQUIRE(hidden == HID, "cb_layernorm_fwd: hidden size %d unsupported (built for %d)", hidden, HID);
   CB_REQUIRE(x && gamma && beta && y && m > 0, "cb_layernorm_fwd: bad arguments");
-  ln_fwd_kernel<<<ceil_div(m, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(ln_fwd_kernel, ceil_div(m, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), stats, m, eps);
   return check_launch("cb_layernorm_fwd");
 }
@@ -616,7 +642,7 @@ int cb_layernorm_bwd(const void* dy, const void* x, const float* stats, const fl
   CB_REQUIRE(dy && x && stats && gamma && dx && m > 0, "cb_layernorm_bwd: bad arguments");
   // the dgamma / dbeta / dbias atomics contend once per block and column: a few rows per warp, not one
   const int blocks = max(1, min(ceil_div(m, ROWS_PER_BLOCK), 148 * 2));
-  ln_bwd_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(ln_bwd_kernel, blocks, 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), stats, gamma,
       static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dx_drop), dgamma, dbeta, dbias_drop, m,
       make_drop(dropout_p, dropout_seed));
@@ -628,7 +654,7 @@ int cb_embed_text_fwd(const int64_t* ids, const float* word, const float* pos, c
                       float eps, float dropout_p, uint64_t seed, void* stream) {
   CB_REQUIRE(hidden == HID, "cb_embed_text_fwd: hidden size %d unsupported", hidden);
   CB_REQUIRE(ids && word && pos && type0 && out && stats && nseq > 0 && lt > 0 && l >= lt, "cb_embed_text_fwd: bad arguments");
-  embed_text_fwd_kernel<<<ceil_div(static_cast<int64_t>(nseq) * lt, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(embed_text_fwd_kernel, ceil_div(static_cast<int64_t>(nseq) * lt, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream), 
       ids, word, pos, type0, gamma, beta, static_cast<__nv_bfloat16*>(out), stats, nseq, lt, l, vocab, eps,
       make_drop(dropout_p, seed));
   return check_launch("cb_embed_text_fwd");
@@ -641,7 +667,7 @@ int cb_embed_text_bwd(const void* dh, const int64_t* ids, const float* word, con
   CB_REQUIRE(hidden == HID, "cb_embed_text_bwd: hidden size %d unsupported", hidden);
   CB_REQUIRE(dh && ids && dword && dpos && dtype0 && dgamma && dbeta, "cb_embed_text_bwd: bad arguments");
   const int blocks = min(ceil_div(static_cast<int64_t>(nseq) * lt, ROWS_PER_BLOCK), 148 * 4);
-  embed_text_bwd_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(embed_text_bwd_kernel, blocks, 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dh), ids, word, pos, type0, gamma, stats, dword, dpos, dtype0, dgamma, dbeta,
       nseq, lt, l, vocab, make_drop(dropout_p, seed));
   return check_launch("cb_embed_text_bwd");
@@ -654,7 +680,7 @@ int cb_embed_visual_fwd(const void* grid, const int32_t* seq2vid, int n_ex, cons
   CB_REQUIRE(hidden == HID, "cb_embed_visual_fwd: hidden size %d unsupported", hidden);
   CB_REQUIRE(grid && out && stats && nseq > 0 && t > 0 && gh > 0 && gw > 0 && l == lt + gh * gw, "cb_embed_visual_fwd: bad arguments");
   CB_REQUIRE(seq2vid || n_ex > 0, "cb_embed_visual_fwd: need seq2vid or uniform n_ex");
-  embed_visual_fwd_kernel<<<ceil_div(static_cast<int64_t>(nseq) * gh * gw, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(embed_visual_fwd_kernel, ceil_div(static_cast<int64_t>(nseq) * gh * gw, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(grid), seq2vid, n_ex, rowemb, colemb, type0, gamma, beta,
       static_cast<__nv_bfloat16*>(out), stats, nseq, t, gh, gw, lt, l, eps, make_drop(dropout_p, seed));
   return check_launch("cb_embed_visual_fwd");
@@ -670,14 +696,13 @@ int cb_embed_visual_bwd(const void* dh, const void* grid, const int32_t* seq2vid
   CB_REQUIRE((seq2vid && vid_start) || n_ex > 0, "cb_embed_visual_bwd: need seq2vid+vid_start or uniform n_ex");
   const int Lv = gh * gw;
   const int blocks = min(ceil_div(static_cast<int64_t>(nseq) * Lv, ROWS_PER_BLOCK), 148 * 4);
-  embed_visual_bwd_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(embed_visual_bwd_kernel, blocks, 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(grid), seq2vid, n_ex, rowemb, colemb,
       type0, gamma, stats, dv_tmp, drow, dcol, dtype0, dgamma, dbeta, nseq, t, gh, gw, lt, l, make_drop(dropout_p, seed));
   int rc = check_launch("cb_embed_visual_bwd");
   if (rc != CB_OK) return rc;
   if (dgrid) {
-    embed_visual_bwd_reduce_kernel<<<ceil_div(static_cast<int64_t>(nvid) * Lv, ROWS_PER_BLOCK), 128, 0,
-                                     static_cast<cudaStream_t>(stream)>>>(dv_tmp, vid_start, n_ex,
+    launch_k(embed_visual_bwd_reduce_kernel, ceil_div(static_cast<int64_t>(nvid) * Lv, ROWS_PER_BLOCK), 128, 0, static_cast<cudaStream_t>(stream), dv_tmp, vid_start, n_ex,
                                                                           static_cast<__nv_bfloat16*>(dgrid), nvid, t, Lv);
     rc = check_launch("cb_embed_visual_bwd(reduce)");
   }
@@ -687,27 +712,27 @@ int cb_embed_visual_bwd(const void* dh, const void* grid, const int32_t* seq2vid
 int cb_colsum(const void* x, int64_t ld, float* out, int m, int n, void* stream) {
   CB_REQUIRE(x && out && m > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "cb_colsum: bad arguments (n, ld must be multiples of 8)");
   dim3 grid(ceil_div(n, 256), ceil_div(m, 128));
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, out, m, n);
+  launch_k(colsum_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), ld, out, m, n);
   return check_launch("cb_colsum");
 }
 
 int cb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* stream) {
   CB_REQUIRE(x && y && n > 0 && n % 8 == 0, "cb_dropout: n must be a positive multiple of 8");
-  dropout_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(dropout_kernel, ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, make_drop(p, seed));
   return check_launch("cb_dropout");
 }
 
 int cb_gelu_bwd(const void* dy, const void* u, void* dx, int64_t n, void* stream) {
   CB_REQUIRE(dy && u && dx && n > 0 && n % 8 == 0, "cb_gelu_bwd: n must be a positive multiple of 8");
-  gelu_bwd_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gelu_bwd_kernel, ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(dx), n / 8);
   return check_launch("cb_gelu_bwd");
 }
 
 int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int cpad, void* stream) {
   CB_REQUIRE(in && out && rows > 0 && c > 0 && cpad >= c, "cb_pad_cast: bad arguments");
-  pad_cast_kernel<<<ceil_div(static_cast<int64_t>(rows) * cpad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pad_cast_kernel, ceil_div(static_cast<int64_t>(rows) * cpad, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       in, in_ld, static_cast<__nv_bfloat16*>(out), rows, c, cpad);
   return check_launch("cb_pad_cast");
 }
@@ -716,14 +741,14 @@ int cb_cast_scale_segments(const float* master, void* packed, const int64_t* seg
   CB_REQUIRE(master && packed && segments && nseg > 0, "cb_cast_scale_segments: bad arguments");
   CB_REQUIRE((reinterpret_cast<uintptr_t>(master) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0, "cb_cast_scale_segments: misaligned");
   dim3 grid(64, nseg);
-  cast_scale_segments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(master, static_cast<__nv_bfloat16*>(packed), segments, scales);
+  launch_k(cast_scale_segments_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), master, static_cast<__nv_bfloat16*>(packed), segments, scales);
   return check_launch("cb_cast_scale_segments");
 }
 
 int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void* out, int64_t n, void* stream) {
   CB_REQUIRE(in && out && n > 0 && (!rowscale || row_len > 0), "cb_cast_scale: bad arguments");
   CB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "cb_cast_scale: misaligned");
-  cast_scale_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cast_scale_kernel, ceil_div(ceil_div(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       in, rowscale, row_len, static_cast<__nv_bfloat16*>(out), n);
   return check_launch("cb_cast_scale");
 }

@@ -32,6 +32,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <typename TIn>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
                                                           int Ho, int Wo, int KP, float m0, float m1, float m2) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   extern __shared__ __nv_bfloat16 srow[];          // [7 rows][3 planes][W + 6]
   const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
   const int WP = W + 6;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const TIn* __restrict_
 // 3x3 stride-2 pad-1 max pool, NHWC
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
                                     int C, int Ho, int Wo) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int c8n = C / 8;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
@@ -98,6 +102,8 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 // stride-2 pixel subsample (input of a stride-2 1x1 conv): y[n, oy, ox] = x[n, 2oy, 2ox]
 __global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
                                   int C, int Ho, int Wo) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int c8n = C / 8;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
@@ -113,6 +119,8 @@ __global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 //   dx[n,y,x] = (y,x even ? dsub[n,y/2,x/2] : 0) * (act[n,y,x] > 0)
 __global__ void unsubsample2_mask_kernel(const __nv_bfloat16* __restrict__ dsub, const __nv_bfloat16* __restrict__ act,
                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int c8n = C / 8;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<int64_t>(N) * H * W * c8n) return;
@@ -135,6 +143,8 @@ __global__ void unsubsample2_mask_kernel(const __nv_bfloat16* __restrict__ dsub,
 // grid_encoder tail: MaxPool2d(2,2) (floor) then ReLU, NHWC compact -> NHWC compact
 __global__ void maxpool2x2_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                            int W, int C, int Ho, int Wo) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int c8n = C / 8;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<int64_t>(N) * Ho * Wo * c8n) return;
@@ -161,6 +171,8 @@ __global__ void maxpool2x2_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, 
 // Writes EVERY element of dx_pad [N, H+2, W+2, C] (zeros on the border and on non-argmax pixels).
 __global__ void maxpool2x2_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                            __nv_bfloat16* __restrict__ dx_pad, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int c8n = C / 8;
   const int Hp = H + 2, Wp = W + 2;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -202,6 +214,8 @@ __global__ void maxpool2x2_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
 // y = dy * (act > 0), both compact: ReLU backward where no GEMM epilogue can carry it
 __global__ void relu_mask_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act,
                                  __nv_bfloat16* __restrict__ dx, int64_t n8) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= n8) return;
   float g[8], a[8];
@@ -229,10 +243,10 @@ int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, 
   CB_REQUIRE(smem <= 48 * 1024, "cb_stem_im2col: frame width %d too large for the row staging buffer", w);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0)
-    stem_im2col_kernel<float><<<n * ho, 256, smem, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo, kp,
+    launch_k(stem_im2col_kernel<float>, n * ho, 256, smem, st, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo, kp,
                                                          mean_r, mean_g, mean_b);
   else if (in_dtype == 1)
-    stem_im2col_kernel<uint8_t><<<n * ho, 256, smem, st>>>(static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo,
+    launch_k(stem_im2col_kernel<uint8_t>, n * ho, 256, smem, st, static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out), n, h, w, ho, wo,
                                                            kp, mean_r, mean_g, mean_b);
   else
     CB_REQUIRE(false, "cb_stem_im2col: in_dtype must be 0 (fp32) or 1 (uint8)");
@@ -246,7 +260,7 @@ int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* st
   CB_NHWC_CHECK("cb_maxpool3x3s2");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
-  maxpool3x3s2_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(maxpool3x3s2_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
   return check_launch("cb_maxpool3x3s2");
 }
@@ -255,7 +269,7 @@ int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stre
   CB_NHWC_CHECK("cb_subsample2");
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
-  subsample2_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(subsample2_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
   return check_launch("cb_subsample2");
 }
@@ -265,7 +279,7 @@ int cb_unsubsample2_mask(const void* dsub, const void* act, void* dx, int n, int
   CB_REQUIRE(dsub && act && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "cb_unsubsample2_mask: bad arguments");
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
-  unsubsample2_mask_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(unsubsample2_mask_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dsub), static_cast<const __nv_bfloat16*>(act), static_cast<__nv_bfloat16*>(dx), n, h, w, c,
       ho, wo);
   return check_launch("cb_unsubsample2_mask");
@@ -276,7 +290,7 @@ int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, v
   CB_REQUIRE(h >= 2 && w >= 2, "cb_maxpool2x2_relu_fwd: spatial size must be >= 2");
   const int ho = h / 2, wo = w / 2;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
-  maxpool2x2_relu_fwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(maxpool2x2_relu_fwd_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
   return check_launch("cb_maxpool2x2_relu_fwd");
 }
@@ -285,7 +299,7 @@ int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, v
 int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, int h, int w, int c, void* stream) {
   CB_REQUIRE(dy && x && dx_pad && n > 0 && h >= 2 && w >= 2 && c > 0 && c % 8 == 0, "cb_maxpool2x2_relu_bwd: bad arguments");
   const int64_t total = static_cast<int64_t>(n) * (h + 2) * (w + 2) * (c / 8);
-  maxpool2x2_relu_bwd_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(maxpool2x2_relu_bwd_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx_pad), n, h, w, c,
       h / 2, w / 2);
   return check_launch("cb_maxpool2x2_relu_bwd");
@@ -293,7 +307,7 @@ int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, i
 
 int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* stream) {
   CB_REQUIRE(dy && act && dx && n > 0 && n % 8 == 0, "cb_relu_mask: n must be a positive multiple of 8");
-  relu_mask_kernel<<<ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(relu_mask_kernel, ceil_div(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), static_cast<__nv_bfloat16*>(dx), n / 8);
   return check_launch("cb_relu_mask");
 }

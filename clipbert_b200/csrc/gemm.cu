@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader of the CTA pair
   const int unit = blockIdx.x / CG;                                     // persistent work unit (CTA or CTA pair)
   const int n_units = gridDim.x / CG;
-  if (threadIdx.x == 0) dbg_stamp(epi, 0);
-
+  if (threadIdx.x == 0) dbg_stamp(epi, 0);   // (debug-only buffer, not produced by any kernel: safe before pdl_wait)
+  pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kc_per_tap = (K + BK - 1) / BK;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the previous kernel's tail; from here on
+  // this kernel touches global memory (TMA loads, epilogue loads/stores), so its producers must have completed.
+  pdl_wait();
   if (threadIdx.x == 0) dbg_stamp(epi, 1);
 
   if (warp == 0) {
@@ -794,8 +797,8 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   const int units = sm_count() / CG;
   const int grid = (total < units ? total : units) * CG;
   if (CG == 1) {
-    kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(*ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-                                                      iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
+    launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+             iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/clipbert_b200.h"
 
@@ -24,6 +25,29 @@ inline int check_launch(const char* what) {
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return CB_OK;
+}
+
+// Programmatic dependent launch (PDL). Every kernel of this library starts with griddepcontrol.wait (all of its global
+// memory traffic comes after it) and griddepcontrol.launch_dependents, and is launched with the programmatic-stream-
+// serialization attribute: the next kernel's CTAs are scheduled while this one drains and run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch) under its tail. A step is ~500-900 dependent launches of 5-60 us, so the
+// ~2-4 us launch + prologue bubble between them is a double-digit share of the step. Works inside CUDA-graph capture
+// (programmatic dependency edges). cb_set_pdl(0) / CB_PDL=0 falls back to plain stream-ordered launches.
+extern std::atomic<int> g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors are picked up by check_launch()
 }
 
 // 2D bf16 row-major tensor [rows, inner] (row pitch ld elements), 128B-swizzled boxes.

@@ -56,6 +56,49 @@ class ClipBert(nn.Module):
             batch["sample_size"] = len(repeat_counts)  # batch size
         return self.transformer(_repeat_counts=list(repeat_counts), **batch)
 
+    def forward_clips(self, batch, num_clips):
+        """All ``num_clips`` clips of a step in ONE pass ("clip batching").
+
+        The reference loops ``for clip_idx in range(num_clips): model(mini_batch)`` over
+        ``visual_inputs.view(B, num_clips, num_frm, ...)[:, clip_idx]`` and stacks the logits
+        (src/tasks/run_video_retrieval.py:388-404, run_video_qa.py:470-486). Nothing on the path mixes rows of
+        different (video, clip) units (FrozenBN, per-sequence attention, per-row LayerNorm), so running the
+        ``B * num_clips`` units as one batch is the same arithmetic with twice/four times the GEMM rows and
+        1/num_clips of the launches. ``batch`` is the reference batch dict with ``visual_inputs`` still
+        ``(B, num_clips * num_frm, 3, H, W)``; returns ``dict(logits=(num_clips, B', C))`` - the tensor the
+        reference builds with ``torch.stack(logits)`` - for the caller's clip aggregation + loss. Only the
+        dropout streams differ from the loop (one seed per pass instead of one per clip).
+        """
+        vis = batch["visual_inputs"]
+        counts = [int(c) for c in batch["n_examples_list"]]
+        bsz, frames = vis.shape[0], vis.shape[1]
+        assert frames % num_clips == 0, "visual_inputs must hold num_clips * num_frm frames per video"
+        key = (tuple(counts), num_clips, str(vis.device))
+        plan = getattr(self, "_clip_plan", None)
+        if plan is None or plan[0] != key:
+            # text rows of unit (b, c) = the rows of video b; output row (c, b, e) <- pass row (b, c, e)
+            starts = [0]
+            for c in counts:
+                starts.append(starts[-1] + c)
+            gather = [starts[b] + e for b in range(bsz) for _c in range(num_clips) for e in range(counts[b])]
+            unit0 = [num_clips * starts[b] for b in range(bsz)]
+            scatter = [unit0[b] + c * counts[b] + e for c in range(num_clips) for b in range(bsz) for e in range(counts[b])]
+            dev = vis.device
+            plan = (key, torch.tensor(gather, dtype=torch.int64, device=dev), torch.tensor(scatter, dtype=torch.int64, device=dev),
+                    [counts[b] for b in range(bsz) for _c in range(num_clips)])
+            self._clip_plan = plan
+        _, gather, scatter, unit_counts = plan
+        mb = dict(visual_inputs=vis.reshape((bsz * num_clips, frames // num_clips) + tuple(vis.shape[2:])),
+                  text_input_ids=batch["text_input_ids"].index_select(0, gather),
+                  text_input_mask=batch["text_input_mask"].index_select(0, gather),
+                  labels=None, n_examples_list=unit_counts)
+        logits = self.forward(mb)["logits"]
+        if logits.shape[0] == scatter.shape[0]:
+            return dict(logits=logits.index_select(0, scatter).view(num_clips, -1, logits.shape[-1]))
+        # multiple choice: calc_loss already folded the options of a unit into one row (modeling.py:436-437)
+        assert logits.shape[0] == bsz * num_clips
+        return dict(logits=logits.view(bsz, num_clips, -1).permute(1, 0, 2).contiguous())
+
     def load_separate_ckpt(self, cnn_weights_path=None, bert_weights_path=None):
         if cnn_weights_path:
             self.cnn.load_state_dict(cnn_weights_path)

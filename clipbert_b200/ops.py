@@ -85,6 +85,11 @@ def launch_count():
     return int(L.lib().cb_launch_count())
 
 
+def set_pdl(enable):
+    """Programmatic dependent launch between the library's kernels (default on). Returns the previous setting."""
+    return int(L.lib().cb_set_pdl(int(bool(enable))))
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core contraction
 # ------------------------------------------------------------------------------------------------

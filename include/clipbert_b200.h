@@ -37,6 +37,11 @@ int cb_version(void);
 int cb_sm_arch(void);
 /* number of kernels this library has launched since load (process-wide, all threads). */
 int64_t cb_launch_count(void);
+/* Programmatic dependent launch between this library's kernels (default on; env CB_PDL=0 disables): each kernel's
+ * prologue overlaps the previous kernel's tail; every kernel issues griddepcontrol.wait before its first global
+ * access, so results are identical to plain stream order. Returns the previous setting. Replaces nothing in the
+ * reference (its ~400 launches per clip are plain stream-ordered cuDNN/cuBLAS/ATen kernels). */
+int cb_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core contraction (tcgen05.mma, TMA operand staging, TMEM accumulators).

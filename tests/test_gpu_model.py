@@ -341,3 +341,58 @@ def test_native_resolution_448_and_long_text(cuda, weights):
         ref = R.video_text_retrieval(ids, R.repeat_tensor_rows(grid, [2]), mask, weights, rnd=R.Rounding.bf16())
         got = model.transformer(ids.to(cuda), grid.to(cuda), mask.to(cuda), _repeat_counts=[2])
     assert relerr(got["logits"], ref["logits"]) < TOL_LOGITS
+
+
+def test_forward_clips_equals_the_reference_clip_loop(cuda, weights):
+    """ClipBert.forward_clips (all clips in one pass) against the per-clip loop of
+    run_video_retrieval.py:396-404 on the same model - logits and every parameter gradient - with ragged
+    n_examples_list, and with programmatic dependent launch off vs on (must be bit-identical: every kernel
+    waits for its producers before its first global access)."""
+    from clipbert_b200 import ops
+    from oracle import synth
+    model = _build("ClipBertForVideoTextRetrieval", weights, cuda).train()      # dropout p = 0 (see _build)
+    n_clips, T, B = 2, 2, 3
+    counts = [2, 1, 3]
+    batch = synth.synth_batch(B, n_clips * T, n_ex=1, size=96, seed=11)
+    ids, mask = synth.synth_text(sum(counts), 24, seed=12)
+    labels = torch.tensor([1, 0, 1, 0, 0, 1])
+    dev_batch = dict(visual_inputs=batch["visual_inputs"].to(cuda), text_input_ids=ids.to(cuda), text_input_mask=mask.to(cuda))
+
+    def lse(lg):
+        lg = lg.permute(1, 0, 2).contiguous()
+        o = torch.logsumexp(lg.view(lg.shape[0], -1), dim=-1, keepdim=True) - torch.logsumexp(lg, dim=1)
+        return torch.gather(o, -1, labels.to(cuda).view(-1, 1)).mean()
+
+    def grads():
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+
+    # reference loop
+    model.zero_grad()
+    vis = dev_batch["visual_inputs"].view(B, n_clips, T, 3, 96, 96)
+    per_clip = []
+    for c in range(n_clips):
+        mb = dict(dev_batch, visual_inputs=vis[:, c], n_examples_list=list(counts))
+        per_clip.append(model(mb)["logits"])
+    loop_logits = torch.stack(per_clip)
+    lse(loop_logits).backward()
+    g_loop = grads()
+    # one batched pass, PDL on and off
+    res = {}
+    for pdl in (1, 0):
+        prev = ops.set_pdl(pdl)
+        model.zero_grad()
+        out = model.forward_clips(dict(dev_batch, n_examples_list=list(counts)), n_clips)["logits"]
+        lse(out).backward()
+        torch.cuda.synchronize()
+        res[pdl] = (out.detach().clone(), grads())
+        ops.set_pdl(prev)
+    out, g_b = res[1]
+    assert out.shape == loop_logits.shape == (n_clips, sum(counts), 2)
+    assert relerr(out, loop_logits) < 1e-3, relerr(out, loop_logits)
+    assert set(g_b) == set(g_loop)
+    bad = [(n, relerr(g_b[n], g_loop[n])) for n in g_loop if float(g_loop[n].abs().sum()) > 0 and
+           not (relerr(g_b[n], g_loop[n]) < 2e-2 and cosine(g_b[n], g_loop[n]) > 0.999)]
+    assert not bad, bad[:8]
+    assert torch.equal(res[0][0], res[1][0]), "PDL changed the forward result"
+    # wgrad accumulates with fp32 red.add (order is not deterministic), so gradients are compared to a tight tolerance
+    assert all(relerr(res[0][1][n], res[1][1][n]) < 1e-4 for n in g_loop if float(g_loop[n].abs().sum()) > 0)

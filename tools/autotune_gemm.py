@@ -35,12 +35,17 @@ def record_step(args):
     os.environ["CB_NO_TUNING"] = "1"
     ops._tuning = {}
     ops._gemm_record = []
-    vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
-    logits = []
-    for c in range(n_clips):
-        mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"], labels=d["labels"],
-                  n_examples_list=[n_ex] * B)
-        logits.append(model(mb)["logits"])
+    if getattr(args, "clip_batching", 1):
+        mb = dict(visual_inputs=d["visual_inputs"], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
+                  labels=d["labels"], n_examples_list=[n_ex] * B)
+        logits = model.forward_clips(mb, n_clips)["logits"]
+    else:
+        vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+        logits = []
+        for c in range(n_clips):
+            mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"], labels=d["labels"],
+                      n_examples_list=[n_ex] * B)
+            logits.append(model(mb)["logits"])
     bench.lse_loss(logits, d["labels"]).backward()
     torch.cuda.synchronize()
     rec, ops._gemm_record = ops._gemm_record, None
@@ -115,6 +120,7 @@ def main():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--txt_len", type=int, default=32)
     ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--clip_batching", type=int, default=1)
     ap.add_argument("--out", default=os.path.join(ROOT, "clipbert_b200", "gemm_tuning.json"))
     ap.add_argument("--merge", type=int, default=1)
     args = ap.parse_args()
