@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libclipbert_sm100.so")
 
 CB_GEMM_TN, CB_GEMM_WGRAD = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
-AUX_NONE, AUX_RELU_MASK, AUX_GELU_GRAD, AUX_TANH_GRAD = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_GELU_STASH_GRAD = 0, 1, 2, 3, 4
+AUX_NONE, AUX_RELU_MASK, AUX_GELU_GRAD, AUX_TANH_GRAD, AUX_MUL = 0, 1, 2, 3, 4
 ROWMAP_NONE, ROWMAP_PAD, ROWMAP_UNPAD = 0, 1, 2
 
 

@@ -26,42 +26,44 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // 7x7/s2/p3 patches, K index = (r*7 + s)*3 + c with c in BGR order (the x[:, [2,1,0]] flip of
 // grid_feat.py:92-94 is folded into the gather). KP = 152 (147 zero-padded to a multiple of 8).
 // ------------------------------------------------------------------------------------------------
-// One block per (image, output row): the 7 input rows x 3 planes it needs are staged once in shared memory
-// (coalesced row reads, mean subtraction + bf16 rounding applied there, zero padding materialised), then the
-// 19 x Wo 128-bit patch chunks of that output row are written fully coalesced.
+// One block per (image, output row): the 7 input rows it needs are staged once in shared memory as PIXEL-INTERLEAVED BGR
+// rows [r][x][c] (coalesced planar reads, mean subtraction + bf16 rounding + BGR flip applied there, zero padding
+// materialised). With that layout the 21 K-elements (s, c) of tap row r of output pixel ox are ONE contiguous run
+// srow[r][6*ox .. 6*ox + 21), so a warp's 16-byte output chunks gather from consecutive shared-memory words (the planar
+// layout of the first version cost an ~8-way bank conflict per element and ran at 1.1 TB/s); the 19 x Wo 128-bit patch
+// chunks of the output row are written fully coalesced.
 template <typename TIn>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
                                                           int Ho, int Wo, int KP, float m0, float m1, float m2) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
   pdl_trigger();
-  extern __shared__ __nv_bfloat16 srow[];          // [7 rows][3 planes][W + 6]
+  extern __shared__ __nv_bfloat16 srow[];          // [7 rows][W + 6 pixels][3 channels, BGR]
   const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
   const int WP = W + 6;
+  const int RP = WP * 3;                           // row pitch in elements
   const float mean_rgb[3] = {m0, m1, m2};
   for (int i = threadIdx.x; i < 21 * WP; i += blockDim.x) {
-    const int xp = i % WP, rp = i / WP;            // rp = r * 3 + plane
+    const int xp = i % WP, rp = i / WP;            // rp = r * 3 + plane: consecutive threads read consecutive x of one plane row
     const int plane = rp % 3, r = rp / 3;
     const int iy = oy * 2 - 3 + r, ix = xp - 3;
     float v = 0.f;
     if (iy >= 0 && iy < H && ix >= 0 && ix < W)
       v = static_cast<float>(x[((static_cast<int64_t>(n) * 3 + plane) * H + iy) * W + ix]) - mean_rgb[plane];
-    srow[i] = __float2bfloat16(v);
+    srow[r * RP + xp * 3 + (2 - plane)] = __float2bfloat16(v);     // BGR channel c is RGB plane 2-c
   }
   __syncthreads();
   const int chunks = KP / 8;
   __nv_bfloat16* orow = out + (static_cast<int64_t>(n) * Ho + oy) * Wo * KP;
   for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
     const int chunk = i % chunks, ox = i / chunks;
+    const int k0 = chunk * 8;
+    int r = k0 / 21, off = k0 - r * 21;            // K index k = r * 21 + (s * 3 + c)
+    const __nv_bfloat16* src = srow + r * RP + ox * 6;
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = chunk * 8 + j;
-      __nv_bfloat16 val = __float2bfloat16(0.f);
-      if (k < 147) {
-        const int c = k % 3, rs = k / 3, sx = rs % 7, r = rs / 7;
-        val = srow[(r * 3 + (2 - c)) * WP + ox * 2 + sx];     // BGR channel c reads RGB plane 2-c
-      }
-      v[j] = val;
+      v[j] = (k0 + j < 147) ? src[off] : __float2bfloat16(0.f);
+      if (++off == 21) { off = 0; src += RP; }
     }
     *reinterpret_cast<uint4*>(orow + static_cast<int64_t>(ox) * KP + chunk * 8) = *reinterpret_cast<const uint4*>(v);
   }

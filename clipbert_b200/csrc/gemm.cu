@@ -100,7 +100,17 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
       f[2 * j + 1] += r2.y;
     }
   }
-  if (o2_16) {
+  if (epi.act == CB_ACT_GELU_STASH_GRAD) {      // out = gelu(v), out2 = gelu'(v): one erf for both
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float y0, g0, y1, g1;
+      gelu_erf_and_grad(f[2 * j], y0, g0);
+      gelu_erf_and_grad(f[2 * j + 1], y1, g1);
+      f[2 * j] = y0;
+      f[2 * j + 1] = y1;
+      if (o2_16) o2_16[j] = pack_bf16x2(g0, g1);
+    }
+  } else if (o2_16) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) o2_16[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
   }
@@ -127,6 +137,9 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
       } else if (epi.aux_mode == CB_AUX_TANH_GRAD) {
         f[2 * j] *= (1.0f - a2.x * a2.x);
         f[2 * j + 1] *= (1.0f - a2.y * a2.y);
+      } else if (epi.aux_mode == CB_AUX_MUL) {
+        f[2 * j] *= a2.x;
+        f[2 * j + 1] *= a2.y;
       }
     }
   }

@@ -376,7 +376,8 @@ class _ClipBertHeadModel(nn.Module):
             u = new(M, in_l.n) if need_backward else None
             gel = new(M, in_l.n)
             if need_backward:
-                self._gemm_fwd(a, M, in_l, gel, act=ops.ACT_GELU, out2=u, out2_ld=in_l.n)
+                # u holds gelu'(pre-activation), not the pre-activation: the backward epilogue is then one multiply
+                self._gemm_fwd(a, M, in_l, gel, act=ops.ACT_GELU_STASH_GRAD, out2=u, out2_ld=in_l.n)
             else:
                 self._gemm_fwd(a, M, in_l, gel, act=ops.ACT_GELU)
             s2 = new(M, H)
@@ -490,7 +491,7 @@ class _ClipBertHeadModel(nn.Module):
             dd = ds2d if ds2d is not None else ds2
             self._wgrad(out_l, dd, ly["gel"], M)
             du = new(M, in_l.n)
-            self._dgrad(out_l, dd, M, du, aux=ly["u"], aux_ld=in_l.n, aux_mode=ops.AUX_GELU_GRAD)
+            self._dgrad(out_l, dd, M, du, aux=ly["u"], aux_ld=in_l.n, aux_mode=ops.AUX_MUL)
             self._wgrad(in_l, du, ly["a"], M)
             ops.colsum(du, in_l.gb, M, in_l.n)
             da = new(M, H)

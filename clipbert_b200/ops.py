@@ -8,8 +8,8 @@ import ctypes
 import torch
 
 from . import _lib as L
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_GELU_GRAD, AUX_NONE, AUX_RELU_MASK,  # noqa: F401
-                   AUX_TANH_GRAD, CB_GEMM_TN, CB_GEMM_WGRAD, ROWMAP_NONE, ROWMAP_PAD, ROWMAP_UNPAD)
+from ._lib import (ACT_GELU, ACT_GELU_STASH_GRAD, ACT_NONE, ACT_RELU, ACT_TANH, AUX_GELU_GRAD, AUX_MUL, AUX_NONE,  # noqa: F401
+                   AUX_RELU_MASK, AUX_TANH_GRAD, CB_GEMM_TN, CB_GEMM_WGRAD, ROWMAP_NONE, ROWMAP_PAD, ROWMAP_UNPAD)
 
 CB_GEMM_NN = 2
 _c = ctypes
@@ -160,7 +160,8 @@ def gemm(**kw):
         if _gemm_timing is not None:
             _gemm_timing.append((e0, e1))
         if _op_timing is not None:
-            _op_timing.append(("gemm mode=%d m=%d n=%d k=%d taps=%d" % (d.mode, d.m, d.n, d.k, d.ntaps), e0, e1))
+            _op_timing.append(("gemm mode=%d m=%d n=%d k=%d taps=%d res=%d aux=%d o2=%d f32=%d rm=%d" % (
+                d.mode, d.m, d.n, d.k, d.ntaps, bool(d.residual), bool(d.aux), bool(d.out2), d.out_fp32, d.rowmap), e0, e1))
 
 
 def wgrad_split(m, n, k, ntaps=1, block_n=128):

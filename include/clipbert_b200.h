@@ -67,19 +67,25 @@ int cb_set_pdl(int enable);
  *     v = v * scale[n] + shift[n]        (FrozenBN affine / bias; either may be NULL)
  *     v = dropout(v)                     (if dropout_p > 0; counter RNG keyed by seed + out index)
  *     v += residual[m, n]                (bf16, optional)
- *     if out2: out2[row, n] = v          (bf16 pre-activation stash, optional)
+ *     if out2: out2[row, n] = v          (bf16 pre-activation stash, optional; gelu'(v) for CB_ACT_GELU_STASH_GRAD)
  *     v = act(v)                         (none / relu / gelu(erf) / tanh)
  *     v *= auxfn(aux[m, n])              (backward masks: relu' , gelu', tanh' ; optional)
  *     out[row(m), n] = v                 (bf16 or fp32)
  * row(m) re-maps between compact NHWC pixel rows and zero-bordered rows (cb_rowmap).
  * ------------------------------------------------------------------------------------------ */
 enum { CB_GEMM_TN = 0, CB_GEMM_WGRAD = 1, CB_GEMM_NN = 2 };
-enum { CB_ACT_NONE = 0, CB_ACT_RELU = 1, CB_ACT_GELU = 2, CB_ACT_TANH = 3 };
+enum {
+  CB_ACT_NONE = 0, CB_ACT_RELU = 1, CB_ACT_GELU = 2, CB_ACT_TANH = 3,
+  CB_ACT_GELU_STASH_GRAD = 4 /* out = gelu(v) and, instead of the pre-activation, out2 = gelu'(v) (bf16): the erf and the
+                                exp(-v^2/2) are shared, and the backward of BertIntermediate (transformers.py:363-366)
+                                becomes CB_AUX_MUL - one multiply - instead of re-evaluating erf + exp per element      */
+};
 enum {
   CB_AUX_NONE = 0,
   CB_AUX_RELU_MASK = 1, /* v *= (aux > 0)              aux = forward output of the ReLU       */
   CB_AUX_GELU_GRAD = 2, /* v *= gelu'(aux)             aux = forward pre-activation            */
-  CB_AUX_TANH_GRAD = 3  /* v *= 1 - aux^2              aux = forward tanh output               */
+  CB_AUX_TANH_GRAD = 3, /* v *= 1 - aux^2              aux = forward tanh output               */
+  CB_AUX_MUL = 4        /* v *= aux                    aux = stashed derivative (CB_ACT_GELU_STASH_GRAD) */
 };
 enum {
   CB_ROWMAP_NONE = 0,

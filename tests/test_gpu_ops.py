@@ -70,7 +70,14 @@ def test_gemm_epilogues(cuda, staged, shape):
     assert relerr(C, F.gelu(acc + shift)) < TOL_BF16_OP
     ops.gemm(**base, shift=shift, act=ops.ACT_TANH, out=C)
     assert relerr(C, torch.tanh(acc + shift)) < TOL_BF16_OP
+    # gelu + stashed derivative from one erf (BertIntermediate forward), consumed by AUX_MUL in the backward
+    u = acc + shift
+    ops.gemm(**base, shift=shift, act=ops.ACT_GELU_STASH_GRAD, out=C, out2=C2, out2_ld=N)
+    dgelu = 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+    assert relerr(C, F.gelu(u)) < TOL_BF16_OP and relerr(C2, dgelu) < TOL_BF16_OP
     a = AUX.float()
+    ops.gemm(**base, aux=AUX, aux_ld=N, aux_mode=ops.AUX_MUL, out=C)
+    assert relerr(C, acc * a) < TOL_BF16_OP
     gelu_grad = 0.5 * (1 + torch.erf(a / math.sqrt(2))) + a * torch.exp(-0.5 * a * a) / math.sqrt(2 * math.pi)
     for mode, fac in [(ops.AUX_RELU_MASK, (a > 0).float()), (ops.AUX_GELU_GRAD, gelu_grad), (ops.AUX_TANH_GRAD, 1 - a * a)]:
         ops.gemm(**base, residual=R, res_ld=N, aux=AUX, aux_ld=N, aux_mode=mode, out=C)

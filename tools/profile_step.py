@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--txt_len", type=int, default=32)
     ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--clip_batching", type=int, default=1)
     ap.add_argument("--out", default="gpurun_out/step_breakdown.txt")
     ap.add_argument("--ncu", type=int, default=0, help="1: bracket ONE step with cudaProfilerStart/Stop for "
                     "`ncu --profile-from-start off` instead of timing with events")
@@ -39,14 +40,21 @@ def main():
     d = {k: v.to(dev) for k, v in host.items()}
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
 
+    ops.set_pdl(0)      # per-launch durations: no prologue/tail overlap between consecutive kernels
+
     def step():
         model.zero_grad()
-        vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
-        logits = []
-        for c in range(n_clips):
-            mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
+        if args.clip_batching:
+            mb = dict(visual_inputs=d["visual_inputs"], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
                       labels=d["labels"], n_examples_list=[n_ex] * B)
-            logits.append(model(mb)["logits"])
+            logits = model.forward_clips(mb, n_clips)["logits"]
+        else:
+            vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+            logits = []
+            for c in range(n_clips):
+                mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
+                          labels=d["labels"], n_examples_list=[n_ex] * B)
+                logits.append(model(mb)["logits"])
         bench.lse_loss(logits, d["labels"]).backward()
 
     for _ in range(3):
@@ -79,15 +87,31 @@ def main():
     lines.append("-- by family")
     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]):
         lines.append("  %-28s %8.3f ms  %5.1f %%" % (k, v, 100 * v / ksum))
-    lines.append("-- by kernel/shape (total ms, count, avg us, TFLOP/s for gemm)")
-    for label, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        tf = ""
+    peaks = bench.load_peaks()
+    lines.append("-- by kernel/shape: total ms, count, avg us; for gemm: TFLOP/s, algorithmic GB/s (A + B + out + residual + aux, each once),"
+                 " ideal us = max(flop/%.0f TF/s, bytes/%.0f GB/s), lost ms = total - count x ideal" % (peaks["tflops"], peaks["hbm"]))
+    rows = []
+    for label, (ms, cnt) in agg.items():
+        tf, lost = "", 0.0
         if label.startswith("gemm"):
             f = dict(kv.split("=") for kv in label.split(" ")[1:])
             m, n, k, taps, mode = int(f["m"]), int(f["n"]), int(f["k"]), int(f["taps"]), int(f["mode"])
             fl = 2.0 * m * n * k * taps
-            tf = "%7.1f TF/s" % (fl * cnt / (ms / 1e3) / 1e12)
-        lines.append("  %-46s %8.3f ms x%-4d %8.1f us %s" % (label, ms, cnt, 1e3 * ms / cnt, tf))
+            if mode == 1:      # wgrad: A = dY [k, m], B = X [k, n], out fp32 [m, taps*n] (red.add: read + write)
+                by = 2.0 * k * (m + n) + 8.0 * m * n * taps
+            else:
+                by = 2.0 * m * k + 2.0 * n * k * taps + (4.0 if f.get("f32") == "1" else 2.0) * m * n * (1 + int(f.get("o2", 0))) \
+                    + 2.0 * m * n * (int(f.get("res", 0)) + int(f.get("aux", 0)))
+            us = 1e3 * ms / cnt
+            ideal = max(fl / (peaks["tflops"] * 1e12), by / (peaks["hbm"] * 1e9)) * 1e6
+            lost = (us - ideal) * cnt / 1e3
+            tf = "%7.1f TF/s %7.0f GB/s  ideal %6.1f us  lost %6.3f ms" % (fl / us / 1e6, by / us / 1e3, ideal, lost)
+        rows.append((lost if label.startswith("gemm") else ms, label, ms, cnt, tf))
+    for _, label, ms, cnt, tf in sorted(rows, key=lambda r: -r[2]):
+        lines.append("  %-62s %8.3f ms x%-4d %8.1f us %s" % (label, ms, cnt, 1e3 * ms / cnt, tf))
+    lines.append("-- gemm shapes by lost time")
+    for lost, label, ms, cnt, tf in sorted((r for r in rows if r[1].startswith("gemm")), key=lambda r: -r[0])[:25]:
+        lines.append("  %-62s lost %6.3f ms of %6.3f" % (label, lost, ms))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     open(args.out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:60]))
