@@ -411,33 +411,33 @@ class GridFeatBackbone(nn.Module):
         ge = self.grid_encoder[0]
         dgrid = dgrid.to(bf16).contiguous()
         p = n * (h + 2) * (w + 2)
+        # wgrad GEMMs run on the side queue beside the dgrad chain; zero-bordered buffers they read go back to the pool
+        # only after the join at the end (a recycled buffer would be overwritten by a later main-stream launch)
+        sq = ops.SideQueue()
+        recycle = []
         dg_pad = torch.empty(p, ge.cout, dtype=bf16, device=dev)
         ops.maxpool2x2_relu_bwd(dgrid, stash["gconv"], dg_pad, n, h, w, ge.cout)
+        res5_pad = stash["res5_pad"]
+        recycle.append(res5_pad)
         if ge.weight.requires_grad:
-            self._wgrad(ge, dg_pad, stash["res5_pad"], p, ntaps=9, tap_w=w + 2)
+            sq.run(lambda: self._wgrad(ge, dg_pad, res5_pad, p, ntaps=9, tap_w=w + 2), dg_pad, res5_pad)
         blocks = stash["blocks"]
-        if not blocks:
-            self._pad_put(stash["res5_pad"])
-            self._dirty = True
-            return
-        # grad w.r.t. the pre-ReLU output of the last block, compact
-        g = self._dgrad3x3(ge, dg_pad, n, h, w, stash["res5_pad"])
+        if blocks:
+            # grad w.r.t. the pre-ReLU output of the last block, compact
+            g = self._dgrad3x3(ge, dg_pad, n, h, w, res5_pad)
         del dg_pad
-        self._pad_put(stash["res5_pad"])
-        for st in reversed(blocks):
+        for st in (reversed(blocks) if blocks else ()):
             blk, hh, ww = st["blk"], st["h"], st["w"]
             rows = n * hh * ww
             pp = n * (hh + 2) * (ww + 2)
-            self._wgrad(blk.conv3, g, st["b"], rows)
+            sq.run(lambda: self._wgrad(blk.conv3, g, st["b"], rows), g, st["b"])
             db_pad = self._pad_get(pp, blk.mid, dev)
+            recycle += [db_pad, st["a_pad"]]
             self._dgrad1x1(blk.conv3, g, rows, aux=st["b"], rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=db_pad)
-            self._wgrad(blk.conv2, db_pad, st["a_pad"], pp, ntaps=9, tap_w=ww + 2)
+            sq.run(lambda: self._wgrad(blk.conv2, db_pad, st["a_pad"], pp, ntaps=9, tap_w=ww + 2), db_pad, st["a_pad"])
             da = self._dgrad3x3(blk.conv2, db_pad, n, hh, ww, st["a_pad"])
-            self._pad_put(db_pad)
-            self._pad_put(st["a_pad"])
-            self._wgrad(blk.conv1, da, st["xs"], rows)
             if blk.has_shortcut:
-                self._wgrad(blk.shortcut, g, st["xs"], rows)
+                sq.run(lambda: (self._wgrad(blk.conv1, da, st["xs"], rows), self._wgrad(blk.shortcut, g, st["xs"], rows)), da, g, st["xs"])
                 if st["first_trainable"]:
                     break                                     # d2 FREEZE_AT: no gradient below this block
                 dxs = self._dgrad1x1(blk.shortcut, g, rows)
@@ -448,7 +448,11 @@ class GridFeatBackbone(nn.Module):
                 else:
                     ops.relu_mask(dxs, st["x_in"], g)
             else:
+                sq.run(lambda: self._wgrad(blk.conv1, da, st["xs"], rows), da, st["xs"])
                 if st["first_trainable"]:
                     break
                 g = self._dgrad1x1(blk.conv1, da, rows, residual=g, aux=st["x_in"])
+        sq.join()
+        for t in recycle:
+            self._pad_put(t)
         self._dirty = True   # an optimizer step normally follows: repack bf16 operands on the next forward

@@ -468,6 +468,7 @@ class _ClipBertHeadModel(nn.Module):
         def new(*shape, dtype=bf16):
             return torch.empty(*shape, dtype=dtype, device=dev)
 
+        sq = ops.SideQueue()                               # wgrad GEMMs / bias sums run beside the dgrad chain
         dpre = self._head_backward(st, dout, nseq, H)      # grad w.r.t. pooler pre-activation
         pl = self._lin["pooler"]
         x_last = st["x_last"]
@@ -489,11 +490,10 @@ class _ClipBertHeadModel(nn.Module):
             ds2d = new(M, H) if p_h > 0 else None
             ops.layernorm_bwd(dx, ly["s2"], ly["st2"], g2, ds2, ds2d, dg2, db2, out_l.gb, p_h, ls + 3)
             dd = ds2d if ds2d is not None else ds2
-            self._wgrad(out_l, dd, ly["gel"], M)
+            sq.run(lambda: self._wgrad(out_l, dd, ly["gel"], M), dd, ly["gel"])
             du = new(M, in_l.n)
             self._dgrad(out_l, dd, M, du, aux=ly["u"], aux_ld=in_l.n, aux_mode=ops.AUX_MUL)
-            self._wgrad(in_l, du, ly["a"], M)
-            ops.colsum(du, in_l.gb, M, in_l.n)
+            sq.run(lambda: (self._wgrad(in_l, du, ly["a"], M), ops.colsum(du, in_l.gb, M, in_l.n)), du, ly["a"])
             da = new(M, H)
             self._dgrad(in_l, du, M, da, residual=ds2, res_ld=H)
             # a = LN1(s1), s1 = dropout(ctx @ Wao^T + b) + x
@@ -501,13 +501,12 @@ class _ClipBertHeadModel(nn.Module):
             ds1d = new(M, H) if p_h > 0 else None
             ops.layernorm_bwd(da, ly["s1"], ly["st1"], g1, ds1, ds1d, dg1, db1, ao_l.gb, p_h, ls + 2)
             dd1 = ds1d if ds1d is not None else ds1
-            self._wgrad(ao_l, dd1, ly["ctx"], M)
+            sq.run(lambda: self._wgrad(ao_l, dd1, ly["ctx"], M), dd1, ly["ctx"])
             dctx = new(M, H)
             self._dgrad(ao_l, dd1, M, dctx)
             dqkv = new(M, 3 * H)
             ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], dctx, ly["lse"], dqkv, nseq, L, lt, heads, p_a, ls + 1)
-            self._wgrad(qkv_l, dqkv, ly["x"], M)
-            ops.colsum(dqkv, qkv_l.gb, M, 3 * H)
+            sq.run(lambda: (self._wgrad(qkv_l, dqkv, ly["x"], M), ops.colsum(dqkv, qkv_l.gb, M, 3 * H)), dqkv, ly["x"])
             dxn = new(M, H)
             self._dgrad(qkv_l, dqkv, M, dxn, residual=ds1, res_ld=H)
             dx = dxn
@@ -523,6 +522,7 @@ class _ClipBertHeadModel(nn.Module):
         dgrid = new(nvid, T, gh, gw, H) if grid_needs_grad else None
         ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row, col, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow, dcol, dvtyp,
                              dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
+        sq.join()          # every weight gradient is in the flat buffer before the caller (all-reduce hook, optimizer) sees it
         self._dirty = True
         return dgrid
 

@@ -91,6 +91,55 @@ def set_pdl(enable):
 
 
 # ------------------------------------------------------------------------------------------------
+# side queue: weight-gradient work off the backward critical path
+# ------------------------------------------------------------------------------------------------
+class SideQueue:
+    """Runs launches that nothing downstream in the backward pass waits for (wgrad GEMMs, bias column sums) on a second
+    CUDA stream, forked from / joined back into the current stream with events, so that they fill SMs the dgrad chain
+    leaves idle (grids below 148 CTAs, tails, the LayerNorm / attention kernels between GEMMs). Works under CUDA-graph
+    capture (fork/join become graph edges). Operands are kept referenced until ``join()`` so the caching allocator cannot
+    hand their memory to a later launch on the main stream while the side stream still reads them."""
+    _streams = {}
+
+    def __init__(self, enabled=True):
+        self.enabled = bool(enabled) and overlap_wgrad
+        self.keep = []
+        self.side = None
+        self.forked = False
+
+    def _side_stream(self):
+        dev = torch.cuda.current_device()
+        st = SideQueue._streams.get(dev)
+        if st is None:
+            st = SideQueue._streams[dev] = torch.cuda.Stream(device=dev)
+        return st
+
+    def run(self, fn, *keep):
+        if not self.enabled:
+            fn()
+            return
+        if self.side is None:
+            self.side = self._side_stream()
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.keep.extend(keep)
+        self.forked = True
+
+    def join(self):
+        if self.forked:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.forked = False
+        self.keep.clear()
+
+
+overlap_wgrad = True      # module switch (bench --overlap_wgrad 0 / tests flip it)
+
+
+# ------------------------------------------------------------------------------------------------
 # tensor-core contraction
 # ------------------------------------------------------------------------------------------------
 _GEMM_PTR_FIELDS = ("a", "b", "scale", "shift", "residual", "aux", "out", "out2")
