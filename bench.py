@@ -269,7 +269,8 @@ def run_b200(args):
     cpu = None
     if True:      # every rank runs the instrumented pass (it contains the collectives); rank 0 reports
         ev = []
-        ops.set_pdl(0)               # per-launch durations: no overlap of a kernel's prologue with its predecessor's tail
+        ops.set_pdl(0)               # per-launch durations: no overlap of a kernel's prologue with its predecessor's tail,
+        ops.overlap_wgrad = False    # and one stream, so that every launch runs alone between its two events
         ops.set_gemm_timing(ev)
         for _ in range(2):
             model.zero_grad()
@@ -277,6 +278,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         ops.set_gemm_timing(None)
         ops.set_pdl(args.pdl)
+        ops.overlap_wgrad = bool(args.overlap_wgrad)
         half = len(ev) // 2
         gemm_ms = sum(a.elapsed_time(b) for a, b in ev[half:])
         n_gemm = len(ev) - half
@@ -414,7 +416,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
-    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch between the library's kernels")
+    ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -13,7 +13,7 @@ static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 static int pdl_default() {
   const char* e = getenv("CB_PDL");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] == '1') ? 1 : 0;
 }
 std::atomic<int> g_pdl{pdl_default()};
 

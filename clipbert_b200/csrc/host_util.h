@@ -32,7 +32,8 @@ inline int check_launch(const char* what) {
 // serialization attribute: the next kernel's CTAs are scheduled while this one drains and run their prologue (barrier
 // init, TMEM allocation, descriptor prefetch) under its tail. A step is ~500-900 dependent launches of 5-60 us, so the
 // ~2-4 us launch + prologue bubble between them is a double-digit share of the step. Works inside CUDA-graph capture
-// (programmatic dependency edges). cb_set_pdl(0) / CB_PDL=0 falls back to plain stream-ordered launches.
+// (programmatic dependency edges). OFF by default (cb_set_pdl(1) / CB_PDL=1 enables): it is worth +1.6 % on a single
+// stream but defeats the two-stream wgrad overlap (+9.6 %), see include/clipbert_b200.h.
 extern std::atomic<int> g_pdl;
 
 template <typename... KArgs, typename... Args>

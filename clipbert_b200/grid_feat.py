@@ -141,6 +141,7 @@ class GridFeatBackbone(nn.Module):
         self._segments = None
         self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
+        self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
         # d2 FREEZE_AT: stem (1) and res2 (2) get no gradient
         bb = self.feature.backbone
         if freeze_at >= 1:
@@ -251,6 +252,24 @@ class GridFeatBackbone(nn.Module):
         stem = self.feature.backbone.stem.conv1
         self._stem_w[:, :147] = stem._w      # [64, (r,s,c)] -> row pitch 152
         stem._w = self._stem_w
+
+    # ---- FusedAdamW hooks (clipbert_b200/optim.py) -------------------------------------------------
+    def optimizer_segments(self):
+        """Per conv weight: where its bf16 operand lives and which FrozenBN scale row-block folds into it."""
+        return [dict(param=m.weight, row_len=m.k * m.k * m.cin, scale_off=m._bn_off if hasattr(m, "norm") else -1, emit=True)
+                for _, m in self._convs()]
+
+    def optimizer_scales(self):
+        return self._bn_scale
+
+    def packed_written_by_optimizer(self):
+        """The optimizer kernel refreshed ``_flat.packed`` for every trainable conv: no re-cast on the next forward."""
+        stem = self.feature.backbone.stem.conv1
+        if stem.weight.requires_grad:       # FREEZE_AT = 0 only: the stem GEMM reads a 152-pitch copy
+            e = stem._e
+            self._stem_w[:, :147] = self._flat.packed[e["offset"]: e["offset"] + e["numel"]].view(64, 147)
+        self._dirty = False
+        self._flat.needs_repack()
 
     # ---- zero-bordered buffers --------------------------------------------------------------------
     # Only interior rows of a padded activation are ever written (CB_ROWMAP_PAD epilogues), so a buffer that was
@@ -455,4 +474,5 @@ class GridFeatBackbone(nn.Module):
         sq.join()
         for t in recycle:
             self._pad_put(t)
-        self._dirty = True   # an optimizer step normally follows: repack bf16 operands on the next forward
+        if not self._optimizer_emits_packed:
+            self._dirty = True   # an optimizer step normally follows: repack bf16 operands on the next forward

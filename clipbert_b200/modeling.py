@@ -176,6 +176,7 @@ class _ClipBertHeadModel(nn.Module):
         self._capture = None     # tests set this to a dict to receive per-layer activations
         self._pending_backward = 0
         self._grad_ready_hook = None
+        self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
 
     # ---- flat parameter storage -------------------------------------------------------------------
     def _head_linears(self):
@@ -192,6 +193,20 @@ class _ClipBertHeadModel(nn.Module):
 
     def mark_weights_updated(self):
         self._dirty = True
+
+    # ---- FusedAdamW hooks (clipbert_b200/optim.py) -------------------------------------------------
+    def optimizer_segments(self):
+        """Linear weights (the prefix of the flat buffer) have a bf16 tensor-core copy; biases, LayerNorm and embedding
+        tables are consumed in fp32."""
+        f = self._flat
+        return [dict(param=e["param"], row_len=0, scale_off=-1, emit=e["offset"] + e["numel"] <= f.packed_prefix) for e in f.entries]
+
+    def optimizer_scales(self):
+        return None
+
+    def packed_written_by_optimizer(self):
+        self._dirty = False
+        self._flat.needs_repack()
 
     def _add_linear(self, flat, name, lins, pad_rows=None):
         """Register weight(s) then bias(es) of one or several nn.Linear (fused along the output dim)."""
@@ -523,7 +538,8 @@ class _ClipBertHeadModel(nn.Module):
         ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row, col, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow, dcol, dvtyp,
                              dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
         sq.join()          # every weight gradient is in the flat buffer before the caller (all-reduce hook, optimizer) sees it
-        self._dirty = True
+        if not self._optimizer_emits_packed:
+            self._dirty = True
         return dgrid
 
     def _extra_sequence_grad(self, st):
@@ -717,6 +733,13 @@ class ClipBertForPreTraining(_ClipBertHeadModel):
         if self._word_bf16 is None or self._word_bf16.device != self._flat.master.device:
             self._word_bf16 = torch.zeros(vp, h, dtype=torch.bfloat16, device=self._flat.master.device)
         ops.cast_scale(self._flat.master[e["offset"]: e["offset"] + v * h], self._word_bf16.view(-1)[: v * h])
+
+    def packed_written_by_optimizer(self):
+        super().packed_written_by_optimizer()
+        e = self._spec["emb.word"]                 # the tied MLM decoder reads a bf16 copy of the word-embedding table
+        v, h = e["param"].shape
+        if self._word_bf16 is not None:
+            ops.cast_scale(self._flat.master[e["offset"]: e["offset"] + v * h], self._word_bf16.view(-1)[: v * h])
 
     def _head_forward(self, pooled, st, nseq, p_h, seed, need_backward):
         dev = pooled.device

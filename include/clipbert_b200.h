@@ -37,10 +37,13 @@ int cb_version(void);
 int cb_sm_arch(void);
 /* number of kernels this library has launched since load (process-wide, all threads). */
 int64_t cb_launch_count(void);
-/* Programmatic dependent launch between this library's kernels (default on; env CB_PDL=0 disables): each kernel's
- * prologue overlaps the previous kernel's tail; every kernel issues griddepcontrol.wait before its first global
- * access, so results are identical to plain stream order. Returns the previous setting. Replaces nothing in the
- * reference (its ~400 launches per clip are plain stream-ordered cuDNN/cuBLAS/ATen kernels). */
+/* Programmatic dependent launch between this library's kernels (default OFF; env CB_PDL=1 or cb_set_pdl(1) enables):
+ * each kernel's prologue overlaps the previous kernel's tail; every kernel issues griddepcontrol.wait before its first
+ * global access, so results are identical to plain stream order. Measured on B200 (profiles/r01b_ab_runs.txt): +1.6 %
+ * on a single-stream step, but it cancels the +9.6 % of running the wgrad GEMMs on a second stream, because early-
+ * launched dependent CTAs hold their 200 KB of shared memory while they wait and keep the other stream off those SMs.
+ * Returns the previous setting. Replaces nothing in the reference (its ~400 launches per clip are plain stream-
+ * ordered cuDNN/cuBLAS/ATen kernels). */
 int cb_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------
@@ -226,6 +229,28 @@ int cb_unsubsample2_mask(const void* dsub, const void* act, void* dx, int n, int
 int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, void* stream);
 int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, int h, int w, int c, void* stream);
 int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused optimizer step over the flat fp32 parameter buffers.
+ *   cb_sumsq       out[0] += sum(x^2)  - the norm half of torch.nn.utils.clip_grad_norm_ as called at
+ *                  src/tasks/run_video_retrieval.py:477-480 (one call per flat gradient buffer, caller zeroes out); with a
+ *                  chunk table only the table's elements are summed (alignment padding between parameters and the
+ *                  zero-padded classifier rows belong to no parameter), else x[0, n)
+ *   cb_adamw_step  AdamW of src/optimization/adamw.py:40-103 (eps added to sqrt(v), bias-corrected step size,
+ *                  decoupled decay p -= lr*wd*p AFTER the Adam update) on every element named by the chunk table,
+ *                  with the clip coefficient min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6)) applied to the gradient
+ *                  on the fly (grad_sumsq NULL or max_norm <= 0: no clipping), optional zeroing of the gradient
+ *                  (optimizer.zero_grad(), :486) and emission of the bf16 tensor-core operand copy (the apex amp O2
+ *                  master->model copy, :307-309) with the FrozenBN scale folded in for conv weights.
+ * chunks: int64 [nchunks][8] device = offset, numel (<= 65536), group, row_len, scale_off (-1 none), flags (bit 0: emit
+ *         packed), elem0 (index of the chunk's first element inside its parameter), 0
+ * hyper : fp32 [ngroups][8] device = lr, step_size (lr * sqrt(1-b2^t) / (1-b1^t) when correct_bias), weight_decay,
+ *         beta1, beta2, eps, 0, 0  - refreshed by the caller each step, so the launch itself is graph-capturable.
+ * ------------------------------------------------------------------------------------------ */
+int cb_sumsq(const float* x, int64_t n, const int64_t* chunks, int nchunks, float* out, void* stream);
+int cb_adamw_step(float* master, float* grad, float* exp_avg, float* exp_avg_sq, void* packed_bf16, const int64_t* chunks,
+                  int nchunks, const float* hyper, const float* scales, const float* grad_sumsq, float max_norm, int zero_grad,
+                  void* stream);
 
 #ifdef __cplusplus
 }

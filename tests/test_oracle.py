@@ -156,3 +156,50 @@ def test_rounding_matched_oracle_stays_close_to_fp32(weights):
         a = R.clipbert_forward(dict(batch), weights)["logits"]
         b = R.clipbert_forward(dict(batch), weights, rnd=R.Rounding.bf16())["logits"]
     assert float((a - b).norm() / a.norm()) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer step: oracle/adamw_ref.py against the reference's own AdamW + clip_grad_norm_
+# ------------------------------------------------------------------------------------------------
+def _adamw_case():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_adamw", os.path.join(os.path.dirname(GOLD), "..", "tools", "make_golden_adamw.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_adamw_oracle_matches_reference_golden():
+    from oracle import adamw_ref as A
+    gold = _load("adamw.pt")
+    params, grads, groups = _adamw_case().case(gold["seed"], gold["steps"])
+    for g in groups:
+        g["betas"] = (0.9, 0.98)
+    for max_norm in (-1.0, 2.0):
+        run = gold["runs"]["max_norm_%g" % max_norm]
+        traj, norms = A.run(params, grads, groups, max_norm=max_norm)
+        for t in range(gold["steps"]):
+            for a, b in zip(traj[t], run["traj"][t]):
+                assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+        for a, b in zip(norms, run["norms"]):
+            assert torch.allclose(a, b, rtol=1e-6)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="needs /root/reference")
+def test_adamw_oracle_matches_live_reference_class():
+    import warnings
+    from oracle import adamw_ref as A
+    mk = _adamw_case()
+    AdamW = mk.reference_adamw()
+    params, grads, groups = mk.case(seed=21, steps=3)
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt = AdamW([dict(params=[ps[i] for i in g["idx"]], lr=g["lr"], weight_decay=g["weight_decay"]) for g in groups], lr=1e-4)
+        for gs in grads:
+            for p, g_ in zip(ps, gs):
+                p.grad = g_.clone()
+            opt.step()
+    traj, _ = A.run(params, grads, groups)
+    for a, b in zip(traj[-1], ps):
+        assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-8)
