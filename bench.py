@@ -149,6 +149,7 @@ def run_b200(args):
     model.load_state_dict(synth.cnn_state_dict(42), strict=False)     # randomised FrozenBN statistics (random-init weights)
     model = model.to(dev).train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
+    model.cnn.stem_mode = args.stem
     if world > 1:
         model.enable_overlapped_allreduce()
 
@@ -299,6 +300,30 @@ def run_b200(args):
                     gemm_share_of_step=round(gemm_ms / eager_ms, 3),
                     whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4))
         cpu = None if (args.no_cpu or rank != 0) else cpu_baseline(args)
+    # ---- informational: the fused optimizer step that follows fwd+bwd in training (not part of the metric) ----
+    opt_info = None
+    if args.optimizer:
+        from clipbert_b200.optim import FusedAdamW
+        no_decay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+        named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
+        opt = FusedAdamW([dict(params=[p_ for n_, p_ in named if not any(nd in n_ for nd in no_decay)], weight_decay=1e-3),
+                          dict(params=[p_ for n_, p_ in named if any(nd in n_ for nd in no_decay)], weight_decay=0.0)],
+                         lr=5e-5, betas=(0.9, 0.98), model=model)
+        for _ in range(3):
+            opt.clip_grad_norm(1.0)
+            opt.step(zero_grad=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            opt.clip_grad_norm(1.0)
+            opt.step(zero_grad=True)
+        e1.record()
+        torch.cuda.synchronize()
+        opt_ms = e0.elapsed_time(e1) / 10
+        n_el = sum(p_.numel() for _, p_ in named)
+        opt_info = dict(ms_per_step=round(opt_ms, 4), params=n_el, gbytes_per_s=round(n_el * 38.0 / opt_ms / 1e6, 1),
+                        note="clip_grad_norm + AdamW + zero_grad + bf16 operand emission, 3 launches per flat buffer; 38 B per parameter")
 
     if rank == 0:
         out = dict(metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=round(value, 2), unit="clips/s", n_gpus=world,
@@ -308,12 +333,12 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad),
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4),
                    gpu_launches=int(launches), gpu_launches_per_step=int(launches // args.steps), clocks=clocks, roofline=roof,
-                   cpu_baseline=cpu)
+                   cpu_baseline=cpu, fused_optimizer=opt_info)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -415,9 +440,11 @@ def main():
     ap.add_argument("--n_ex", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
+    ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
     ap.add_argument("--cpu_batch", type=int, default=4)
+    ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -69,9 +69,59 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const TIn* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem without an im2col buffer: space-to-depth(2) of the zero-padded frame.
+//   S[n, Y, X, (dy*2 + dx)*4 + c] = padded[n, c(BGR), 2Y + dy, 2X + dx],  c = 3 is a zero lane, padded = 3 zero rows / columns
+//   on the top / left (and whatever is needed bottom / right), Y < Ho + 3, X < Wo + 3.
+// The 7x7/s2/p3 conv, its kernel zero-extended to 8x8, is then a 4-row-tap contraction: tap r' of output pixel (oy, ox) is
+// the 64 CONTIGUOUS bf16 of S pixels (oy + r', ox .. ox + 3), i.e. row (m + r'*(Wo+3)) of a matrix whose rows OVERLAP
+// (row pitch = 16 elements, row length 64): one TMA tensor map, four row-shifted K-slabs, exactly like the 3x3 convs.
+// `ld` = 16 writes S itself (54 MB per 128 frames instead of the 488 MB patch matrix); `ld` = 64 writes every row's
+// 4-pixel window explicitly (for drivers that reject overlapping tensor-map rows).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+                                                       int Hs, int Ws, int ld, float m0, float m1, float m2) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(N) * Hs * Ws;
+  if (t >= total) return;
+  const int X = static_cast<int>(t % Ws), Y = static_cast<int>((t / Ws) % Hs);
+  const int n = static_cast<int>(t / (static_cast<int64_t>(Ws) * Hs));
+  const float mean_bgr[3] = {m2, m1, m0};
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int iy = 2 * Y + dy - 3, ix = 2 * X + dx - 3;
+      const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {      // BGR channel c is RGB plane 2-c (the flip of grid_feat.py:92-94)
+        float f = 0.f;
+        if (in) f = static_cast<float>(x[((static_cast<int64_t>(n) * 3 + (2 - c)) * H + iy) * W + ix]) - mean_bgr[c];
+        v[(dy * 2 + dx) * 4 + c] = __float2bfloat16(f);
+      }
+      v[(dy * 2 + dx) * 4 + 3] = __float2bfloat16(0.f);
+    }
+  const uint4 lo = *reinterpret_cast<const uint4*>(v), hi = *reinterpret_cast<const uint4*>(v + 8);
+  if (ld == 16) {
+    uint4* o = reinterpret_cast<uint4*>(out + t * 16);
+    o[0] = lo; o[1] = hi;
+  } else {                                // row (n, Y, X - j) holds this pixel in its j-th 16-channel slot
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (X - j < 0) continue;
+      uint4* o = reinterpret_cast<uint4*>(out + (t - j) * 64 + j * 16);
+      o[0] = lo; o[1] = hi;
+    }
+  }
+}
+
 // 3x3 stride-2 pad-1 max pool, NHWC
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
-                                    int C, int Ho, int Wo) {
+                                    int C, int Ho, int Wo, int64_t row_pitch /* pixels */, int64_t img_pitch /* pixels */) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
   pdl_trigger();
   const int c8n = C / 8;
@@ -93,7 +143,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
       const int ix = ox * 2 - 1 + s;
       if (ix < 0 || ix >= W) continue;
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c8 * 8), f);
+      unpack8(*reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(n) * img_pitch + iy * row_pitch + ix) * C + c8 * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
     }
@@ -258,13 +308,37 @@ int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, 
 #define CB_NHWC_CHECK(name) \
   CB_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, name ": bad arguments (c must be a multiple of 8)")
 
-int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+int cb_maxpool3x3s2_strided(const void* x, void* y, int n, int h, int w, int c, int64_t row_pitch, int64_t img_pitch, void* stream) {
   CB_NHWC_CHECK("cb_maxpool3x3s2");
+  CB_REQUIRE(row_pitch >= w && img_pitch >= static_cast<int64_t>(h) * row_pitch, "cb_maxpool3x3s2: pitches smaller than the image");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
-  launch_k(maxpool3x3s2_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
+  launch_k(maxpool3x3s2_kernel, ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream),
+           static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo, row_pitch, img_pitch);
   return check_launch("cb_maxpool3x3s2");
+}
+
+int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  return cb_maxpool3x3s2_strided(x, y, n, h, w, c, w, static_cast<int64_t>(h) * w, stream);
+}
+
+int cb_stem_s2d(const void* x, int in_dtype, void* out, int n, int h, int w, int ld, float mean_r, float mean_g, float mean_b,
+                void* stream) {
+  CB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "cb_stem_s2d: bad arguments");
+  CB_REQUIRE(ld == 16 || ld == 64, "cb_stem_s2d: ld must be 16 (overlapping rows) or 64 (explicit 4-pixel windows)");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "cb_stem_s2d: out must be 16-byte aligned");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(n) * (ho + 3) * (wo + 3);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == 0)
+    launch_k(stem_s2d_kernel<float>, ceil_div(total, 256), 256, 0, st, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), n, h, w,
+             ho + 3, wo + 3, ld, mean_r, mean_g, mean_b);
+  else if (in_dtype == 1)
+    launch_k(stem_s2d_kernel<uint8_t>, ceil_div(total, 256), 256, 0, st, static_cast<const uint8_t*>(x), static_cast<__nv_bfloat16*>(out), n, h,
+             w, ho + 3, wo + 3, ld, mean_r, mean_g, mean_b);
+  else
+    CB_REQUIRE(false, "cb_stem_s2d: in_dtype must be 0 (fp32) or 1 (uint8)");
+  return check_launch("cb_stem_s2d");
 }
 
 int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stream) {

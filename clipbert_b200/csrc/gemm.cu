@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             } else {
               int shift = 0;
               if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
+              else if (ntaps > 1) shift = tap_sign * tp * tap_w;        // row taps (space-to-depth stem): tap t reads row m + t * tap_w
               load(sa, &tmA, kc * BK, t.m0 + shift);
               if (MODE == 0) {
                 load(sb, &tmB, tp * K + kc * BK, t.nb0);
@@ -898,7 +899,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CB_REQUIRE(d.a && d.b && d.out, "cb_gemm: null operand pointer");
   CB_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "cb_gemm: empty problem m=%d n=%d k=%d", d.m, d.n, d.k);
-  CB_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "cb_gemm: ntaps must be 1 or 9 (got %d)", d.ntaps);
+  CB_REQUIRE(d.ntaps == 1 || d.ntaps == 9 || (d.ntaps == 4 && d.mode == CB_GEMM_TN),
+             "cb_gemm: ntaps must be 1, 9 (3x3 conv) or 4 (row taps, TN only) (got %d)", d.ntaps);
   CB_REQUIRE(d.mode == CB_GEMM_TN || d.mode == CB_GEMM_WGRAD || d.mode == CB_GEMM_NN, "cb_gemm: bad mode %d", d.mode);
   CB_REQUIRE(d.dropout_p >= 0.0f && d.dropout_p < 1.0f, "cb_gemm: dropout_p out of range");
 
@@ -941,7 +943,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(!d.out2 || d.out2_ld % 8 == 0, "cb_gemm(TN): out2_ld must be a multiple of 8");
     CB_REQUIRE(!(d.out2 && d.out_fp32), "cb_gemm(TN): out2 requires a bf16 primary output");
     CB_REQUIRE(d.rowmap == CB_ROWMAP_NONE || (d.map_h > 0 && d.map_w > 0), "cb_gemm: rowmap needs map_h/map_w");
-    CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: 9-tap mode needs tap_w = W + 2");
+    CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: tap modes need tap_w (padded row pitch in pixels)");
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
     // TMA-prefetch epilogue whenever the output is bf16 (residual / aux tiles arrive by TMA; the output leaves by TMA store
     // or, when rows are re-mapped, by cooperative coalesced stores)

@@ -141,6 +141,8 @@ class GridFeatBackbone(nn.Module):
         self._segments = None
         self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
+        self.stem_mode = "s2d"   # "s2d": space-to-depth implicit GEMM (no patch matrix); "im2col": patch gather + GEMM
+        self._s2d_ld = 16        # 16: overlapping tensor-map rows; 64: explicit windows (set automatically if the driver refuses)
         self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
         # d2 FREEZE_AT: stem (1) and res2 (2) get no gradient
         bb = self.feature.backbone
@@ -216,6 +218,7 @@ class GridFeatBackbone(nn.Module):
             self._bn_scale = torch.empty(ctot, dtype=torch.float32, device=device)
             self._bn_shift = torch.empty(ctot, dtype=torch.float32, device=device)
             self._stem_w = torch.zeros(64, STEM_KP, dtype=torch.bfloat16, device=device)
+            self._stem_w_s2d = torch.zeros(64, 256, dtype=torch.bfloat16, device=device)
             self._segments = None
             self._pad_pool = {}
             self._dirty = True
@@ -251,6 +254,7 @@ class GridFeatBackbone(nn.Module):
             m._gw = flat.grad[e["offset"]: e["offset"] + n].view(m.cout, row_len)
         stem = self.feature.backbone.stem.conv1
         self._stem_w[:, :147] = stem._w      # [64, (r,s,c)] -> row pitch 152
+        self._pack_stem_s2d(stem._w)
         stem._w = self._stem_w
 
     # ---- FusedAdamW hooks (clipbert_b200/optim.py) -------------------------------------------------
@@ -268,8 +272,16 @@ class GridFeatBackbone(nn.Module):
         if stem.weight.requires_grad:       # FREEZE_AT = 0 only: the stem GEMM reads a 152-pitch copy
             e = stem._e
             self._stem_w[:, :147] = self._flat.packed[e["offset"]: e["offset"] + e["numel"]].view(64, 147)
+            self._pack_stem_s2d(self._stem_w[:, :147])
         self._dirty = False
         self._flat.needs_repack()
+
+    def _pack_stem_s2d(self, w147):
+        """[64, (r, s, c)] 7x7x3 (BN scale folded) -> [64, (r', x', dy, dx, c4)] = [64, 256] for the space-to-depth stem:
+        kernel zero-extended to 8x8x4, row r = 2r' + dy, column s = 2x' + dx (see cb_stem_s2d in the C header)."""
+        w = torch.zeros(64, 8, 8, 4, dtype=w147.dtype, device=w147.device)
+        w[:, :7, :7, :3] = w147.reshape(64, 7, 7, 3)
+        self._stem_w_s2d.copy_(w.view(64, 4, 2, 4, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(64, 256))
 
     # ---- zero-bordered buffers --------------------------------------------------------------------
     # Only interior rows of a padded activation are ever written (CB_ROWMAP_PAD epilogues), so a buffer that was
@@ -329,18 +341,43 @@ class GridFeatBackbone(nn.Module):
         x = x.contiguous()
         bb = self.feature.backbone
         bf16 = torch.bfloat16
-        # ---- stem: im2col gather (BGR flip + cast fused) -> GEMM(+BN shift, ReLU) -> maxpool 3x3/s2 ----
+        # ---- stem: 7x7/s2 conv (+BN shift, ReLU) -> maxpool 3x3/s2 ----
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        col = torch.empty(n * ho * wo, STEM_KP, dtype=bf16, device=dev)
-        ops.stem_im2col(x, col, n, h, w, STEM_KP, mean)
-        stem = bb.stem.conv1
-        c1 = torch.empty(n * ho * wo, 64, dtype=bf16, device=dev)
-        ops.gemm(mode=ops.CB_GEMM_TN, m=n * ho * wo, n=64, k=STEM_KP, a=col, a_rows=n * ho * wo, a_ld=STEM_KP, b=stem._w,
-                 b_rows=64, b_ld=STEM_KP, shift=stem._shift, act=ops.ACT_RELU, out=c1, out_ld=64)
-        del col
         hh, ww = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+        stem = bb.stem.conv1
         cur = torch.empty(n * hh * ww, 64, dtype=bf16, device=dev)
-        ops.maxpool3x3s2(c1, cur, n, ho, wo, 64)
+        mode = self.stem_mode
+        if mode == "s2d":
+            # space-to-depth frame (no patch matrix) -> 4-row-tap tcgen05 GEMM over its overlapping 64-element rows; the
+            # output keeps the (ho+3) x (wo+3) grid of the s2d frame, the pool reads it with those pitches
+            hs, ws = ho + 3, wo + 3
+            rows = n * hs * ws
+            ld = self._s2d_ld
+            s2d = torch.empty((rows + 4) * ld, dtype=bf16, device=dev)        # + slack: the last rows' windows run past the frame
+            ops.stem_s2d(x, s2d, n, h, w, ld, mean)
+            c1 = torch.empty(rows, 64, dtype=bf16, device=dev)
+            kw = dict(mode=ops.CB_GEMM_TN, m=rows, n=64, k=64, a=s2d, a_rows=rows, a_ld=ld, b=self._stem_w_s2d, b_rows=64, b_ld=256,
+                      ntaps=4, tap_w=ws, tap_sign=1, shift=stem._shift, act=ops.ACT_RELU, out=c1, out_ld=64)
+            try:
+                ops.gemm(**kw)
+            except RuntimeError as e:      # a driver that rejects overlapping tensor-map rows: store the windows explicitly
+                if ld == 64 or "cuTensorMapEncodeTiled" not in str(e):
+                    raise
+                self._s2d_ld = ld = 64
+                s2d = torch.empty((rows + 4) * ld, dtype=bf16, device=dev)
+                ops.stem_s2d(x, s2d, n, h, w, ld, mean)
+                ops.gemm(**dict(kw, a=s2d, a_ld=ld))
+            del s2d
+            ops.maxpool3x3s2(c1, cur, n, ho, wo, 64, row_pitch=ws, img_pitch=hs * ws)
+        else:
+            # im2col gather (BGR flip + cast fused) -> GEMM over the [pixels, 152] patch matrix
+            col = torch.empty(n * ho * wo, STEM_KP, dtype=bf16, device=dev)
+            ops.stem_im2col(x, col, n, h, w, STEM_KP, mean)
+            c1 = torch.empty(n * ho * wo, 64, dtype=bf16, device=dev)
+            ops.gemm(mode=ops.CB_GEMM_TN, m=n * ho * wo, n=64, k=STEM_KP, a=col, a_rows=n * ho * wo, a_ld=STEM_KP, b=stem._w,
+                     b_rows=64, b_ld=STEM_KP, shift=stem._shift, act=ops.ACT_RELU, out=c1, out_ld=64)
+            del col
+            ops.maxpool3x3s2(c1, cur, n, ho, wo, 64)
         del c1
         if self._capture is not None:
             self._capture["stem"] = cur.view(n, hh, ww, 64)

@@ -32,6 +32,8 @@ _SIGS = {
     "cb_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_stem_im2col": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
     "cb_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "cb_maxpool3x3s2_strided": [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp],
+    "cb_stem_s2d": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
     "cb_subsample2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "cb_unsubsample2_mask": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cb_maxpool2x2_relu_fwd": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -295,8 +297,16 @@ def stem_im2col(x, out, n, h, w, kp, mean=(0.0, 0.0, 0.0)):
     _call("cb_stem_im2col", _p(x), dt, _p(out), n, h, w, kp, mean[0], mean[1], mean[2], _s())
 
 
-def maxpool3x3s2(x, y, n, h, w, c):
-    _call("cb_maxpool3x3s2", _p(x), _p(y), n, h, w, c, _s())
+def stem_s2d(x, out, n, h, w, ld, mean=(0.0, 0.0, 0.0)):
+    dt = 0 if x.dtype == torch.float32 else 1
+    _call("cb_stem_s2d", _p(x), dt, _p(out), n, h, w, ld, mean[0], mean[1], mean[2], _s())
+
+
+def maxpool3x3s2(x, y, n, h, w, c, row_pitch=None, img_pitch=None):
+    if row_pitch is None:
+        _call("cb_maxpool3x3s2", _p(x), _p(y), n, h, w, c, _s())
+    else:
+        _call("cb_maxpool3x3s2_strided", _p(x), _p(y), n, h, w, c, row_pitch, img_pitch, _s())
 
 
 def subsample2(x, y, n, h, w, c):

@@ -59,6 +59,7 @@ int cb_set_pdl(int enable);
  *     ntaps = 1 for Linear / 1x1 conv. ntaps = 9 is a 3x3 pad-1 conv over a zero-bordered
  *     ("padded") NHWC activation whose rows are flat pixels p = (img*(H+2) + y)*(W+2) + x;
  *     shift_t = tap_sign * ((t/3 - 1)*(W+2) + (t%3 - 1)). tap_sign = -1 gives the dgrad conv.
+ *     ntaps = 4 ("row taps", TN only): shift_t = tap_sign * t * tap_w - the space-to-depth stem (cb_stem_s2d).
  * mode CB_GEMM_NN : as TN but B is stored [K, ntaps*N] row-major (the forward weight [out=K, in=N]
  *     read "MN-major"): out[m, n] = epi( sum_t sum_k A[m + shift_t, k] * B[k, t*N + n] ). This is
  *     the dgrad of Linear / conv straight from the forward weight layout (no transposed copy).
@@ -214,7 +215,14 @@ int cb_cast_scale_segments(const float* master, void* packed, const int64_t* seg
  *                           K = (r, s, c) with c in BGR order (the x[:, [2,1,0]] flip of grid_feat.py:92-94
  *                           is folded in); in_dtype 1 = uint8 frames with the ImageNorm mean subtraction
  *                           (src/datasets/data_utils.py:256-276) fused. The stem GEMM follows.
- *   cb_maxpool3x3s2         BasicStem max_pool2d(3, 2, 1)
+ *   cb_stem_s2d             the stem WITHOUT a patch matrix: space-to-depth(2) of the zero-padded BGR frame,
+ *                           S[n, Y, X, (dy*2+dx)*4 + c] (c = 3 is a zero lane), Y < ho+3, X < wo+3. The 7x7/s2/p3 conv
+ *                           (kernel zero-extended to 8x8) is then cb_gemm with ntaps = 4, k = 64, tap_w = wo+3 over
+ *                           the matrix whose row m is the 64 contiguous bf16 starting at S pixel m: ld = 16 makes the
+ *                           rows overlap (a_ld = 16 < k; 54 MB per 128 frames instead of 488 MB of patches), ld = 64
+ *                           stores every 4-pixel window explicitly. Output rows follow the same (ho+3) x (wo+3) grid.
+ *   cb_maxpool3x3s2         BasicStem max_pool2d(3, 2, 1); _strided reads an input whose pixel rows / images are
+ *                           row_pitch / img_pitch pixels apart (the (ho+3) x (wo+3) grid of the s2d stem)
  *   cb_subsample2           input of a stride-2 1x1 conv (res3/4/5 block 0 conv1 + shortcut)
  *   cb_unsubsample2_mask    its backward fused with the ReLU mask of the producing block
  *   cb_maxpool2x2_relu_fwd  grid_encoder MaxPool2d(2,2) + ReLU (7x7 -> 3x3 at 224 px, 14x14 -> 7x7 at 448)
@@ -223,7 +231,10 @@ int cb_cast_scale_segments(const float* master, void* packed, const int64_t* seg
  * ------------------------------------------------------------------------------------------ */
 int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, int kp, float mean_r, float mean_g,
                    float mean_b, void* stream);
+int cb_stem_s2d(const void* x, int in_dtype, void* out, int n, int h, int w, int ld, float mean_r, float mean_g, float mean_b,
+                void* stream);
 int cb_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int cb_maxpool3x3s2_strided(const void* x, void* y, int n, int h, int w, int c, int64_t row_pitch, int64_t img_pitch, void* stream);
 int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stream);
 int cb_unsubsample2_mask(const void* dsub, const void* act, void* dx, int n, int h, int w, int c, void* stream);
 int cb_maxpool2x2_relu_fwd(const void* x, void* y, int n, int h, int w, int c, void* stream);

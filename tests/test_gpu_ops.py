@@ -425,6 +425,56 @@ def test_stem_im2col_matches_unfold_with_bgr_flip(cuda, hw):
     assert torch.equal(col, col2)
 
 
+@pytest.mark.parametrize("ld", [16, 64])
+@pytest.mark.parametrize("hw", [(224, 224), (64, 96), (38, 54)])
+def test_stem_space_to_depth_conv_matches_conv2d(cuda, hw, ld):
+    """The patch-matrix-free stem: cb_stem_s2d -> 4-row-tap cb_gemm over overlapping rows -> strided max pool, against
+    F.conv2d(7, s2, p3) on the bf16-rounded BGR frame + F.max_pool2d, and bit-exact frame layout (index op)."""
+    ops = _ops()
+    H, W = hw
+    N = 2
+    g = torch.Generator().manual_seed(24)
+    u8 = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    mean = (123.675, 116.28, 103.53)
+    xf = u8.float() - torch.tensor(mean).view(1, 3, 1, 1)
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    hs, ws = ho + 3, wo + 3
+    rows = N * hs * ws
+    s2d = torch.zeros((rows + 4) * ld, device=cuda, dtype=torch.bfloat16)
+    ops.stem_s2d(u8.to(cuda), s2d, N, H, W, ld, mean)
+    # ---- layout, bit-exact: S[n, Y, X, (dy*2+dx)*4 + c] = padded_bgr[n, c, 2Y+dy, 2X+dx]
+    pad = torch.zeros(N, 3, 2 * hs, 2 * ws)
+    pad[:, :, 3:3 + H, 3:3 + W] = xf[:, [2, 1, 0]]
+    ref = torch.zeros(N, hs, ws, 2, 2, 4)
+    ref[..., :3] = pad.view(N, 3, hs, 2, ws, 2).permute(0, 2, 4, 3, 5, 1)
+    ref = ref.reshape(rows, 16).to(torch.bfloat16)
+    if ld == 16:
+        assert torch.equal(s2d[: rows * 16].view(rows, 16).cpu(), ref)
+    else:
+        win = s2d[: rows * 64].view(N, hs, ws, 4, 16).cpu()
+        r4 = ref.view(N, hs, ws, 16)
+        for j in range(4):          # slot j of row (Y, X) = pixel (Y, X + j) wherever that pixel exists
+            assert torch.equal(win[:, :, : ws - j, j], r4[:, :, j:])
+    # ---- conv + BN shift + ReLU + pool through the tensor cores
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * 0.02)                 # BGR-order weights, as the model's
+    shift = torch.randn(64, generator=g).to(cuda)
+    w147 = wt.permute(0, 2, 3, 1).reshape(64, 147).to(torch.bfloat16)
+    w8 = torch.zeros(64, 8, 8, 4, dtype=torch.bfloat16)
+    w8[:, :7, :7, :3] = w147.view(64, 7, 7, 3)
+    wp = w8.view(64, 4, 2, 4, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(64, 256).contiguous().to(cuda)
+    c1 = torch.empty(rows, 64, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(mode=ops.CB_GEMM_TN, m=rows, n=64, k=64, a=s2d, a_rows=rows, a_ld=ld, b=wp, b_rows=64, b_ld=256, ntaps=4, tap_w=ws,
+             tap_sign=1, shift=shift, act=ops.ACT_RELU, out=c1, out_ld=64)
+    xb = xf[:, [2, 1, 0]].to(torch.bfloat16).float()
+    conv = F.relu(F.conv2d(xb, w147.float().view(64, 7, 7, 3).permute(0, 3, 1, 2), stride=2, padding=3) + shift.cpu().view(1, 64, 1, 1))
+    got = c1.view(N, hs, ws, 64)[:, :ho, :wo].float().cpu().permute(0, 3, 1, 2)
+    assert relerr(got, conv) < TOL_BF16_OP
+    hh, ww = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    y = torch.empty(N, hh, ww, 64, device=cuda, dtype=torch.bfloat16)
+    ops.maxpool3x3s2(c1, y, N, ho, wo, 64, row_pitch=ws, img_pitch=hs * ws)
+    assert torch.equal(y.float().cpu(), F.max_pool2d(got, 3, 2, 1).permute(0, 2, 3, 1))
+
+
 def test_pool_and_subsample_ops(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(15)
