@@ -22,9 +22,11 @@ namespace cb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int GEMM_THREADS = 64 + EPI_THREADS;
+// Epilogue warps: 8 (two per TMEM lane quarter, 32 columns each per 64-column chunk) or, for the TMA epilogue, 16 (four per
+// quarter, 16 columns each). ncu on the 8-warp HBM-bound 1x1 convs (profiles/r01b_gemm_full_stalls.txt): two warps per
+// scheduler issue only 38 % of the cycles of a chunk - the rest is fixed-latency / scoreboard / barrier wait nothing else
+// can fill; four warps per scheduler with half the registers each hide it.
+constexpr int gemm_threads(int ew) { return 64 + ew * 32; }
 constexpr int MAX_STAGES = 8;
 constexpr int CHUNK_BYTES = BM * 128;           // one 128-row x 64-column bf16 chunk (TMA epilogue path)
 constexpr int SMEM_LIMIT = 232448;              // 227 KB opt-in limit per CTA
@@ -66,12 +68,13 @@ struct GemmCfg {
 };
 
 // fused elementwise epilogue on 32 consecutive columns [nb, nb+32) of one output row
-__device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi, int nb, int N, int64_t orow,
+template <int NC>
+__device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi, int nb, int N, int64_t orow,
                                               const uint32_t* res16, const uint32_t* aux16, uint32_t* o2_16) {
   if (nb >= N) return;
   if (epi.scale) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < NC; j += 4) {
       if (nb + j + 4 <= N) {
         const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.scale + nb + j));
         f[j] *= s4.x; f[j + 1] *= s4.y; f[j + 2] *= s4.z; f[j + 3] *= s4.w;
@@ -80,7 +83,7 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
   }
   if (epi.shift) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < NC; j += 4) {
       if (nb + j + 4 <= N) {
         const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
         f[j] += s4.x; f[j + 1] += s4.y; f[j + 2] += s4.z; f[j + 3] += s4.w;
@@ -90,11 +93,11 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
   if (epi.drop_thresh) {
     const uint64_t base = static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] *= dropout_mult(epi.seed, base + j, epi.drop_thresh, epi.drop_inv_keep);
+    for (int j = 0; j < NC; ++j) f[j] *= dropout_mult(epi.seed, base + j, epi.drop_thresh, epi.drop_inv_keep);
   }
   if (res16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NC / 2; ++j) {
       const float2 r2 = unpack_bf16x2(res16[j]);
       f[2 * j] += r2.x;
       f[2 * j + 1] += r2.y;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
   }
   if (epi.act == CB_ACT_GELU_STASH_GRAD) {      // out = gelu(v), out2 = gelu'(v): one erf for both
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NC / 2; ++j) {
       float y0, g0, y1, g1;
       gelu_erf_and_grad(f[2 * j], y0, g0);
       gelu_erf_and_grad(f[2 * j + 1], y1, g1);
@@ -112,21 +115,21 @@ __device__ __forceinline__ void epilogue_math(float (&f)[32], const GemmEpi& epi
     }
   } else if (o2_16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o2_16[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    for (int j = 0; j < NC / 2; ++j) o2_16[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
   }
   if (epi.act == CB_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (epi.act == CB_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < NC; ++j) f[j] = gelu_erf(f[j]);
   } else if (epi.act == CB_ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+    for (int j = 0; j < NC; ++j) f[j] = tanhf(f[j]);
   }
   if (aux16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NC / 2; ++j) {
       const float2 a2 = unpack_bf16x2(aux16[j]);
       if (epi.aux_mode == CB_AUX_RELU_MASK) {
         f[2 * j] = a2.x > 0.0f ? f[2 * j] : 0.0f;
@@ -181,14 +184,18 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles
   return t;
 }
 
-template <int BN, int MODE, int EPI, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int MODE, int EPI, int CG, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
                 int tap_w, int tap_sign,
                 int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, GemmEpi epi) {
   using Cfg = GemmCfg<BN, CG>;
+  constexpr int EPI_WARPS = EW;
+  constexpr int EPI_THREADS = EW * 32;
+  constexpr int NGRP = EW / 4;                  // warps sharing one TMEM lane quarter
+  static_assert(EW == 8 || (EW == 16 && EPI == 1), "16 epilogue warps only with the TMA epilogue");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = KCH * Cfg::STAGE_BYTES;           // a stage holds KCH consecutive 64-deep k-chunks (one barrier round trip)
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
       const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: cooperative coalesced stores instead of TMA
-      const int etid = threadIdx.x - 64;                // 0..255 among the epilogue threads
+      const int etid = threadIdx.x - 64;                // index among the epilogue threads
       const bool elected = (ew == 0 && lane == 0);
       const int row = q * 32 + lane;                    // row inside the 128-row tile
       const int swz = row & 7;                          // 128B-swizzle XOR of this row
@@ -403,25 +410,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++g) {
+          constexpr int NC = 64 / NGRP;                 // columns of a 64-column chunk owned by this thread: 32 (8 warps) or 16
+          constexpr int NU = NC / 8;                    // ... in 16-byte units
           const int b = g & 1;
           const uint32_t bph = (g >> 1) & 1;
-          const int nb = t.n0 + c * 64 + grp * 32;      // this thread's 32 columns
-          uint32_t v[32];
+          const int nb = t.n0 + c * 64 + grp * NC;      // this thread's columns
+          uint32_t v[NC];
           __syncwarp();
-          tmem_ld32(trow + c * 64 + grp * 32, v);
+          if constexpr (NC == 32) tmem_ld32(trow + c * 64 + grp * NC, reinterpret_cast<uint32_t(&)[32]>(v));
+          else tmem_ld16(trow + c * 64 + grp * NC, reinterpret_cast<uint32_t(&)[16]>(v));
           tmem_ld_wait();
           if (c == CPT - 1) {                           // last TMEM read of this tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) release_acc(&tempty_bar[acc]);
           }
-          uint32_t res16[16], aux16[16];
+          uint32_t res16[NC / 2], aux16[NC / 2];
           if (has_res) {
             mbar_wait(&rfull_bar[b], bph);
             const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rr + (((grp * 4 + j) ^ swz) << 4));
+            for (int j = 0; j < NU; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rr + (((grp * NU + j) ^ swz) << 4));
               res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
             }
           }
@@ -429,27 +439,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             mbar_wait(&xfull_bar[b], bph);
             const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(xr + (((grp * 4 + j) ^ swz) << 4));
+            for (int j = 0; j < NU; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(xr + (((grp * NU + j) ^ swz) << 4));
               aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
             }
           }
-          float f[32];
+          float f[NC];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          uint32_t o2_16[16];
-          epilogue_math(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
+          for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
+          uint32_t o2_16[NC / 2];
+          epilogue_math<NC>(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
           const int cb = g & (n_cbuf - 1);
           uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
           if (has_out2) {
             uint8_t* c2r = c2buf + cb * CHUNK_BYTES + row * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(c2r + (((grp * 4 + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+            for (int j = 0; j < NU; ++j)
+              *reinterpret_cast<uint4*>(c2r + (((grp * NU + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(cr + (((grp * 4 + j) ^ swz) << 4)) =
+          for (int j = 0; j < NU; ++j)
+            *reinterpret_cast<uint4*>(cr + (((grp * NU + j) ^ swz) << 4)) =
                 make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           if (!remap) {
@@ -471,12 +481,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           if (remap) {
             // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment,
-            // 32 rows per pass; the buffer is rewritten two chunks later, after the next named barrier
+            // EPI_THREADS / 8 rows per pass; the buffer is rewritten two chunks later, after the next named barrier
             const int seg = etid & 7;
             const int n = t.n0 + c * 64 + seg * 8;
+            constexpr int ROWS_PER_PASS = EPI_THREADS / 8;
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int r = (etid >> 3) + pass * 32;
+            for (int pass = 0; pass < 128 / ROWS_PER_PASS; ++pass) {
+              const int r = (etid >> 3) + pass * ROWS_PER_PASS;
               const int mm = t.m0 + r;
               bool ok = mm < M && n + 8 <= N;
               int64_t orr = mm;
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
               const int nb = ncol + h * 32;
-              epilogue_math(f, epi, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
+              epilogue_math<32>(f, epi, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
                             epi.out2 ? o2 + h * 16 : nullptr);
               if (epi.out_fp32) {
                 // fp32 output: stage 32 columns (128 B per row) and store coalesced right away
@@ -723,6 +734,7 @@ static int sm_count() {
 static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
 static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
+static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
 // stage. Measured (profiles/r01_gemm_kch_probe.txt, r01_gemm_staged_probe.txt): every stage costs a ~450-cycle barrier
@@ -736,7 +748,7 @@ static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_a
   p.chunk_bytes = BM * BK * 2 + (bn / cg) * BK * 2;
   p.n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
   if (tma_epi) p.epi_bytes = p.n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + 2 * CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
-  else p.epi_bytes = (EPI_WARPS * STG_BYTES + 1023) & ~1023;
+  else p.epi_bytes = (8 * STG_BYTES + 1023) & ~1023;     // staged epilogue: always 8 warps
   const int chunks_fit = (SMEM_LIMIT - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
   p.kch = 1;
   if (force_kch > 0) p.kch = force_kch;
@@ -751,11 +763,12 @@ static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_a
   return p;
 }
 
-template <int BN, int MODE, int EPI, int CG>
+template <int BN, int MODE, int EPI, int CG, int EW = 8>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
+  constexpr int GEMM_THREADS = gemm_threads(EW);
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE, EPI, CG>;
+  auto kern = gemm_kernel<BN, MODE, EPI, CG, EW>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
@@ -891,6 +904,7 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi
 extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline = static_cast<long long*>(device_buf); }
 extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
+extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;
@@ -952,17 +966,27 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
     const LaunchCfg lc = choose_config(d, force_cg, tma_epi);
-#define CB_DISPATCH(BN_, CG_)                                                                                                \
-  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))         \
-            : (tma_epi ? launch_gemm<BN_, 0, 1, CG_>(d, epi, stream) : launch_gemm<BN_, 0, 0, CG_>(d, epi, stream))
+#define CB_DISPATCH(BN_, CG_, EW_)                                                                                                  \
+  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_, EW_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))            \
+            : (tma_epi ? launch_gemm<BN_, 0, 1, CG_, EW_>(d, epi, stream) : launch_gemm<BN_, 0, 0, CG_>(d, epi, stream))
     if (lc.cg == 2) {
-      if (lc.bn == 128) { CB_DISPATCH(128, 2); }
-      CB_DISPATCH(256, 2);
+      if (lc.bn == 128) { CB_DISPATCH(128, 2, 8); }
+      CB_DISPATCH(256, 2, 8);
+    }
+    // TMA epilogue: 16 epilogue warps (4 per scheduler) unless the caller pins the 8-warp variant (reserved bit 4: A/B runs)
+    const bool ew16 = g_epi_warps == 16 && (d.reserved & 16) == 0;
+    if (ew16) {
+      switch (lc.bn) {
+        case 64: CB_DISPATCH(64, 1, 16);
+        case 128: CB_DISPATCH(128, 1, 16);
+        case 256: CB_DISPATCH(256, 1, 16);
+        default: break;
+      }
     }
     switch (lc.bn) {
-      case 64: CB_DISPATCH(64, 1);
-      case 128: CB_DISPATCH(128, 1);
-      case 256: CB_DISPATCH(256, 1);
+      case 64: CB_DISPATCH(64, 1, 8);
+      case 128: CB_DISPATCH(128, 1, 8);
+      case 256: CB_DISPATCH(256, 1, 8);
       default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", lc.bn);
     }
 #undef CB_DISPATCH

@@ -87,6 +87,11 @@ def launch_count():
     return int(L.lib().cb_launch_count())
 
 
+def set_epi_warps(n):
+    """Tuning hook: epilogue warps of the GEMM's TMA epilogue, 16 (default) or 8."""
+    L.lib().cb_debug_gemm_epi_warps(int(n))
+
+
 def set_pdl(enable):
     """Programmatic dependent launch between the library's kernels (default on). Returns the previous setting."""
     return int(L.lib().cb_set_pdl(int(bool(enable))))
