@@ -26,7 +26,7 @@ constexpr int BK = 64;
 // quarter, 16 columns each). ncu on the 8-warp HBM-bound 1x1 convs (profiles/r01b_gemm_full_stalls.txt): two warps per
 // scheduler issue only 38 % of the cycles of a chunk - the rest is fixed-latency / scoreboard / barrier wait nothing else
 // can fill; four warps per scheduler with half the registers each hide it.
-constexpr int gemm_threads(int ew) { return 64 + ew * 32; }
+constexpr int gemm_threads(int ew) { return 96 + ew * 32; }   // TMA producer, MMA issuer, epilogue loader, EW epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int CHUNK_BYTES = BM * 128;           // one 128-row x 64-column bf16 chunk (TMA epilogue path)
 constexpr int SMEM_LIMIT = 232448;              // 227 KB opt-in limit per CTA
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
                 int tap_w, int tap_sign,
-                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, GemmEpi epi) {
+                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, int n_rbuf, GemmEpi epi) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int EPI_WARPS = EW;
   constexpr int EPI_THREADS = EW * 32;
@@ -247,9 +247,9 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator stage drained by the epilogue
-  uint64_t* rfull_bar = tempty_bar + 2;          // [2] residual chunk landed (EPI 1)
-  uint64_t* xfull_bar = rfull_bar + 2;           // [2] aux chunk landed (EPI 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;          // [4] residual / aux chunk landed (EPI 1)
+  uint64_t* rempty_bar = rfull_bar + 4;          // [4] ... and consumed by every epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -274,8 +274,10 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], EPI_WARPS * CG);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&rfull_bar[s], 1);
-      mbar_init(&xfull_bar[s], 1);
+      mbar_init(&rempty_bar[s], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -396,13 +398,38 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
       }
       dbg_stamp(epi, 6);
     }
+  } else if (warp == 2) {
+    // ===================== epilogue loader =====================
+    // One thread streams the residual / aux tiles of every 64-column output chunk of this CTA into a ring of n_rbuf
+    // swizzled smem buffers, running ahead of the epilogue warps (rempty / rfull mbarriers). It used to be the elected
+    // epilogue thread's job after every chunk barrier: ~200 serial single-thread instructions (tile decode, two TMA
+    // issues) on the critical path of all sixteen epilogue warps, and a fixed look-ahead of two chunks.
+    if (EPI == 1 && lane == 0 && (epi.residual != nullptr || epi.aux != nullptr)) {
+      constexpr int CPT = BN / 64;
+      const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr, has_out2 = epi.out2 != nullptr;
+      uint8_t* rbuf = stg_base + n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1);
+      uint8_t* xbuf = rbuf + (has_res ? n_rbuf * CHUNK_BYTES : 0);
+      const uint32_t bytes = CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
+      int g = 0;
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        for (int c = 0; c < CPT; ++c, ++g) {
+          const int b = g & (n_rbuf - 1);
+          const uint32_t ph = (g / n_rbuf) & 1;
+          mbar_wait(&rempty_bar[b], ph ^ 1);
+          mbar_expect_tx(&rfull_bar[b], bytes);
+          if (has_res) tma_load_2d(rbuf + b * CHUNK_BYTES, &tmR, &rfull_bar[b], t.n0 + c * 64, t.m0);
+          if (has_aux) tma_load_2d(xbuf + b * CHUNK_BYTES, &tmX, &rfull_bar[b], t.n0 + c * 64, t.m0);
+        }
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     auto release_acc = [&](uint64_t* bar) {   // hand the accumulator stage back to the (leader's) MMA warp
       if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
       else mbar_arrive(bar);
     };
-    const int ew = warp - 2;          // 0..7
+    const int ew = warp - 3;          // 0 .. EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = ew >> 2;          // two warps share each lane quarter and split the columns
     int local = 0;
@@ -413,34 +440,15 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
       uint8_t* cbuf = stg_base;                         // [n_cbuf][128 x 128 B] output chunks (n_cbuf = 2 or 4)
       const bool has_out2 = epi.out2 != nullptr;        // pre-activation stash: a second set of output chunks
       uint8_t* c2buf = cbuf + n_cbuf * CHUNK_BYTES;
-      uint8_t* rbuf = c2buf + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [2] residual chunks (if any)
-      uint8_t* xbuf = rbuf + (epi.residual ? 2 * CHUNK_BYTES : 0);
+      uint8_t* rbuf = c2buf + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [n_rbuf] residual chunks (if any), filled by the loader warp
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
+      uint8_t* xbuf = rbuf + (has_res ? n_rbuf * CHUNK_BYTES : 0);     // [n_rbuf] aux chunks
+      const bool has_in = has_res || has_aux;
       const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: cooperative coalesced stores instead of TMA
-      const int etid = threadIdx.x - 64;                // index among the epilogue threads
+      const int etid = threadIdx.x - 96;                // index among the epilogue threads
       const bool elected = (ew == 0 && lane == 0);
       const int row = q * 32 + lane;                    // row inside the 128-row tile
       const int swz = row & 7;                          // 128B-swizzle XOR of this row
-      const int my_tiles = (total_tiles - unit + n_units - 1) / n_units;
-      const int total_chunks = my_tiles * CPT;
-      auto prefetch = [&](int g) {                      // elected thread: TMA-load residual / aux of chunk g
-        if (g >= total_chunks) return;
-        const int tile = unit + (g / CPT) * n_units;
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
-        const int b = g & 1, nc = t.n0 + (g % CPT) * 64;
-        if (has_res) {
-          mbar_expect_tx(&rfull_bar[b], CHUNK_BYTES);
-          tma_load_2d(rbuf + b * CHUNK_BYTES, &tmR, &rfull_bar[b], nc, t.m0);
-        }
-        if (has_aux) {
-          mbar_expect_tx(&xfull_bar[b], CHUNK_BYTES);
-          tma_load_2d(xbuf + b * CHUNK_BYTES, &tmX, &xfull_bar[b], nc, t.m0);
-        }
-      };
-      if (elected) {
-        prefetch(0);
-        prefetch(1);
-      }
       // epilogue kind, fixed for the launch (see epilogue_shift_act / epilogue_relu_mask)
       const bool plain = epi.scale == nullptr && epi.drop_thresh == 0 && !has_out2 && (N & 63) == 0;
       const int kind = !plain ? 0
@@ -461,8 +469,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
         for (int c = 0; c < CPT; ++c, ++g) {
           constexpr int NC = 64 / NGRP;                 // columns of a 64-column chunk owned by this thread: 32 (8 warps) or 16
           constexpr int NU = NC / 8;                    // ... in 16-byte units
-          const int b = g & 1;
-          const uint32_t bph = (g >> 1) & 1;
+          const int b = g & (n_rbuf - 1);
+          const uint32_t bph = (g / n_rbuf) & 1;
           const int nb = t.n0 + c * 64 + grp * NC;      // this thread's columns
           uint32_t v[NC];
           __syncwarp();
@@ -475,8 +483,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
             if (lane == 0) release_acc(&tempty_bar[acc]);
           }
           uint32_t res16[NC / 2], aux16[NC / 2];
+          if (has_in) mbar_wait(&rfull_bar[b], bph);
           if (has_res) {
-            mbar_wait(&rfull_bar[b], bph);
             const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
@@ -485,13 +493,16 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
             }
           }
           if (has_aux) {
-            mbar_wait(&xfull_bar[b], bph);
             const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
               const uint4 u = *reinterpret_cast<const uint4*>(xr + (((grp * NU + j) ^ swz) << 4));
               aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
             }
+          }
+          if (has_in) {                                 // this warp has its residual / aux values in registers: hand the buffer back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty_bar[b]);
           }
           float f[NC];
 #pragma unroll
@@ -528,7 +539,6 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
               if (has_out2) tma_store_2d(&tmC2, c2buf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
               tma_store_commit();
             }
-            prefetch(g + 2);                            // rbuf[b] / xbuf[b] were fully consumed before the barrier
           }
           if (remap) {
             // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment,
@@ -792,14 +802,23 @@ static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default
 // round trip whatever its size, so deep stages beat many stages (1312x768x3072: 26.5 / 18.3 / 15.8 us with 1 / 2 / 4
 // chunks per stage); two output buffers perform like four.
 struct SmemPlan {
-  int epi_bytes, n_cbuf, kch, stages, chunk_bytes;
+  int epi_bytes, n_cbuf, n_rbuf, kch, stages, chunk_bytes;
 };
 static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0) {
   SmemPlan p;
   p.chunk_bytes = BM * BK * 2 + (bn / cg) * BK * 2;
   p.n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
-  if (tma_epi) p.epi_bytes = p.n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + 2 * CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
-  else p.epi_bytes = (8 * STG_BYTES + 1023) & ~1023;     // staged epilogue: always 8 warps
+  p.n_rbuf = 2;
+  const int n_in = (has_res ? 1 : 0) + (has_aux ? 1 : 0);
+  auto epi_bytes_for = [&](int n_rbuf) { return p.n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in; };
+  if (tma_epi) {
+    // short K loops (the HBM-bound 1x1 convs) need little operand ring: spend the smem on a deeper residual / aux ring instead
+    // (4 x 16 KB per tensor in flight per SM against the ~2 us loaded HBM latency)
+    if (n_in > 0 && kiters <= 2 && (SMEM_LIMIT - 1024 - 256 - epi_bytes_for(4)) / p.chunk_bytes >= kiters + 1) p.n_rbuf = 4;
+    p.epi_bytes = epi_bytes_for(p.n_rbuf);
+  } else {
+    p.epi_bytes = (8 * STG_BYTES + 1023) & ~1023;     // staged epilogue: always 8 warps
+  }
   const int chunks_fit = (SMEM_LIMIT - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
   p.kch = 1;
   if (force_kch > 0) p.kch = force_kch;
@@ -866,7 +885,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   if (!tx) tx = ta;
   if (!tc2) tc2 = ta;
   const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15);
-  const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, kch = sp.kch, stages = sp.stages;
+  const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, n_rbuf = sp.n_rbuf, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
     set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B)", BN, epi_bytes);
     return CB_ERR_INVALID;
@@ -876,7 +895,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   const int grid = (total < units ? total : units) * CG;
   if (CG == 1) {
     launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-             iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
+             iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -891,7 +910,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
-                                       tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, epi);
+                                       tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
     if (e != cudaSuccess) {
       set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return CB_ERR_CUDA;
