@@ -155,6 +155,8 @@ def run_b200(args):
 
     ops.set_pdl(args.pdl)
     ops.set_epi_warps(args.epi_warps)
+    ops.set_cbuf(args.cbuf)
+    ops.set_direct_store(args.direct_store)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
@@ -334,7 +336,7 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps,
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4),
@@ -442,6 +444,8 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
+    ap.add_argument("--direct_store", type=int, default=1, help="GEMM epilogue output: 1 direct register->global stores, 0 smem chunk + TMA store")
+    ap.add_argument("--cbuf", type=int, default=0, choices=[0, 2, 4], help="TMA-store chunk buffers of the GEMM epilogue (0 = library default)")
     ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")

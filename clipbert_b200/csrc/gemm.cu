@@ -51,6 +51,8 @@ struct GemmEpi {
   uint32_t drop_thresh;
   float drop_inv_keep;
   uint64_t seed;
+  int direct;       // TMA epilogue only: 1 = every thread stores its own row segment straight from registers (no smem staging,
+                    // no chunk barrier, no TMA store); 0 = swizzled smem chunk + TMA store / cooperative re-mapped copy
   long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
 };
 
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
                      : (epi.shift != nullptr && !has_aux && (epi.act == CB_ACT_NONE || epi.act == CB_ACT_RELU)) ? 1
                      : (epi.shift == nullptr && has_aux && epi.aux_mode == CB_AUX_RELU_MASK && epi.act == CB_ACT_NONE) ? 2 : 0;
       const bool kind_relu = epi.act == CB_ACT_RELU;
+      const bool direct = epi.direct != 0;
       int g = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
         const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
@@ -465,6 +468,26 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
         tc_fence_after();
         if (elected && local == 0) dbg_stamp(epi, 7);
         const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        // direct stores: this thread's output row (re-mapped between compact and zero-bordered pixel rows if asked)
+        bool drow_ok = orow < M;
+        int64_t drow = orow;
+        if (direct && remap) {
+          const int m = static_cast<int>(orow);
+          if (epi.rowmap == CB_ROWMAP_PAD) {
+            const int hw = epi.H * epi.W;
+            const int img = m / hw;
+            const int rr = m - img * hw;
+            const int y = rr / epi.W, x = rr - y * epi.W;
+            drow = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
+          } else {
+            const int wp = epi.W + 2, hp = epi.H + 2;
+            const int img = m / (hp * wp);
+            const int rr = m - img * (hp * wp);
+            const int y = rr / wp, x = rr - y * wp;
+            drow_ok = drow_ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
+            drow = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
+          }
+        }
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++g) {
           constexpr int NC = 64 / NGRP;                 // columns of a 64-column chunk owned by this thread: 32 (8 warps) or 16
@@ -511,6 +534,26 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
           if (kind == 1) epilogue_shift_act<NC>(f, epi.shift + nb, has_res ? res16 : nullptr, kind_relu);
           else if (kind == 2) epilogue_relu_mask<NC>(f, has_res ? res16 : nullptr, aux16);
           else epilogue_math<NC>(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
+          if (direct) {
+            // 16 (or 32) contiguous bf16 of one output row per thread: full 32-byte sectors; the four warps of a lane quarter
+            // complete every 128-byte line within the same chunk, so L2 writes whole lines back
+            if (drow_ok) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + drow * epi.out_ld + nb;
+#pragma unroll
+              for (int j = 0; j < NU; ++j)
+                if (nb + 8 * j + 8 <= N)
+                  *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              if (has_out2) {
+                __nv_bfloat16* o2 = epi.out2 + drow * epi.out2_ld + nb;
+#pragma unroll
+                for (int j = 0; j < NU; ++j)
+                  if (nb + 8 * j + 8 <= N)
+                    *reinterpret_cast<uint4*>(o2 + 8 * j) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+              }
+            }
+            continue;
+          }
           const int cb = g & (n_cbuf - 1);
           uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
           if (has_out2) {
@@ -795,6 +838,7 @@ static int sm_count() {
 static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
 static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
+static int g_direct_store = 1; // TMA epilogue: 1 = direct register -> global stores (default), 0 = smem chunk + TMA store
 static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
@@ -975,6 +1019,7 @@ extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline =
 extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
+extern "C" void cb_debug_gemm_direct_store(int on) { cb::g_direct_store = on ? 1 : 0; }
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;
@@ -1007,6 +1052,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.W = d.map_w;
   epi.seed = d.dropout_seed;
   epi.dbg = g_gemm_timeline;
+  epi.direct = g_direct_store;
   if (d.dropout_p > 0.0f) {
     double t = static_cast<double>(d.dropout_p) * 4294967296.0;
     epi.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);

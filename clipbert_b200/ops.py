@@ -92,6 +92,16 @@ def set_epi_warps(n):
     L.lib().cb_debug_gemm_epi_warps(int(n))
 
 
+def set_direct_store(on):
+    """Tuning hook: GEMM TMA-epilogue output path: 1 = direct register -> global stores, 0 = smem chunk + TMA store."""
+    L.lib().cb_debug_gemm_direct_store(int(bool(on)))
+
+
+def set_cbuf(n):
+    """Tuning hook: output chunk buffers of the GEMM's TMA-store epilogue (0 = automatic, 2 or 4)."""
+    L.lib().cb_debug_gemm_cbuf(int(n))
+
+
 def set_pdl(enable):
     """Programmatic dependent launch between the library's kernels (default on). Returns the previous setting."""
     return int(L.lib().cb_set_pdl(int(bool(enable))))

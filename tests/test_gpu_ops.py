@@ -50,9 +50,21 @@ def test_gemm_nn_dgrad(cuda, shape, knob):
     assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
 
 
+@pytest.fixture(params=["direct", "tma_store", "tma_store_8warps"])
+def epilogue_variant(request):
+    """Output path of the GEMM's TMA-prefetch epilogue: direct register->global stores with 16 epilogue warps (default),
+    swizzled smem chunk + TMA store with 16 warps, and with 8 warps (the round-1a kernel)."""
+    ops = _ops()
+    ops.set_direct_store(request.param == "direct")
+    ops.set_epi_warps(8 if request.param.endswith("8warps") else 16)
+    yield request.param
+    ops.set_direct_store(1)
+    ops.set_epi_warps(16)
+
+
 @pytest.mark.parametrize("staged", [0, STAGED, PAIR, PAIR | STAGED])
 @pytest.mark.parametrize("shape", [(500, 384, 256), (20000, 512, 128), (3000, 64, 64)])
-def test_gemm_epilogues(cuda, staged, shape):
+def test_gemm_epilogues(cuda, staged, shape, epilogue_variant):
     """Both epilogue I/O paths (TMA-prefetched / TMA-stored vs. per-warp staged), several tiles per persistent CTA."""
     ops = _ops()
     M, N, K = shape
@@ -97,7 +109,7 @@ def test_gemm_epilogues(cuda, staged, shape):
 
 @pytest.mark.parametrize("knob", [SINGLE, PAIR, SINGLE | STAGED])
 @pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64), (64, 14, 14, 256, 256)])
-def test_conv3x3_fwd_and_dgrad(cuda, dims, knob):
+def test_conv3x3_fwd_and_dgrad(cuda, dims, knob, epilogue_variant):
     ops = _ops()
     NB, H, W, Cin, Cout = dims
     g = torch.Generator().manual_seed(4)
@@ -123,7 +135,7 @@ def test_conv3x3_fwd_and_dgrad(cuda, dims, knob):
 
 @pytest.mark.parametrize("knob", [0, STAGED])
 @pytest.mark.parametrize("dims", [(3, 5, 6, 64, 64), (40, 28, 28, 256, 128)])
-def test_rowmap_pad_keeps_border_zero(cuda, dims, knob):
+def test_rowmap_pad_keeps_border_zero(cuda, dims, knob, epilogue_variant):
     ops = _ops()
     NB, H, W, K, N = dims
     M = NB * H * W
