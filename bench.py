@@ -444,7 +444,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
-    ap.add_argument("--direct_store", type=int, default=1, help="GEMM epilogue output: 1 direct register->global stores, 0 smem chunk + TMA store")
+    ap.add_argument("--direct_store", type=int, default=0, help="GEMM epilogue output: 1 direct register->global stores, 0 smem chunk + TMA store")
     ap.add_argument("--cbuf", type=int, default=0, choices=[0, 2, 4], help="TMA-store chunk buffers of the GEMM epilogue (0 = library default)")
     ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")

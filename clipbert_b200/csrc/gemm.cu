@@ -838,7 +838,9 @@ static int sm_count() {
 static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
 static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
-static int g_direct_store = 1; // TMA epilogue: 1 = direct register -> global stores (default), 0 = smem chunk + TMA store
+static int g_direct_store = 0; // TMA epilogue: 0 = smem chunk + TMA store (default); 1 = direct register -> global stores. EXPERIMENTAL:
+                               // +1.3 % on the step but an intermittent mismatch (one warp's 32x16 block of one launch in ~100) on
+                               // multi-tile CTAs when the epilogue warps drift apart without the per-chunk barrier - not yet explained
 static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
