@@ -326,6 +326,15 @@ def run_b200(args):
                     note="gemm_ms_per_step = the step's GEMM launches replayed back to back on one stream; gemm_share_of_step divides it by the "
                          "timed (two-stream) step, so wgrad/dgrad overlap can push it towards or past 1",
                     whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4))
+    # Ranks > 0 are done: nothing below is collective. They leave with os._exit after a last barrier - tearing the NCCL process
+    # group down while CUDA graphs that captured its kernels are alive hung the run (seen at N = 2), and nothing needs cleanup.
+    if world > 1:
+        barrier()
+        if rank != 0:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+    if True:
         cpu = None if (args.no_cpu or rank != 0) else cpu_baseline(args)
     # ---- informational: the fused optimizer step that follows fwd+bwd in training (not part of the metric) ----
     opt_info = None
@@ -367,8 +376,10 @@ def run_b200(args):
                    gpu_launches=int(launches), gpu_launches_per_step=int(launches // args.steps), clocks=clocks, roofline=roof,
                    cpu_baseline=cpu, fused_optimizer=opt_info)
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:          # see above: no NCCL teardown with live captured graphs
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
