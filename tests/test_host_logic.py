@@ -109,3 +109,30 @@ def test_synthetic_text_follows_the_survey_recipe():
     for i in range(16):
         n = int(lens[i])
         assert int(ids[i, n - 1]) == 102 and (ids[i, n:] == 0).all() and (mask[i, :n] == 1).all()
+
+
+@pytest.mark.parametrize("counts", [[1, 1, 1], [2, 1, 3], [5, 5]])
+def test_forward_clips_index_plan_reproduces_the_reference_clip_loop(counts, monkeypatch):
+    """ClipBert.forward_clips only re-indexes: with the model replaced by a row-wise stand-in, one batched pass
+    must give exactly the tensor the reference loop builds with torch.stack (run_video_retrieval.py:388-404) - bit-exact index op."""
+    import clipbert_b200 as cb
+    model = cb.ClipBert(make_cfg(), detectron2_model_cfg="R-50-grid.yaml")
+    n_clips, T, B = 3, 2, len(counts)
+    g = torch.Generator().manual_seed(5)
+    vis = torch.randn(B, n_clips * T, 3, 4, 4, generator=g)
+    ids = torch.randint(0, 1000, (sum(counts), 6), generator=g)
+    mask = torch.ones_like(ids)
+
+    def fake_forward(self, batch):
+        # one "logit" pair per text row from (its video's frames of this clip, its own ids): what any per-row model computes
+        reps = batch["n_examples_list"]
+        v = batch["visual_inputs"].flatten(1).sum(1)                                   # (units,)
+        v = torch.repeat_interleave(v, torch.tensor(reps))
+        t = batch["text_input_ids"].float().sum(1)
+        return dict(logits=torch.stack([v * 3 + t, v - t], dim=1), loss=0)
+    monkeypatch.setattr(cb.ClipBert, "forward", fake_forward)
+    visr = vis.view(B, n_clips, T, 3, 4, 4)
+    loop = torch.stack([model.forward(dict(visual_inputs=visr[:, c], text_input_ids=ids, text_input_mask=mask, n_examples_list=list(counts)))["logits"]
+                        for c in range(n_clips)])
+    out = model.forward_clips(dict(visual_inputs=vis, text_input_ids=ids, text_input_mask=mask, n_examples_list=list(counts)), n_clips)["logits"]
+    assert out.shape == (n_clips, sum(counts), 2) and torch.equal(out, loop)
