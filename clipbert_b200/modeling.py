@@ -124,6 +124,17 @@ class ClipBertBaseModel(nn.Module):
         self.pooler = BertPooler(config)
 
 
+def get_random_sample_indices(seq_len, num_samples=100, device=torch.device("cpu")):
+    """src/modeling/modeling.py:15-34: sorted indices of a sample without replacement, drawn from numpy's global
+    generator exactly as the reference does (np.random.seed reproduces its choice); all indices if num_samples >= seq_len."""
+    import numpy as np
+    if num_samples >= seq_len:
+        sample_indices = np.arange(seq_len)
+    else:
+        sample_indices = np.sort(np.random.choice(seq_len, size=num_samples, replace=False))
+    return torch.from_numpy(sample_indices).long().to(device)
+
+
 def _init_bert_weights(module, std):
     """BertPreTrainedModel._init_weights (src/modeling/transformers.py:559-570)."""
     for m in module.modules():
@@ -359,7 +370,24 @@ class _ClipBertHeadModel(nn.Module):
         def new(*shape, dtype=bf16):
             return torch.empty(*shape, dtype=dtype, device=dev)
 
-        st = dict(ids=ids, mask=mask, grid=grid, repeat=repeat, seed=seed, p_h=p_h, p_a=p_a, dims=(nseq, nvid, T, gh, gw, lt, L), layers=[])
+        # ---- pre-training only, train mode only: keep a random subset of the visual tokens (modeling.py:80-88) ----
+        # The kept positions are the same for every sequence of the batch, so the subset is presented to the embedding kernels
+        # as a (n_keep x 1) grid whose "row" table is row[idx // w] + col[idx % w] (its "column" table is one zero row): index
+        # bookkeeping on the host, arithmetic in the same kernels. (The host draw makes such a step not graph-capturable.)
+        row_tab, col_tab = self._emb("vis.row")[0], self._emb("vis.col")[0]
+        sample = None
+        n_keep = int(_cfg(cfg, "pixel_random_sampling_size", 0) or 0)
+        if n_keep > 0 and train and n_keep < gh * gw:
+            idx = get_random_sample_indices(gh * gw, n_keep, dev)
+            grid = grid.view(nvid, T, gh * gw, H).index_select(2, idx).view(nvid, T, n_keep, 1, H)
+            row_tab = (row_tab[idx // gw] + col_tab[idx % gw]).contiguous()
+            col_tab = torch.zeros(1, H, dtype=f32, device=dev)
+            sample = (idx, gh, gw, row_tab, col_tab)
+            gh, gw = n_keep, 1
+            L = lt + n_keep
+            M = nseq * L
+        st = dict(ids=ids, mask=mask, grid=grid, repeat=repeat, seed=seed, p_h=p_h, p_a=p_a, dims=(nseq, nvid, T, gh, gw, lt, L), layers=[],
+                  sample=sample)
         # ---- embeddings: [text ; visual] written straight into one (B', L, 768) buffer ----
         x = new(M, H)
         st["stats_t"] = new(nseq * lt, 2, dtype=f32)
@@ -368,7 +396,7 @@ class _ClipBertHeadModel(nn.Module):
         g_v, b_v, _, _ = self._ln("vis.ln")
         word, pos, typ = self._emb("emb.word")[0], self._emb("emb.pos")[0], self._emb("emb.type")[0]
         ops.embed_text_fwd(ids, word, pos, typ, g_t, b_t, x, st["stats_t"], nseq, lt, L, eps, p_h, seed + 1)
-        ops.embed_visual_fwd(grid, s2v, n_ex, self._emb("vis.row")[0], self._emb("vis.col")[0], self._emb("vis.type")[0], g_v, b_v,
+        ops.embed_visual_fwd(grid, s2v, n_ex, row_tab, col_tab, self._emb("vis.type")[0], g_v, b_v,
                              x, st["stats_v"], nseq, T, gh, gw, lt, L, eps, p_h, seed + 2)
         if self._capture is not None:
             self._capture["embeddings"] = x.view(nseq, L, H).clone()
@@ -535,8 +563,22 @@ class _ClipBertHeadModel(nn.Module):
         (row, drow), (col, dcol), (vtyp, dvtyp) = self._emb("vis.row"), self._emb("vis.col"), self._emb("vis.type")
         dv_tmp = new(nseq * gh * gw, H, dtype=f32)
         dgrid = new(nvid, T, gh, gw, H) if grid_needs_grad else None
-        ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row, col, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow, dcol, dvtyp,
-                             dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
+        sample = st.get("sample")
+        if sample is None:
+            ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row, col, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow, dcol, dvtyp,
+                                 dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
+        else:
+            # sampled visual tokens (see _forward_impl): gradients of the (n_keep x 1) virtual grid, scattered back by index
+            idx, gh0, gw0, row_s, col_s = sample
+            drow_s, dcol_s = torch.zeros_like(row_s), torch.zeros_like(col_s)
+            ops.embed_visual_bwd(dx, st["grid"], s2v, starts, n_ex, row_s, col_s, vtyp, g_v, st["stats_v"], dv_tmp, dgrid, drow_s, dcol_s,
+                                 dvtyp, dg_v, db_v, nseq, nvid, T, gh, gw, lt, L, p_h, st["seed"] + 2)
+            drow.index_add_(0, idx // gw0, drow_s)         # d(row[r] + col[c]) goes to both tables
+            dcol.index_add_(0, idx % gw0, drow_s)
+            if dgrid is not None:
+                full = torch.zeros(nvid, T, gh0 * gw0, H, dtype=bf16, device=dev)
+                full.index_copy_(2, idx, dgrid.view(nvid, T, gh, H))
+                dgrid = full.view(nvid, T, gh0, gw0, H)
         sq.join()          # every weight gradient is in the flat buffer before the caller (all-reduce hook, optimizer) sees it
         if not self._optimizer_emits_packed:
             self._dirty = True

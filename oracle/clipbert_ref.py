@@ -178,13 +178,26 @@ def bert_embeddings(input_ids, sd, prefix, eps):
     return layer_norm(e, sd, prefix + "LayerNorm.", eps)
 
 
-def visual_embeddings(grid, sd, prefix, eps):
-    """VisualInputEmbedding.forward (modeling.py:62-101): frame mean, +row/col, +type[0], LN."""
+def random_sample_indices(seq_len, num_samples=100):
+    """get_random_sample_indices (modeling.py:15-34): sorted sample without replacement drawn from numpy's GLOBAL
+    generator (so np.random.seed reproduces the reference's choice); all indices when num_samples >= seq_len."""
+    import numpy as np
+    if num_samples >= seq_len:
+        return torch.arange(seq_len)
+    return torch.from_numpy(np.sort(np.random.choice(seq_len, size=num_samples, replace=False))).long()
+
+
+def visual_embeddings(grid, sd, prefix, eps, sample_indices=None):
+    """VisualInputEmbedding.forward (modeling.py:62-101): frame mean, +row/col, [pre-training, train mode only: keep the
+    visual tokens listed in sample_indices, :80-88], +type[0], LN."""
     bsz, _, hh, ww, hsz = grid.shape
     g = grid.mean(1)
     g = g + sd[prefix + "row_position_embeddings.weight"][:hh].view(1, hh, 1, hsz)
     g = g + sd[prefix + "col_position_embeddings.weight"][:ww].view(1, 1, ww, hsz)
-    v = g.reshape(bsz, -1, hsz) + sd[prefix + "token_type_embeddings.weight"][0].view(1, 1, -1)
+    v = g.reshape(bsz, -1, hsz)
+    if sample_indices is not None:
+        v = v.index_select(1, sample_indices.to(v.device))
+    v = v + sd[prefix + "token_type_embeddings.weight"][0].view(1, 1, -1)
     return layer_norm(v, sd, prefix + "LayerNorm.", eps)
 
 
@@ -210,11 +223,11 @@ def bert_layer(h, ext_mask, sd, prefix, n_heads, eps, rnd=EXACT):
 
 
 def clipbert_base_model(text_input_ids, grid, text_mask, sd, prefix="transformer.bert.", cfg=BERT_CFG,
-                        return_layers=False, rnd=EXACT):
+                        return_layers=False, rnd=EXACT, sample_indices=None):
     """ClipBertBaseModel.forward: returns (sequence_output, pooled_output)."""
     eps = cfg["layer_norm_eps"]
     te = rnd.act(bert_embeddings(text_input_ids, sd, prefix + "embeddings.", eps))
-    ve = rnd.act(visual_embeddings(rnd.act(grid), sd, prefix + "visual_embeddings.", eps))
+    ve = rnd.act(visual_embeddings(rnd.act(grid), sd, prefix + "visual_embeddings.", eps, sample_indices))
     mask = torch.cat([text_mask, text_mask.new_ones(ve.shape[:2])], dim=-1)      # modeling.py:217-220
     h = torch.cat([te, ve], dim=1)                                               # [text ; visual]
     ext = (1.0 - mask[:, None, None, :].to(h.dtype)) * -10000.0                  # hf get_extended_attention_mask
@@ -271,9 +284,14 @@ def sequence_classification(text_input_ids, grid, text_mask, sd, labels=None, lo
     return dict(logits=logits, loss=loss)
 
 
-def pretraining(text_input_ids, grid, text_mask, sd, mlm_labels=None, itm_labels=None, cfg=BERT_CFG):
-    """ClipBertForPreTraining.forward (modeling.py:254-307); MLM head on text positions only."""
-    seq, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd)
+def pretraining(text_input_ids, grid, text_mask, sd, mlm_labels=None, itm_labels=None, cfg=BERT_CFG, pixel_random_sampling_size=0,
+                rnd=EXACT):
+    """ClipBertForPreTraining.forward (modeling.py:254-307); MLM head on text positions only. pixel_random_sampling_size > 0
+    = the train-mode visual-token sampling of pre-training (pretrain_image_text_base_resnet50_mlm_itm.json:59)."""
+    idx = None
+    if pixel_random_sampling_size > 0:
+        idx = random_sample_indices(grid.shape[2] * grid.shape[3], pixel_random_sampling_size)
+    seq, pooled = clipbert_base_model(text_input_ids, grid, text_mask, sd, rnd=rnd, sample_indices=idx)
     lt = text_mask.shape[1]
     p = "transformer.cls.predictions."
     t = F.gelu(linear(seq[:, :lt], sd, p + "transform.dense."))

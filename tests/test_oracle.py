@@ -98,6 +98,41 @@ def test_oracle_matches_live_reference_import(weights):
     assert torch.allclose(got["logits"], ref["logits"], atol=2e-6) and torch.allclose(got["loss"], ref["loss"], atol=2e-6)
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_visual_token_sampling_matches_live_reference(weights):
+    """Pre-training's train-mode random sampling of visual tokens (modeling.py:15-34,80-88): same numpy seed => the oracle
+    keeps the same sorted subset as the reference's own ClipBertForPreTraining in train() mode (dropout 0)."""
+    import numpy as np
+    sd = {k: v for k, v in weights.items() if not k.startswith("transformer.classifier.")}
+    sd.update({k: v for k, v in synth.transformer_state_dict(60, head="pretraining").items() if k.startswith("transformer.cls.")})
+    g = torch.Generator().manual_seed(5)
+    grid = torch.randn(2, 2, 4, 5, 768, generator=g).abs()          # 20 visual tokens, keep 7
+    ids, mask = synth.synth_text(2, 12, seed=9)
+    model = ref_import.build_reference_transformer(sd, "ClipBertForPreTraining", hidden_dropout_prob=0.0,
+                                                   attention_probs_dropout_prob=0.0, pixel_random_sampling_size=7)
+    model.train()
+    np.random.seed(1234)
+    with torch.no_grad():
+        ref = model(ids, grid, mask)
+    np.random.seed(1234)
+    idx = R.random_sample_indices(20, 7)
+    assert idx.numel() == 7 and torch.equal(idx, idx.sort()[0]) and idx.unique().numel() == 7
+    np.random.seed(1234)
+    with torch.no_grad():
+        got = R.pretraining(ids, grid, mask, sd, pixel_random_sampling_size=7)
+    assert torch.allclose(got["itm_scores"], ref["itm_scores"], atol=2e-6)
+    assert torch.allclose(got["mlm_scores"], ref["mlm_scores"], atol=2e-5)
+    # eval mode: no sampling in the reference (self.training is False) == oracle with size 0; >= seq_len keeps everything
+    model.eval()
+    with torch.no_grad():
+        ref_eval = model(ids, grid, mask)
+        got_eval = R.pretraining(ids, grid, mask, sd)
+        got_all = R.pretraining(ids, grid, mask, sd, pixel_random_sampling_size=100)
+    assert torch.allclose(got_eval["itm_scores"], ref_eval["itm_scores"], atol=2e-6)
+    assert torch.equal(got_all["itm_scores"], got_eval["itm_scores"])
+    assert not torch.allclose(got["itm_scores"], got_eval["itm_scores"], atol=1e-4)
+
+
 def test_oracle_cnn_against_torchvision_resnet50(weights):
     """Independent cross-check of the d2 restatement: torchvision ResNet-50 with FrozenBN, stride moved to conv1
     (STRIDE_IN_1X1), weights mapped with the reference's own key map (src/utils/load_save.py:335-345)."""
