@@ -138,6 +138,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if args.nccl_ctas:      # experiment: fewer NCCL CTAs leave more SMs to the persistent GEMMs the exchange overlaps with
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
     import clipbert_b200 as cb
     from clipbert_b200 import ops
@@ -152,12 +154,14 @@ def run_b200(args):
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
     if world > 1:
-        model.enable_overlapped_allreduce()
+        model.enable_overlapped_allreduce(cnn_buckets=bool(args.cnn_buckets))
 
     ops.set_pdl(args.pdl)
     ops.set_epi_warps(args.epi_warps)
     ops.set_cbuf(args.cbuf)
     ops.set_direct_store(args.direct_store)
+    if args.sm_limit:
+        ops.set_sm_limit(args.sm_limit)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
@@ -370,6 +374,7 @@ def run_b200(args):
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
+                               cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4),
@@ -484,6 +489,9 @@ def main():
     ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
+    ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
+    ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
+    ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")

@@ -824,6 +824,10 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
   if (threadIdx.x == 32) dbg_stamp(epi, 11);
 }
 
+static int g_sm_limit = 0;    // tuning hook: cap on the persistent grid (0 = every SM). A long-running co-resident kernel (an NCCL
+                              // all-reduce overlapped with the backward pass) pins some SMs for its whole duration; with the static
+                              // round-robin tile schedule the CTAs that cannot be placed run as a second wave, so a launch of 148
+                              // CTAs takes up to twice as long. Capping the grid at 148 - (NCCL CTAs) avoids the second wave.
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -832,7 +836,7 @@ static int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 static long long* g_gemm_timeline = nullptr;
@@ -1022,6 +1026,7 @@ extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
 extern "C" void cb_debug_gemm_direct_store(int on) { cb::g_direct_store = on ? 1 : 0; }
+extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? (n < 2 ? 2 : n & ~1) : 0; }   // even: CTA pairs
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;

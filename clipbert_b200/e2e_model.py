@@ -134,16 +134,30 @@ class ClipBert(nn.Module):
             if m._flat is not None and m._flat.grad is not None:
                 m._flat.grad.zero_()
 
-    def enable_overlapped_allreduce(self, group=None, average=True):
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
-        the CNN buffer and joins. Safe inside CUDA-graph capture (ProcessGroupNCCL forks/joins its stream)."""
-        self._dp = dict(group=group, average=average, works=[])
+        the CNN buffer and joins. Safe inside CUDA-graph capture (ProcessGroupNCCL forks/joins its stream).
+
+        ``cnn_buckets``: also exchange the tail of the CNN buffer (res5 + grid_encoder, 78 % of it) as soon as the
+        res5 backward has enqueued its last weight gradient, leaving only res3/res4 (33 MB) for the final exchange.
+        The collective is issued from the wgrad side stream, which is the stream those gradients are written on."""
+        self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None)
 
         def hook(flat_grad):
             self._dp["works"] += allreduce_flat([flat_grad], group, average, async_op=True)
+            self._dp["tf_started"] = True
         self.transformer._grad_ready_hook = hook
+
+        def cnn_hook(flat_grad, lo, side_stream):
+            if side_stream is not None:
+                with torch.cuda.stream(side_stream):
+                    self._dp["works"] += allreduce_flat([flat_grad[lo:]], group, average, async_op=True)
+            else:
+                self._dp["works"] += allreduce_flat([flat_grad[lo:]], group, average, async_op=True)
+            self._dp["cnn_lo"] = lo
+        self.cnn._bucket_hook = cnn_hook if cnn_buckets else None
 
     def allreduce_grads(self, group=None, average=True, async_op=False):
         """Average the flat fp32 gradient buffers over the data-parallel group (NCCL) - the replacement of
@@ -152,10 +166,18 @@ class ClipBert(nn.Module):
         if dp is None:
             return allreduce_flat(self.flat_grads(), group, average, async_op)
         works, dp["works"] = dp["works"], []
-        if not works:                      # hook did not fire (e.g. transformer frozen): exchange everything now
-            works = allreduce_flat(self.flat_grads(), dp["group"], dp["average"], async_op=True)
-        elif self.cnn._flat is not None and self.cnn._flat.grad is not None:
-            works += allreduce_flat([self.cnn._flat.grad], dp["group"], dp["average"], async_op=True)
+        tf_started, dp["tf_started"] = dp["tf_started"], False
+        lo, dp["cnn_lo"] = dp["cnn_lo"], None
+        rest = []
+        tf = self.transformer._flat
+        if not tf_started and tf is not None and tf.grad is not None:      # hook did not fire (e.g. transformer frozen)
+            rest.append(tf.grad)
+        cf = self.cnn._flat
+        if cf is not None and cf.grad is not None:
+            g = cf.grad if lo is None else cf.grad[:lo]                    # the tail [lo:) is already in flight (cnn_buckets)
+            if g.numel():
+                rest.append(g)
+        works += allreduce_flat(rest, dp["group"], dp["average"], async_op=True)
         for w in works:
             w.wait()
         return []

@@ -110,6 +110,7 @@ class _CnnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, images, anchor):
         grid, stash = module._forward_impl(images, need_backward=True)
+        module._pending_backward += 1
         ctx.module = module
         ctx.stash = stash
         return grid
@@ -117,8 +118,10 @@ class _CnnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dgrid):
         stash, ctx.stash = ctx.stash, None
+        m = ctx.module
+        m._pending_backward = max(0, m._pending_backward - 1)
         if stash is not None:
-            ctx.module._backward_impl(stash, dgrid)
+            m._backward_impl(stash, dgrid, last=m._pending_backward == 0)
         return None, None, None
 
 
@@ -138,6 +141,8 @@ class GridFeatBackbone(nn.Module):
         self._bn = None
         self._dirty = True
         self._capture = None     # tests set this to a dict to receive per-stage activations
+        self._pending_backward = 0
+        self._bucket_hook = None   # data-parallel: called as hook(flat_grad, first_finished_element, side_stream) mid-backward
         self._segments = None
         self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
@@ -459,7 +464,9 @@ class GridFeatBackbone(nn.Module):
                  out=out, out_ld=m.cin, rowmap=ops.ROWMAP_UNPAD, map_h=h, map_w=w)
         return out
 
-    def _backward_impl(self, stash, dgrid):
+    def _backward_impl(self, stash, dgrid, last=True):
+        """``last``: no other backward of this step is outstanding (the reference's per-clip loop runs one per clip and the
+        gradients accumulate), so a finished slice of the gradient buffer may be handed to ``_bucket_hook`` early."""
         self._flat.attach_grads()
         dev = dgrid.device
         bf16 = torch.bfloat16
@@ -494,6 +501,10 @@ class GridFeatBackbone(nn.Module):
             da = self._dgrad3x3(blk.conv2, db_pad, n, hh, ww, st["a_pad"])
             if blk.has_shortcut:
                 sq.run(lambda: (self._wgrad(blk.conv1, da, st["xs"], rows), self._wgrad(blk.shortcut, g, st["xs"], rows)), da, g, st["xs"])
+                if last and self._bucket_hook is not None and st["name"] == "res5.0":
+                    # every weight gradient of res5 + grid_encoder (78 % of the CNN's trainable parameters, the tail of the
+                    # flat buffer) has been enqueued: its exchange can overlap the res4 / res3 backward
+                    self._bucket_hook(self._flat.grad, blk.shortcut._e["offset"], sq.side if sq.forked else None)
                 if st["first_trainable"]:
                     break                                     # d2 FREEZE_AT: no gradient below this block
                 dxs = self._dgrad1x1(blk.shortcut, g, rows)

@@ -97,6 +97,12 @@ def set_direct_store(on):
     L.lib().cb_debug_gemm_direct_store(int(bool(on)))
 
 
+def set_sm_limit(n):
+    """Tuning hook: cap the persistent GEMM grid at ``n`` CTAs (0 = every SM): leaves SMs to a co-resident NCCL kernel so
+    that the static tile schedule does not spill into a second wave while a gradient all-reduce overlaps the backward."""
+    L.lib().cb_debug_gemm_sm_limit(int(n))
+
+
 def set_cbuf(n):
     """Tuning hook: output chunk buffers of the GEMM's TMA-store epilogue (0 = automatic, 2 or 4)."""
     L.lib().cb_debug_gemm_cbuf(int(n))

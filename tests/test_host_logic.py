@@ -90,6 +90,59 @@ def test_data_parallel_gradient_exchange_world_size_2():
         assert b == pytest.approx([1.5 * i for i in range(10)])
 
 
+def _dp_bucket_worker(rank, world, port, q):
+    """Drives ClipBert's exchange bookkeeping (hooks + allreduce_grads) over gloo with stand-in halves: only the flat gradient
+    buffers and the hook attributes are touched by that code."""
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from clipbert_b200.e2e_model import ClipBert
+    out = {}
+    for case in ("buckets", "no_buckets", "no_hooks", "transformer_frozen"):
+        m = ClipBert.__new__(ClipBert)
+        tf = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.full((1000,), float(rank + 1))), _grad_ready_hook=None,
+                                   _pending_backward=0)
+        cnn = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.zeros(640)), _bucket_hook=None, _pending_backward=0)
+        object.__setattr__(m, "transformer", tf)
+        object.__setattr__(m, "cnn", cnn)
+        ClipBert.enable_overlapped_allreduce(m, cnn_buckets=(case in ("buckets", "transformer_frozen")))
+        assert (cnn._bucket_hook is not None) == (case in ("buckets", "transformer_frozen"))
+        for step in range(2):                                   # two steps: the per-step state must reset
+            tf._flat.grad.fill_(float(rank + 1) * (step + 1))
+            cnn._flat.grad.zero_()
+            if case in ("buckets", "no_buckets"):
+                tf._grad_ready_hook(tf._flat.grad)              # end of the transformer backward
+            cnn._flat.grad[256:] = torch.arange(256.0, 640.0) * (rank + 1)      # res5 + grid_encoder gradients are final
+            if cnn._bucket_hook is not None:
+                cnn._bucket_hook(cnn._flat.grad, 256, None)
+            cnn._flat.grad[:256] = torch.arange(256.0) * (rank + 1)             # res4 / res3 gradients arrive later
+            ClipBert.allreduce_grads(m)
+            assert m._dp["works"] == [] and m._dp["cnn_lo"] is None and m._dp["tf_started"] is False
+            out[(case, step)] = (float(tf._flat.grad[0]), float(tf._flat.grad[-1]), cnn._flat.grad.tolist())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_bookkeeping_world_size_2():
+    """Every element of both flat buffers is averaged exactly once per step whichever hooks fired: transformer buffer from its
+    hook, CNN tail [lo:) from the mid-backward bucket hook, the rest in allreduce_grads (SURVEY §8 a23 / e)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 137) % 1000
+    procs = [ctx.Process(target=_dp_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        for (case, step), (t0, t1, c) in out.items():
+            assert t0 == pytest.approx(1.5 * (step + 1)) and t1 == pytest.approx(1.5 * (step + 1)), (case, step)
+            assert c == pytest.approx([1.5 * i for i in range(640)]), (case, step)
+
+
 def test_flop_accounting_matches_baseline_md():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
