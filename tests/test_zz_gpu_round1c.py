@@ -75,3 +75,83 @@ def test_pretraining_random_visual_token_sampling(cuda, weights):
     with torch.no_grad():
         e0 = model(ids.to(cuda), grid0.to(cuda), mask.to(cuda), _repeat_counts=[2, 2])
     assert torch.equal(e1["itm_scores"], e0["itm_scores"])
+
+
+def _clipbert(cls_name, sd, cuda, **cfg_extra):
+    import clipbert_b200 as cb
+    cfg = make_cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **cfg_extra)
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", transformer_cls=getattr(cb, cls_name))
+    assert not model.load_state_dict(sd).missing_keys
+    return model.to(cuda)
+
+
+def test_config4_tgif_qa_multiple_choice_clip_batched(cuda, weights):
+    """BASELINE config 4 in miniature (TGIF-QA action: 2 clips x 1 frame, 5 options per video, ClipBertForMultipleChoice):
+    forward_clips folds the (video, clip) units into one pass and returns the (n_clips, B, 5) tensor the reference stacks
+    (run_video_qa.py:470-486); checked against the oracle's per-clip loop and against this path's own loop."""
+    from oracle import clipbert_ref as R, synth
+    sd = dict(weights)
+    sd.update(synth.transformer_state_dict(50, num_labels=1))
+    model = _clipbert("ClipBertForMultipleChoice", sd, cuda, num_labels=5).eval()
+    B, n_clips, T, n_ex, size = 3, 2, 1, 5, 128
+    batch = synth.synth_batch(B, n_clips * T, n_ex=n_ex, size=size, max_len=16, seed=21)
+    labels = torch.tensor([0, 3, 4])
+    vis = batch["visual_inputs"].view(B, n_clips, T, 3, size, size)
+    dev = {k: v.to(cuda) for k, v in batch.items() if torch.is_tensor(v)}
+    with torch.no_grad():
+        out = model.forward_clips(dict(visual_inputs=dev["visual_inputs"], text_input_ids=dev["text_input_ids"],
+                                       text_input_mask=dev["text_input_mask"], n_examples_list=[n_ex] * B), n_clips)["logits"]
+        loop = torch.stack([model(dict(visual_inputs=dev["visual_inputs"].view(B, n_clips, T, 3, size, size)[:, c],
+                                       text_input_ids=dev["text_input_ids"], text_input_mask=dev["text_input_mask"], labels=None,
+                                       n_examples_list=[n_ex] * B))["logits"] for c in range(n_clips)])
+        ref = torch.stack([R.clipbert_forward(dict(batch, visual_inputs=vis[:, c], labels=labels), sd, head="multiple_choice", num_labels=5,
+                                              rnd=R.Rounding.bf16())["logits"] for c in range(n_clips)])
+    assert out.shape == loop.shape == ref.shape == (n_clips, B, 5)
+    assert relerr(out, loop) < 1e-3, relerr(out, loop)
+    assert relerr(out, ref) < TOL_LOGITS, relerr(out, ref)
+    # clip aggregation + CE over the options as the task script does it (mean pooling of the clip scores, run_video_qa.py:488-501)
+    loss = torch.nn.functional.cross_entropy(out.mean(0), labels.to(cuda))
+    loss_ref = torch.nn.functional.cross_entropy(ref.mean(0), labels)
+    assert abs(float(loss) - float(loss_ref)) < 5e-3
+
+
+def test_config3_four_clips_two_frames_clip_batched(cuda, weights):
+    """BASELINE config 3's per-GPU shape in miniature (4 clips x 2 frames, one caption per video): one batched pass of the 8
+    (video, clip) units against the oracle's clip loop, logits and the LSE-aggregated loss (run_video_retrieval.py:404-422)."""
+    from oracle import clipbert_ref as R, synth
+    model = _clipbert("ClipBertForVideoTextRetrieval", weights, cuda).eval()
+    B, n_clips, T, size = 2, 4, 2, 96
+    batch = synth.synth_batch(B, n_clips * T, n_ex=1, size=size, seed=31)
+    vis = batch["visual_inputs"].view(B, n_clips, T, 3, size, size)
+    with torch.no_grad():
+        out = model.forward_clips(dict(visual_inputs=batch["visual_inputs"].to(cuda), text_input_ids=batch["text_input_ids"].to(cuda),
+                                       text_input_mask=batch["text_input_mask"].to(cuda), n_examples_list=[1] * B), n_clips)["logits"]
+        ref = [R.clipbert_forward(dict(batch, visual_inputs=vis[:, c]), weights, rnd=R.Rounding.bf16())["logits"] for c in range(n_clips)]
+    assert out.shape == (n_clips, B, 2)
+    assert relerr(out, torch.stack(ref)) < TOL_LOGITS
+    loss_ref = R.aggregate_clip_logits(ref, batch["labels"], "lse")
+    lg = out.permute(1, 0, 2).contiguous()
+    o = torch.logsumexp(lg.view(B, -1), dim=-1, keepdim=True) - torch.logsumexp(lg, dim=1)
+    loss = torch.gather(o, -1, batch["labels"].to(cuda).view(-1, 1)).mean()
+    assert abs(float(loss) - float(loss_ref)) < 3e-3
+
+
+def test_forward_error_sits_at_the_bf16_noise_floor_of_the_reference_ops(cuda, weights):
+    """How far may a correct bf16 implementation be from the fp32 reference? Run the ORACLE's own ops (plain torch: cuDNN /
+    cuBLAS bf16 under autocast, fp32 LayerNorm / softmax - the mixed precision the reference trains in) on the same GPU and
+    measure its distance from the fp32 oracle; this path must not be further away than a small multiple of that floor."""
+    from oracle import clipbert_ref as R, synth
+    model = _clipbert("ClipBertForVideoTextRetrieval", weights, cuda).eval()
+    batch = synth.synth_batch(2, 2, n_ex=2, size=224, seed=41)
+    with torch.no_grad():
+        ref32 = R.clipbert_forward(dict(batch), weights)["logits"]
+        sd_gpu = {k: v.to(cuda) for k, v in weights.items()}
+        gb = {k: (v.to(cuda) if torch.is_tensor(v) else list(v)) for k, v in batch.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref16 = R.clipbert_forward(gb, sd_gpu)["logits"].float().cpu()
+        mb = {k: (v.to(cuda) if torch.is_tensor(v) else list(v)) for k, v in batch.items()}
+        out = model(mb)["logits"]
+    e_floor, e_ours = relerr(ref16, ref32), relerr(out, ref32)
+    print("bf16 noise floor of the reference ops %.3e | this path %.3e" % (e_floor, e_ours))
+    assert e_ours < TOL_LOGITS
+    assert e_ours < 3.0 * e_floor + 5e-3, (e_ours, e_floor)
