@@ -107,6 +107,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary roofline: the step's largest memory-bound GEMM launch against the measured HBM copy bandwidth
+# ------------------------------------------------------------------------------------------------
+def gemm_algorithmic_bytes(kw):
+    """Bytes of every distinct operand / result tensor of one cb_gemm launch, each counted once."""
+    m, n, k, taps = kw["m"], kw["n"], kw["k"], kw.get("ntaps", 1)
+    if kw.get("mode", 0) == 1:                              # wgrad: dY [k, m], X [k, n] -> fp32 [taps, m, n]
+        return 2 * k * m + 2 * k * n + 4 * m * n * taps
+    b = 2 * m * k + 2 * n * k * taps + (4 if kw.get("out_fp32") else 2) * m * n
+    for t in ("residual", "aux", "out2"):
+        if kw.get(t) is not None:
+            b += 2 * m * n
+    return b
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+# (profiles/r01c_ncu_full_gemm_summary.txt, first row), keyed by the launch's shape
+NCU_TRAFFIC_BYTES = {(401408, 256, 64, 1, True): 257.014272e6 + 165.274624e6}
+
+
+def hbm_bound_launch(ops, rec, stream, peaks, reps=20):
+    cand = [kw for kw in rec if kw.get("mode", 0) != 1 and kw.get("ntaps", 1) == 1 and kw["k"] <= 128 and kw["m"] >= 4096]
+    if not cand:
+        return None
+    kw = max(cand, key=gemm_algorithmic_bytes)
+    nbytes = gemm_algorithmic_bytes(kw)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            ops.gemm(**kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.gemm(**kw)
+        e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    gbs = nbytes / us / 1e3
+    key = (kw["m"], kw["n"], kw["k"], kw.get("ntaps", 1), kw.get("residual") is not None)
+    return dict(bound="hbm", kernel="cb::gemm_kernel 1x1 conv + FrozenBN shift%s + ReLU, m=%d n=%d k=%d" % (
+                    " + shortcut" if kw.get("residual") is not None else "", kw["m"], kw["n"], kw["k"]),
+                achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
+                peak_source="%s hbm_gbs (copy bandwidth)" % peaks["src"], algorithmic_bytes=int(nbytes), us_per_launch=round(us, 2),
+                traffic=NCU_TRAFFIC_BYTES.get(key), traffic_source="profiles/r01c_ncu_full_gemm_summary.txt (ncu --set full, one launch)",
+                note="%d back-to-back launches of the same problem, CUDA events on the launch stream; working set %.0f MB > 126 MB L2"
+                     % (reps, nbytes / 1e6))
+
+
+# ------------------------------------------------------------------------------------------------
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
 def make_host_batch(args, rank):
@@ -309,6 +356,11 @@ def run_b200(args):
         g1.record()
         torch.cuda.synchronize()
         gemm_ms = g0.elapsed_time(g1) / 5
+        # ---- the largest HBM-bound launch of the step on its own (a 1x1 conv: K <= 128, far below the ~225 FLOP/B ridge) ----
+        try:
+            hbm_roof = hbm_bound_launch(ops, rec, gs, peaks)
+        except Exception as e:          # never lose the bench line over the secondary figure
+            hbm_roof = dict(error="%s: %s" % (type(e).__name__, e))
         del gg, rec
         ops.set_pdl(args.pdl)
         ops.overlap_wgrad = bool(args.overlap_wgrad)
@@ -329,7 +381,8 @@ def run_b200(args):
                     gemm_share_of_step=round(gemm_ms / (ms_dev / args.steps), 3),
                     note="gemm_ms_per_step = the step's GEMM launches replayed back to back on one stream; gemm_share_of_step divides it by the "
                          "timed (two-stream) step, so wgrad/dgrad overlap can push it towards or past 1",
-                    whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4))
+                    whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4),
+                    hbm_bound_launch=hbm_roof)
     # Ranks > 0 are done: nothing below is collective. They leave with os._exit after a last barrier - tearing the NCCL process
     # group down while CUDA graphs that captured its kernels are alive hung the run (seen at N = 2), and nothing needs cleanup.
     if world > 1:
