@@ -124,6 +124,10 @@ class ClipBertBaseModel(nn.Module):
         self.pooler = BertPooler(config)
 
 
+def _require_cuda(t):
+    assert t.is_cuda, "ClipBERT transformer runs on CUDA only (no CPU fallback)"
+
+
 def get_random_sample_indices(seq_len, num_samples=100, device=torch.device("cpu")):
     """src/modeling/modeling.py:15-34: sorted indices of a sample without replacement, drawn from numpy's global
     generator exactly as the reference does (np.random.seed reproduces its choice); all indices if num_samples >= seq_len."""
@@ -315,7 +319,7 @@ class _ClipBertHeadModel(nn.Module):
     # ---- forward ----------------------------------------------------------------------------------
     def _run(self, text_input_ids, visual_inputs, text_input_mask, repeat_counts=None):
         """Returns fp32 logits (B', num_outputs). visual_inputs: (B or B', T, h, w, 768)."""
-        assert text_input_ids.is_cuda, "ClipBERT transformer runs on CUDA only (no CPU fallback)"
+        _require_cuda(text_input_ids)
         dev = text_input_ids.device
         self._ensure_ready(dev)
         nseq = text_input_ids.shape[0]

@@ -1,0 +1,122 @@
+"""Host-side orchestration of clipbert_b200/modeling.py on CPU: the real Python engine (flat parameter buffers, stash, call
+order, epilogue flags, index bookkeeping) driven through tests/ops_emulator.py - torch restatements of what include/
+clipbert_b200.h says each entry point computes - and compared with the oracle's autograd. This checks the host logic
+without a GPU; the kernels behind the same calls are checked on a B200 by tests/test_gpu_*.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+from ops_emulator import emulated_transformer_ops
+from util import TOL_GRAD, TOL_LOGITS, cosine, make_cfg, relerr
+
+
+@pytest.fixture(scope="module")
+def weights():
+    from oracle import synth
+    return synth.full_state_dict(42)
+
+
+def _transformer(cls_name, sd, **cfg_extra):
+    import clipbert_b200 as cb
+    cfg = make_cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **cfg_extra)
+    model = getattr(cb, cls_name)(cfg)
+    res = model.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=False)
+    assert set(res.missing_keys) <= {"cls.predictions.decoder.weight", "cls.predictions.decoder.bias"} and not res.unexpected_keys
+    return model.train()
+
+
+def _check_grads(model, sdr, skip=()):
+    bad = []
+    for name, p in model.named_parameters():
+        ref = sdr["transformer." + name].grad
+        if ref is None or float(ref.abs().sum()) == 0.0 or name.endswith("attention.self.key.bias") or name in skip:
+            continue
+        e, c = relerr(p.grad, ref), cosine(p.grad, ref)
+        if not (e < TOL_GRAD and c > 0.999):
+            bad.append((name, e, c))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("counts", [[2, 2, 2], [1, 3, 2]])
+def test_retrieval_engine_forward_backward_on_emulated_ops(weights, counts):
+    from oracle import clipbert_ref as R, synth
+    nvid, nseq = len(counts), sum(counts)
+    g = torch.Generator().manual_seed(2)
+    grid = (torch.randn(nvid, 2, 3, 3, 768, generator=g).abs() * 2).to(torch.bfloat16)
+    ids, mask = synth.synth_text(nseq, 14, seed=3)
+    labels = torch.randint(0, 2, (nseq,), generator=g)
+    model = _transformer("ClipBertForVideoTextRetrieval", weights)
+    gc = grid.clone().requires_grad_(True)
+    with emulated_transformer_ops() as calls:
+        model._capture = {}
+        out = model(ids, gc, mask, labels=labels, sample_size=nvid, _repeat_counts=list(counts))
+        cap, model._capture = model._capture, None
+        out["loss"].mean().backward()
+    assert calls["gemm"] == 12 * 4 + 3 + (12 * 8 + 2 + 2 + 2) and calls["attention_fwd"] == 12 and calls["attention_bwd"] == 12
+    sdr = {k: (v.clone().requires_grad_(True) if k.startswith("transformer.") else v) for k, v in weights.items()}
+    gr = grid.float().requires_grad_(True)
+    rep = R.repeat_tensor_rows(gr, counts)
+    _, pooled = R.clipbert_base_model(ids, rep, mask, sdr)
+    hpat = R.Rounding(relu_masks={"transformer.classifier.relu": cap["c1"] > 0})
+    logits_ref = R.mlp_head(pooled, sdr, rnd=hpat)
+    R.retrieval_loss(logits_ref, labels).mean().backward()
+    assert relerr(out["logits"], logits_ref) < TOL_LOGITS
+    assert relerr(gc.grad, gr.grad) < TOL_GRAD and cosine(gc.grad, gr.grad) > 0.999
+    _check_grads(model, sdr)
+
+
+def test_pretraining_engine_with_visual_token_sampling_on_emulated_ops(weights):
+    """MLM + ITM heads and pre-training's train-mode random sampling of visual tokens (modeling.py:15-34,80-88): same numpy
+    seed -> same kept tokens as the oracle; dropped tokens get no gradient; row / column tables receive the scattered sums."""
+    from oracle import clipbert_ref as R, synth
+    sd = {k: v for k, v in weights.items() if not k.startswith("transformer.classifier.")}
+    sd.update({k: v for k, v in synth.transformer_state_dict(60, head="pretraining").items() if k.startswith("transformer.cls.")})
+    model = _transformer("ClipBertForPreTraining", sd, pixel_random_sampling_size=7)
+    g = torch.Generator().manual_seed(5)
+    grid0 = torch.randn(2, 2, 4, 5, 768, generator=g).abs().bfloat16()
+    ids, mask = synth.synth_text(4, 12, seed=9)
+    mlm = torch.full((4, 12), -100, dtype=torch.long)
+    mlm[:, 3], mlm[:, 7] = ids[:, 3], ids[:, 7]
+    itm = torch.tensor([1, 1, 1, 0])      # mostly one sign: alternating signs make dW_itm a difference of near-equal pooled rows (ill-conditioned under bf16)
+    grid = grid0.clone().requires_grad_(True)
+    with emulated_transformer_ops():
+        np.random.seed(77)
+        out = model(ids, grid, mask, mlm_labels=mlm, itm_labels=itm, _repeat_counts=[2, 2])
+        (out["mlm_loss"].sum() / 8 + out["itm_loss"].mean()).backward()
+    assert out["mlm_scores"].shape == (4, 12, 30522)
+    sdr = {k: (v.clone().requires_grad_(True) if k.startswith("transformer.") else v) for k, v in sd.items()}
+    gr = grid0.float().requires_grad_(True)
+    np.random.seed(77)
+    ref = R.pretraining(ids, R.repeat_tensor_rows(gr, [2, 2]), mask, sdr, mlm, itm, pixel_random_sampling_size=7)
+    (ref["mlm_loss"].sum() / 8 + ref["itm_loss"].mean()).backward()
+    assert relerr(out["itm_scores"], ref["itm_scores"]) < TOL_LOGITS
+    assert relerr(out["mlm_scores"], ref["mlm_scores"]) < TOL_LOGITS
+    np.random.seed(77)
+    kept = set(R.random_sample_indices(20, 7).tolist())
+    dropped = torch.tensor([j for j in range(20) if j not in kept])
+    assert float(grid.grad.float().view(2, 2, 20, 768)[:, :, dropped].abs().max()) == 0.0
+    assert cosine(grid.grad, gr.grad) > 0.999 and relerr(grid.grad, gr.grad) < TOL_GRAD
+    _check_grads(model, sdr)
+    # eval mode: the whole grid (no sampling), L = 12 + 20
+    model.eval()
+    with emulated_transformer_ops(), torch.no_grad():
+        ev = model(ids, grid0, mask, _repeat_counts=[2, 2])
+        ref_ev = R.pretraining(ids, R.repeat_tensor_rows(grid0.float(), [2, 2]), mask, sd)
+    assert relerr(ev["itm_scores"], ref_ev["itm_scores"]) < TOL_LOGITS
+
+
+def test_multiple_choice_engine_on_emulated_ops(weights):
+    from oracle import clipbert_ref as R, synth
+    sd = dict(weights)
+    sd.update(synth.transformer_state_dict(50, num_labels=1))
+    model = _transformer("ClipBertForMultipleChoice", sd, num_labels=5).eval()
+    g = torch.Generator().manual_seed(4)
+    grid = torch.randn(2, 1, 3, 3, 768, generator=g).abs().to(torch.bfloat16)
+    ids, mask = synth.synth_text(10, 16, seed=5)
+    labels = torch.tensor([1, 4])
+    with emulated_transformer_ops(), torch.no_grad():
+        out = model(ids, grid, mask, labels=labels, _repeat_counts=[5, 5])
+        ref = R.multiple_choice(ids, R.repeat_tensor_rows(grid.float(), [5, 5]), mask, sd, 5, labels, rnd=R.Rounding.bf16())
+    assert out["logits"].shape == (2, 5)
+    assert relerr(out["logits"], ref["logits"]) < TOL_LOGITS and relerr(out["loss"], ref["loss"]) < 1e-2
