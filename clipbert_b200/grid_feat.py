@@ -35,6 +35,10 @@ _D2_CONFIG_TEXT = """MODEL:
 """
 
 
+def _require_cuda(t):
+    assert t.is_cuda, "GridFeatBackbone runs on CUDA only (no CPU fallback)"
+
+
 class FrozenBatchNorm2d(nn.Module):
     """Parameter container with detectron2's buffer names; applied as scale/shift in GEMM epilogues."""
 
@@ -302,7 +306,7 @@ class GridFeatBackbone(nn.Module):
     # ---- forward ----------------------------------------------------------------------------------
     def forward(self, x):
         """x: (B, T, 3, H, W) RGB, float (mean-subtracted) or uint8 if ``pixel_mean`` is set."""
-        assert x.is_cuda, "GridFeatBackbone runs on CUDA only (no CPU fallback)"
+        _require_cuda(x)
         self._ensure_ready(x.device)
         if not (torch.is_grad_enabled() and self._any_trainable()):
             return self._forward_impl(x, need_backward=False)[0]

@@ -28,22 +28,67 @@ def _gelu_grad(v):
     return 0.5 * (1.0 + torch.erf(v / math.sqrt(2.0))) + v * torch.exp(-0.5 * v * v) / math.sqrt(2.0 * math.pi)
 
 
+def _shifted_rows(t, n_rows, cols, ld, m, shift):
+    """[m, cols] fp32: row i = row (i + shift) of the [n_rows, cols] window (pitch ld) of t, zero when out of range - the
+    zero fill TMA gives a box that leaves the tensor map. Rows may overlap (ld < cols: the space-to-depth stem)."""
+    win = _mat(t, n_rows, cols, ld)
+    idx = torch.arange(m) + shift
+    ok = (idx >= 0) & (idx < n_rows)
+    out = torch.zeros(m, cols, dtype=F32)
+    out[ok] = win[idx[ok]].to(F32)
+    return out
+
+
+def _tap_shift(t, ntaps, tap_w, tap_sign):
+    if ntaps == 9:
+        return tap_sign * ((t // 3 - 1) * tap_w + (t % 3 - 1))
+    return tap_sign * t * tap_w if ntaps > 1 else 0
+
+
+def _out_rows(kw, m):
+    """cb_rowmap: destination row of GEMM row i (-1 = dropped), and the number of destination rows."""
+    rm = kw.get("rowmap", 0)
+    i = torch.arange(m)
+    if rm == 0:
+        return i, m
+    H, W = kw["map_h"], kw["map_w"]
+    if rm == 1:                                          # compact -> zero-bordered
+        img, r = i // (H * W), i % (H * W)
+        y, x = r // W, r % W
+        return (img * (H + 2) + y + 1) * (W + 2) + x + 1, (m // (H * W)) * (H + 2) * (W + 2)
+    hp, wp = H + 2, W + 2                                # zero-bordered -> compact, border rows dropped
+    img, r = i // (hp * wp), i % (hp * wp)
+    y, x = r // wp, r % wp
+    ok = (y >= 1) & (y <= H) & (x >= 1) & (x <= W)
+    dst = (img * H + (y - 1)) * W + (x - 1)
+    return torch.where(ok, dst, torch.full_like(dst, -1)), (m // (hp * wp)) * H * W
+
+
 def gemm(**kw):
     mode, m, n, k = kw.get("mode", 0), kw["m"], kw["n"], kw["k"]
-    assert kw.get("ntaps", 1) == 1 and kw.get("rowmap", 0) == 0, "emulator covers the transformer-side contractions only"
+    ntaps, tap_w, tap_sign = kw.get("ntaps", 1), kw.get("tap_w", 0), kw.get("tap_sign", 1)
     assert not kw.get("dropout_p"), "emulator: dropout must be off"
     a, b, out = kw["a"], kw["b"], kw["out"]
-    if mode == 1:                                       # WGRAD: out[m, n] += sum_p A[p, m] B[p, n]
+    if mode == 1:                                       # WGRAD: out[m, t*N + n] += rowscale[m] * sum_p A[p, m] B[p + shift_t, n]
         A = _mat(a, k, m, kw["a_ld"]).to(F32)
-        B = _mat(b, k, n, kw["b_ld"]).to(F32)
-        assert out.dtype == F32 and kw.get("out_fp32") == 1
-        _mat(out, m, n, kw["out_ld"]).add_(A.t() @ B)
+        assert out.dtype == F32 and kw.get("out_fp32") == 1 and kw["a_rows"] == k and kw["b_rows"] == k
+        O = _mat(out, m, ntaps * n, kw["out_ld"])
+        for t in range(ntaps):
+            g = (A.t().double() @ _shifted_rows(b, k, n, kw["b_ld"], k, _tap_shift(t, ntaps, tap_w, tap_sign)).double()).float()
+            if kw.get("scale") is not None:
+                g = g * kw["scale"][:m, None]
+            O[:, t * n:(t + 1) * n] += g
         return
-    A = _mat(a, m, k, kw["a_ld"]).to(F32)
-    if mode == 0:                                       # TN: B [n, k]
-        v = A @ _mat(b, n, k, kw["b_ld"]).to(F32).t()
-    else:                                               # NN: B [k, n] (the forward weight read MN-major)
-        v = A @ _mat(b, k, n, kw["b_ld"]).to(F32)
+    # accumulate in float64: the result must not depend on how the CPU BLAS blocks a particular batch shape (the kernels'
+    # per-element accumulation order is independent of M, and tests compare batched against per-clip runs)
+    v = torch.zeros(m, n, dtype=torch.float64)
+    for t in range(ntaps):
+        At = _shifted_rows(a, kw["a_rows"], k, kw["a_ld"], m, _tap_shift(t, ntaps, tap_w, tap_sign)).double()
+        if mode == 0:                                   # TN: B [n, ntaps*k]
+            v += At @ _mat(b, n, ntaps * k, kw["b_ld"])[:, t * k:(t + 1) * k].double().t()
+        else:                                           # NN: B [k, ntaps*n] (the forward weight read MN-major)
+            v += At @ _mat(b, k, ntaps * n, kw["b_ld"])[:, t * n:(t + 1) * n].double()
+    v = v.float()
     if kw.get("scale") is not None:
         v = v * kw["scale"][:n].to(F32)
     if kw.get("shift") is not None:
@@ -51,8 +96,10 @@ def gemm(**kw):
     if kw.get("residual") is not None:
         v = v + _mat(kw["residual"], m, n, kw["res_ld"]).to(F32)
     act = kw.get("act", 0)
+    dst, n_dst = _out_rows(kw, m)
+    keep = dst >= 0
     if kw.get("out2") is not None:
-        _mat(kw["out2"], m, n, kw["out2_ld"]).copy_(_gelu_grad(v) if act == 4 else v)
+        _mat(kw["out2"], n_dst, n, kw["out2_ld"])[dst[keep]] = (_gelu_grad(v) if act == 4 else v)[keep].to(kw["out2"].dtype)
     if act == 1:
         v = torch.relu(v)
     elif act in (2, 4):
@@ -71,7 +118,7 @@ def gemm(**kw):
         elif am == 4:
             v = v * x
     assert (out.dtype == F32) == bool(kw.get("out_fp32", 0))
-    _mat(out, m, n, kw["out_ld"]).copy_(v)
+    _mat(out, n_dst, n, kw["out_ld"])[dst[keep]] = v[keep].to(out.dtype)
 
 
 def _ln_fwd(v, gamma, beta, eps):
@@ -167,7 +214,7 @@ def embed_visual_bwd(dh, grid, seq2vid, vid_start, n_ex, rowemb, colemb, typ, ga
 def _attention(qkv, text_mask, nseq, l, lt, heads):
     hd = qkv.shape[1] // (3 * heads)
     q, k, v = (x.reshape(nseq, l, heads, hd).permute(0, 2, 1, 3) for x in qkv.view(nseq, l, 3, heads * hd).unbind(2))
-    mask = torch.cat([text_mask.to(F32), torch.ones(nseq, l - lt)], dim=1)
+    mask = torch.cat([text_mask.to(qkv.dtype), torch.ones(nseq, l - lt, dtype=qkv.dtype)], dim=1)
     s = q @ k.transpose(-1, -2) / math.sqrt(hd) + ((1.0 - mask) * -10000.0)[:, None, None, :]
     pr = torch.softmax(s, dim=-1)
     return (pr @ v).permute(0, 2, 1, 3).reshape(nseq * l, heads * hd), torch.logsumexp(s, dim=-1)
@@ -175,7 +222,7 @@ def _attention(qkv, text_mask, nseq, l, lt, heads):
 
 def attention_fwd(qkv, text_mask, ctx, lse, nseq, l, lt, heads, p, seed):
     assert not p
-    o, ls = _attention(qkv.to(F32), text_mask, nseq, l, lt, heads)
+    o, ls = _attention(qkv.double(), text_mask, nseq, l, lt, heads)
     ctx.copy_(o)
     if lse is not None:
         lse.copy_(ls)
@@ -213,16 +260,92 @@ def cast_scale(src, dst, rowscale=None, row_len=1):
     dst.copy_(v)
 
 
+# ---------------------------------------------------------------------------------------------------
+# CNN-side data movement (NHWC bf16)
+# ---------------------------------------------------------------------------------------------------
+def _bgr_frames(x, mean):
+    """NCHW RGB (fp32 already mean-subtracted, or uint8 + ImageNorm mean) -> fp32 NCHW BGR, rounded to bf16 like the kernels."""
+    v = x.to(F32) - torch.tensor(mean, dtype=F32).view(1, 3, 1, 1)
+    return v[:, [2, 1, 0]].to(torch.bfloat16).to(F32)
+
+
+def stem_im2col(x, out, n, h, w, kp, mean=(0.0, 0.0, 0.0)):
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cols = F.unfold(_bgr_frames(x, mean), kernel_size=7, padding=3, stride=2)            # [n, (c, r, s), ho*wo]
+    cols = cols.view(n, 3, 7, 7, ho * wo).permute(0, 4, 2, 3, 1).reshape(n * ho * wo, 147)
+    out.zero_()
+    out[:, :147].copy_(cols)
+
+
+def stem_s2d(x, out, n, h, w, ld, mean=(0.0, 0.0, 0.0)):
+    assert ld == 16, "emulator covers the overlapping-row layout"
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    hs, ws = ho + 3, wo + 3
+    P = torch.zeros(n, 3, 2 * hs, 2 * ws, dtype=F32)
+    P[:, :, 3:3 + h, 3:3 + w] = _bgr_frames(x, mean)
+    S = torch.zeros(n, hs, ws, 2, 2, 4, dtype=F32)
+    S[..., :3] = P.view(n, 3, hs, 2, ws, 2).permute(0, 2, 4, 3, 5, 1)
+    out.view(-1)[: n * hs * ws * 16].copy_(S.reshape(-1))
+    out.view(-1)[n * hs * ws * 16:].zero_()             # the slack the last windows run into (the kernel leaves it unwritten)
+
+
+def maxpool3x3s2(x, y, n, h, w, c, row_pitch=None, img_pitch=None):
+    row_pitch = w if row_pitch is None else row_pitch
+    img_pitch = h * w if img_pitch is None else img_pitch
+    v = torch.as_strided(x, (n, h, w, c), (img_pitch * c, row_pitch * c, c, 1), x.storage_offset()).to(F32)
+    o = F.max_pool2d(v.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    y.view(-1)[: o.numel()].copy_(o.reshape(-1))
+
+
+def subsample2(x, y, n, h, w, c):
+    y.view(-1).copy_(x.view(n, h, w, c)[:, ::2, ::2].reshape(-1))
+
+
+def unsubsample2_mask(dsub, act, dx, n, h, w, c):
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    full = torch.zeros(n, h, w, c, dtype=F32)
+    full[:, ::2, ::2] = dsub.view(n, ho, wo, c).to(F32)
+    dx.view(-1).copy_((full * (act.view(n, h, w, c).to(F32) > 0)).reshape(-1))
+
+
+def maxpool2x2_relu_fwd(x, y, n, h, w, c):
+    o = F.max_pool2d(x.view(n, h, w, c).to(F32).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    y.view(-1).copy_(torch.relu(o).reshape(-1))
+
+
+def maxpool2x2_relu_bwd(dy, x, dx_pad, n, h, w, c):
+    xv = x.view(n, h, w, c).to(F32).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    with torch.enable_grad():
+        torch.relu(F.max_pool2d(xv, 2, 2)).backward(dy.view(n, h // 2, w // 2, c).to(F32).permute(0, 3, 1, 2))
+    pad = torch.zeros(n, h + 2, w + 2, c, dtype=F32)
+    pad[:, 1:-1, 1:-1] = xv.grad.permute(0, 2, 3, 1)
+    dx_pad.view(-1).copy_(pad.reshape(-1))
+
+
+def relu_mask(dy, act, dx):
+    dx.view(-1).copy_((dy.to(F32) * (act.to(F32) > 0)).reshape(-1))
+
+
+def cast_scale_segments(master, packed, segments, scales):
+    for off, numel, row_len, soff in segments.tolist():
+        v = master[off: off + numel].view(-1, row_len)
+        if soff >= 0:
+            v = v * scales[soff: soff + v.shape[0], None]
+        packed[off: off + numel].copy_(v.reshape(-1))
+
+
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
-          "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale")
+          "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
+          "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
+          "cast_scale_segments")
 
 
 @contextlib.contextmanager
-def emulated_transformer_ops():
-    """Swap the transformer-side wrappers of clipbert_b200.ops (and the device check of modeling.py) for the torch code above."""
-    from clipbert_b200 import modeling, ops
+def emulated_ops():
+    """Swap the wrappers of clipbert_b200.ops (and the device checks of modeling.py / grid_feat.py) for the torch code above."""
+    from clipbert_b200 import grid_feat, modeling, ops
     saved = {n: getattr(ops, n) for n in _NAMES}
-    saved_overlap, saved_req = ops.overlap_wgrad, modeling._require_cuda
+    saved_overlap, saved_req, saved_req_cnn = ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda
     calls = {n: 0 for n in _NAMES}
 
     def counted(name, fn):
@@ -234,9 +357,12 @@ def emulated_transformer_ops():
         for n in _NAMES:
             setattr(ops, n, counted(n, globals()[n]))
         ops.overlap_wgrad = False
-        modeling._require_cuda = lambda t: None
+        modeling._require_cuda = grid_feat._require_cuda = lambda t: None
         yield calls
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
-        ops.overlap_wgrad, modeling._require_cuda = saved_overlap, saved_req
+        ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda = saved_overlap, saved_req, saved_req_cnn
+
+
+emulated_transformer_ops = emulated_ops

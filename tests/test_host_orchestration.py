@@ -120,3 +120,85 @@ def test_multiple_choice_engine_on_emulated_ops(weights):
         ref = R.multiple_choice(ids, R.repeat_tensor_rows(grid.float(), [5, 5]), mask, sd, 5, labels, rnd=R.Rounding.bf16())
     assert out["logits"].shape == (2, 5)
     assert relerr(out["logits"], ref["logits"]) < TOL_LOGITS and relerr(out["loss"], ref["loss"]) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# CNN engine (clipbert_b200/grid_feat.py) and the full ClipBert module on the emulated ABI
+# ---------------------------------------------------------------------------------------------------
+def _clipbert(sd, cls_name="ClipBertForVideoTextRetrieval", **cfg_extra):
+    import clipbert_b200 as cb
+    cfg = make_cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **cfg_extra)
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", transformer_cls=getattr(cb, cls_name))
+    assert not model.load_state_dict(sd).missing_keys
+    return model
+
+
+@pytest.mark.parametrize("stem", ["s2d", "im2col"])
+def test_cnn_engine_forward_backward_on_emulated_ops(weights, stem):
+    """GridFeatBackbone's host logic: zero-bordered buffers and their recycling, row maps, stride-2 subsampling, the
+    space-to-depth / patch-matrix stem, the backward walk with FREEZE_AT = 2, the mid-backward bucket hook."""
+    from model_util import cnn_patterns
+    from oracle import clipbert_ref as R, synth
+    from util import TOL_FP32_E2E, TOL_MATCHED_DEEP
+    model = _clipbert(weights).train()
+    cnn = model.cnn
+    cnn.stem_mode = stem
+    x = synth.synth_images(1, 2, size=64, seed=6)
+    sd = {k: (v.clone().requires_grad_(True) if (k.endswith(".weight") and "norm" not in k and k.startswith("cnn.")) else v)
+          for k, v in weights.items()}
+    hook_calls = []
+    cnn._bucket_hook = lambda flat_grad, lo, side: hook_calls.append((lo, side, float(flat_grad[lo:].abs().sum()) > 0))
+    with emulated_transformer_ops() as calls:
+        cnn._capture = {}
+        grid = cnn(x)
+        cap, cnn._capture = cnn._capture, None
+        with torch.no_grad():
+            _, st16 = R.grid_feat_backbone(x, weights, return_stages=True, rnd=R.Rounding.bf16())
+        for name in ("stem", "res2", "res3", "res4", "res5"):
+            got = cap[name].float().permute(0, 3, 1, 2)
+            assert relerr(got, st16[name]) < TOL_MATCHED_DEEP, (name, relerr(got, st16[name]))
+        assert relerr(grid, st16["grid"]) < TOL_MATCHED_DEEP
+        pat = cnn_patterns(cap["stash"], grid)
+        grid_ref = R.grid_feat_backbone(x, sd, rnd=pat)
+        assert relerr(grid, grid_ref) < TOL_FP32_E2E
+        dgrid = torch.randn(grid_ref.shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).float()
+        grid_ref.backward(dgrid)
+        grid.backward(dgrid.to(grid.dtype))
+    assert calls["stem_s2d" if stem == "s2d" else "stem_im2col"] == 1 and calls["stem_im2col" if stem == "s2d" else "stem_s2d"] == 0
+    # the bucket hook fired once, after res5.0, with the tail of the flat buffer = res5 + grid_encoder already holding gradients
+    res5_0 = cnn.feature.backbone.res5[0]
+    assert hook_calls == [(res5_0.shortcut._e["offset"], None, True)]
+    assert cnn._pending_backward == 0
+    checked = 0
+    for name, p in cnn.named_parameters():
+        ref = sd["cnn." + name].grad
+        if not p.requires_grad:
+            continue
+        assert cosine(p.grad, ref) > 0.999 and relerr(p.grad, ref) < TOL_GRAD, (name, cosine(p.grad, ref), relerr(p.grad, ref))
+        checked += 1
+    assert checked == 3 * 13 + 3 + 1
+
+
+def test_clipbert_forward_clips_and_clip_loop_on_emulated_ops(weights):
+    """ClipBert.forward_clips against the reference-order clip loop and the oracle, ragged n_examples_list, end to end
+    (CNN + transformer + LSE aggregation), including the dict mutations of ClipBert.forward (e2e_model.py:29-39)."""
+    from oracle import clipbert_ref as R, synth
+    model = _clipbert(weights).eval()
+    n_clips, T, B, size = 2, 1, 2, 64
+    counts = [2, 1]
+    batch = synth.synth_batch(B, n_clips * T, n_ex=1, size=size, seed=11)
+    ids, mask = synth.synth_text(sum(counts), 10, seed=12)
+    vis = batch["visual_inputs"].view(B, n_clips, T, 3, size, size)
+    with emulated_transformer_ops(), torch.no_grad():
+        out = model.forward_clips(dict(visual_inputs=batch["visual_inputs"], text_input_ids=ids, text_input_mask=mask,
+                                       n_examples_list=list(counts)), n_clips)["logits"]
+        loop = []
+        for c in range(n_clips):
+            mb = dict(visual_inputs=vis[:, c], text_input_ids=ids, text_input_mask=mask, labels=None, n_examples_list=list(counts))
+            loop.append(model(mb)["logits"])
+            assert "n_examples_list" not in mb and mb["sample_size"] == B and mb["visual_inputs"].shape == (B, T, 1, 1, 768)
+        ref = [R.clipbert_forward(dict(visual_inputs=vis[:, c], text_input_ids=ids, text_input_mask=mask, n_examples_list=list(counts)),
+                                  weights, rnd=R.Rounding.bf16())["logits"] for c in range(n_clips)]
+    assert out.shape == (n_clips, sum(counts), 2)
+    assert torch.equal(out, torch.stack(loop))          # float64 accumulation in the emulator: batching must not change a bit
+    assert relerr(out, torch.stack(ref)) < TOL_LOGITS

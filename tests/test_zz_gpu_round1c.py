@@ -43,7 +43,7 @@ def test_pretraining_random_visual_token_sampling(cuda, weights):
     mlm[:, 3] = ids[:, 3]
     mlm[:, 7] = ids[:, 7]
     itm = torch.tensor([1, 1, 1, 0])      # mostly one sign: alternating signs make dW_itm a difference of near-equal pooled rows (ill-conditioned under bf16)
-    grid = grid0.to(cuda).requires_grad_(True)
+    grid = grid0.clone().to(cuda).requires_grad_(True)
     np.random.seed(77)
     out = model(ids.to(cuda), grid, mask.to(cuda), mlm_labels=mlm.to(cuda), itm_labels=itm.to(cuda), _repeat_counts=[2, 2])
     assert out["mlm_scores"].shape == (4, 12, 30522)
