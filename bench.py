@@ -243,7 +243,7 @@ def run_b200(args):
                 mb = dict(visual_inputs=vis[:, c], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
                           labels=dbuf["labels"], n_examples_list=[n_ex] * B)
                 logits.append(model(mb)["logits"])
-        loss = lse_loss(logits, dbuf["labels"])
+        loss = cb.clip_lse_loss(logits, dbuf["labels"]) if args.fused_loss else lse_loss(logits, dbuf["labels"])
         loss.backward()
         if world > 1:
             model.allreduce_grads()       # transformer buffer already in flight since its last backward (overlaps the CNN backward)
@@ -451,7 +451,7 @@ def run_b200(args):
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
-                               cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if (opt is not None and not args.recast_in_step) else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -567,6 +567,7 @@ def main():
     ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
+    ap.add_argument("--fused_loss", type=int, default=0, help="1: clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss) instead of ~45 ATen launches (off until its GPU test has run)")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
     ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")

@@ -34,6 +34,37 @@ def allreduce_flat(grads, group=None, average=True, async_op=False):
     return works
 
 
+class _ClipLseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        from . import ops
+        z = logits.detach()
+        z = (z if z.dtype == torch.float32 else z.float()).contiguous()
+        n_clips, nseq, ncls = z.shape
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        ops.clip_lse_loss(z, labels.to(torch.int64).contiguous(), loss, dz, n_clips, nseq, ncls, 1.0)
+        ctx.dz, ctx.in_dtype = dz, logits.dtype
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dz, ctx.dz = ctx.dz, None
+        return (dz * g).to(ctx.in_dtype), None
+
+
+def clip_lse_loss(logits, labels):
+    """Clip aggregation + loss of the training loops with ``pool_method == "lse"``
+    (src/tasks/run_video_retrieval.py:404-422, run_video_qa.py:484-501) as one fused forward+backward kernel.
+
+    ``logits``: the ``(n_clips, B', C)`` tensor the reference builds with ``torch.stack(logits)`` (what
+    ``ClipBert.forward_clips`` returns); ``labels``: ``(B',)`` int64. Returns the scalar
+    ``mean_b(logsumexp_{k,c} z[k,b,c] - logsumexp_k z[k,b,y_b])`` with autograd support."""
+    if isinstance(logits, (list, tuple)):
+        logits = torch.stack(list(logits))
+    return _ClipLseLoss.apply(logits, labels)
+
+
 class ClipBert(nn.Module):
     def __init__(self, config, input_format="BGR", detectron2_model_cfg=None, transformer_cls=ClipBertForVideoTextRetrieval,
                  freeze_at=2):

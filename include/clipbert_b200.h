@@ -242,6 +242,16 @@ int cb_maxpool2x2_relu_bwd(const void* dy, const void* x, void* dx_pad, int n, i
 int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Clip-level score aggregation + loss of the training loops, pool_method "lse"
+ * (src/tasks/run_video_retrieval.py:404-422, src/tasks/run_video_qa.py:484-501), forward AND backward in one launch:
+ *   loss[0]  = mean_b ( logsumexp_{k,c} z[k,b,c] - logsumexp_k z[k,b,y_b] )          z = logits, fp32 [n_clips, nseq, ncls]
+ *   dlogits  = grad_scale * d loss / d z   (fp32, same shape; NULL = forward only)   y = labels, int64 [nseq]
+ * Replaces torch.stack + permute + two torch.logsumexp + torch.gather + mean and their autograd nodes (~45 ATen launches).
+ * ------------------------------------------------------------------------------------------ */
+int cb_clip_lse_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int n_clips, int nseq, int ncls,
+                     float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused optimizer step over the flat fp32 parameter buffers.
  *   cb_sumsq       out[0] += sum(x^2)  - the norm half of torch.nn.utils.clip_grad_norm_ as called at
  *                  src/tasks/run_video_retrieval.py:477-480 (one call per flat gradient buffer, caller zeroes out); with a

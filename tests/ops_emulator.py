@@ -326,6 +326,18 @@ def relu_mask(dy, act, dx):
     dx.view(-1).copy_((dy.to(F32) * (act.to(F32) > 0)).reshape(-1))
 
 
+def clip_lse_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, grad_scale=1.0):
+    z = logits.detach().clone().requires_grad_(dlogits is not None)
+    with torch.enable_grad():
+        lg = z.permute(1, 0, 2)
+        out = torch.logsumexp(lg.reshape(nseq, -1), dim=-1, keepdim=True) - torch.logsumexp(lg, dim=1)
+        val = torch.gather(out, -1, labels.view(-1, 1)).mean()
+        if dlogits is not None:
+            val.backward()
+            dlogits.copy_(z.grad * grad_scale)
+    loss.copy_(val.detach().reshape(1))
+
+
 def cast_scale_segments(master, packed, segments, scales):
     for off, numel, row_len, soff in segments.tolist():
         v = master[off: off + numel].view(-1, row_len)
@@ -337,7 +349,7 @@ def cast_scale_segments(master, packed, segments, scales):
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
-          "cast_scale_segments")
+          "cast_scale_segments", "clip_lse_loss")
 
 
 @contextlib.contextmanager

@@ -202,3 +202,25 @@ def test_clipbert_forward_clips_and_clip_loop_on_emulated_ops(weights):
     assert out.shape == (n_clips, sum(counts), 2)
     assert torch.equal(out, torch.stack(loop))          # float64 accumulation in the emulator: batching must not change a bit
     assert relerr(out, torch.stack(ref)) < TOL_LOGITS
+
+
+def test_fused_clip_lse_loss_function_on_emulated_ops():
+    """clipbert_b200.clip_lse_loss (autograd wrapper of cb_clip_lse_loss) against the oracle's clip aggregation
+    (run_video_retrieval.py:404-422) - value, gradient, upstream scaling, list input."""
+    import clipbert_b200 as cb
+    from oracle import clipbert_ref as R
+    g = torch.Generator().manual_seed(3)
+    for n_clips, nseq, ncls in ((2, 5, 2), (4, 7, 5), (1, 3, 2)):
+        z = torch.randn(n_clips, nseq, ncls, generator=g)
+        y = torch.randint(0, ncls, (nseq,), generator=g)
+        zr = z.clone().requires_grad_(True)
+        ref = R.aggregate_clip_logits(list(zr.unbind(0)), y, "lse")
+        (3.0 * ref).backward()
+        zt = z.clone().requires_grad_(True)
+        with emulated_transformer_ops() as calls:
+            loss = cb.clip_lse_loss(zt, y)
+            (3.0 * loss).backward()
+            loss_list = cb.clip_lse_loss(list(z.unbind(0)), y)
+        assert calls["clip_lse_loss"] == 2
+        assert loss.shape == () and torch.allclose(loss, ref.detach(), atol=1e-6) and torch.allclose(loss_list, ref.detach(), atol=1e-6)
+        assert torch.allclose(zt.grad, zr.grad, atol=1e-6)

@@ -136,6 +136,27 @@ def test_config3_four_clips_two_frames_clip_batched(cuda, weights):
     assert abs(float(loss) - float(loss_ref)) < 3e-3
 
 
+def test_fused_clip_lse_loss_kernel(cuda):
+    """cb_clip_lse_loss (forward + backward of the "lse" clip aggregation, run_video_retrieval.py:404-422) against the oracle:
+    fp32 in / fp32 out, so the tolerance is accumulation-order noise (fast-math exp / log: 1e-5 relative)."""
+    import clipbert_b200 as cb
+    from oracle import clipbert_ref as R
+    g = torch.Generator().manual_seed(3)
+    for n_clips, nseq, ncls, scale in ((2, 32, 2, 1.0), (4, 320, 5, 3.0), (16, 8, 2, 0.2), (1, 1, 2, 1.0), (2, 700, 3, 10.0)):
+        z = torch.randn(n_clips, nseq, ncls, generator=g) * scale
+        y = torch.randint(0, ncls, (nseq,), generator=g)
+        zr = z.clone().requires_grad_(True)
+        ref = R.aggregate_clip_logits(list(zr.unbind(0)), y, "lse")
+        (2.0 * ref).backward()
+        zt = z.to(cuda).requires_grad_(True)
+        loss = cb.clip_lse_loss(zt, y.to(cuda))
+        (2.0 * loss).backward()
+        assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref))), (n_clips, nseq, ncls, float(loss), float(ref))
+        assert relerr(zt.grad, zr.grad) < 2e-5, (n_clips, nseq, ncls, relerr(zt.grad, zr.grad))
+        with torch.no_grad():                      # forward only (no gradient buffer)
+            assert abs(float(cb.clip_lse_loss(z.to(cuda), y.to(cuda))) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+
+
 def test_forward_error_sits_at_the_bf16_noise_floor_of_the_reference_ops(cuda, weights):
     """How far may a correct bf16 implementation be from the fp32 reference? Run the ORACLE's own ops (plain torch: cuDNN /
     cuBLAS bf16 under autocast, fp32 LayerNorm / softmax - the mixed precision the reference trains in) on the same GPU and
