@@ -1,0 +1,16 @@
+#!/bin/bash
+# N = 2 A/B of the data-parallel exchange switches (charged 2x):
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_multi_gpu.sh 2'
+set -u
+N=${1:-2}
+mkdir -p gpurun_out
+run() {  # label, flags
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) \
+    bench.py --gpus $N --steps 10 --warmup 3 --no_cpu 1 --optimizer 0 $2 > gpurun_out/mg_${N}_$1.json 2> gpurun_out/mg_${N}_$1.err
+  echo "$1 [$2] rc=$? $(python -c "import json; d=json.load(open('gpurun_out/mg_${N}_$1.json')); print(d['value'], 'clips/s', d['ms_per_step'], 'ms/step')" 2>&1 | tail -1)"
+}
+run base ""
+run buckets "--cnn_buckets 1"
+run ctas16 "--nccl_ctas 16 --sm_limit 132"
+run ctas8 "--nccl_ctas 8 --sm_limit 140"
+run buckets_ctas16 "--cnn_buckets 1 --nccl_ctas 16 --sm_limit 132"
