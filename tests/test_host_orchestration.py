@@ -224,3 +224,42 @@ def test_fused_clip_lse_loss_function_on_emulated_ops():
         assert calls["clip_lse_loss"] == 2
         assert loss.shape == () and torch.allclose(loss, ref.detach(), atol=1e-6) and torch.allclose(loss_list, ref.detach(), atol=1e-6)
         assert torch.allclose(zt.grad, zr.grad, atol=1e-6)
+
+
+def test_training_step_clip_loop_vs_batched_pass_on_emulated_ops(weights):
+    """One training step both ways - the reference's per-clip loop (n_clips forward calls, one backward through all of them)
+    and ONE batched pass (forward_clips) - must give the same gradients in both halves; the data-parallel hooks fire once per
+    step, after the LAST outstanding backward of each half (gradients of all clips accumulated)."""
+    import clipbert_b200 as cb
+    from oracle import synth
+    model = _clipbert(weights).train()
+    n_clips, T, B, size = 2, 1, 2, 64
+    batch = synth.synth_batch(B, n_clips * T, n_ex=1, size=size, seed=21)
+    vis = batch["visual_inputs"].view(B, n_clips, T, 3, size, size)
+    fired = []
+    model.transformer._grad_ready_hook = lambda g: fired.append(("transformer", float(g.abs().sum())))
+    model.cnn._bucket_hook = lambda g, lo, side: fired.append(("cnn", lo, model.transformer._pending_backward, model.cnn._pending_backward))
+
+    def grads():
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+
+    with emulated_transformer_ops():
+        model.zero_grad()
+        logits = [model(dict(visual_inputs=vis[:, c], text_input_ids=batch["text_input_ids"], text_input_mask=batch["text_input_mask"],
+                             labels=batch["labels"], n_examples_list=[1] * B))["logits"] for c in range(n_clips)]
+        cb.clip_lse_loss(logits, batch["labels"]).backward()
+        g_loop, fired_loop = grads(), list(fired)
+        fired.clear()
+        model.zero_grad()
+        out = model.forward_clips(dict(visual_inputs=batch["visual_inputs"], text_input_ids=batch["text_input_ids"],
+                                       text_input_mask=batch["text_input_mask"], n_examples_list=[1] * B), n_clips)["logits"]
+        cb.clip_lse_loss(out, batch["labels"]).backward()
+        g_batched = grads()
+    # hooks: once per half per step, when nothing else of that half is pending
+    for events in (fired_loop, fired):
+        assert [e[0] for e in events] == ["transformer", "cnn"], events
+        assert events[0][1] > 0 and events[1][2] == 0 and events[1][3] == 0
+    assert set(g_loop) == set(g_batched) and len(g_loop) > 200
+    bad = [(n, relerr(g_batched[n], g_loop[n])) for n in g_loop
+           if float(g_loop[n].abs().sum()) > 0 and not (relerr(g_batched[n], g_loop[n]) < 2e-2 and cosine(g_batched[n], g_loop[n]) > 0.999)]
+    assert not bad, bad[:8]
