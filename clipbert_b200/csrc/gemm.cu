@@ -53,6 +53,9 @@ struct GemmEpi {
   uint64_t seed;
   int direct;       // TMA epilogue only: 1 = every thread stores its own row segment straight from registers (no smem staging,
                     // no chunk barrier, no TMA store); 0 = swizzled smem chunk + TMA store / cooperative re-mapped copy
+  int pdl_late;     // programmatic dependent launch: 0 = release the dependents at kernel entry; 1 = when this CTA starts its
+                    // LAST tile, so that a dependent's CTAs (200 KB of shared memory each) are not parked on freed SMs for the
+                    // whole launch - which is what kept the wgrad side stream off those SMs (include/clipbert_b200.h, cb_set_pdl)
   long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
 };
 
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
   const int unit = blockIdx.x / CG;                                     // persistent work unit (CTA or CTA pair)
   const int n_units = gridDim.x / CG;
   if (threadIdx.x == 0) dbg_stamp(epi, 0);   // (debug-only buffer, not produced by any kernel: safe before pdl_wait)
-  pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
+  if (!epi.pdl_late) pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
         const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
+        if (epi.pdl_late && tile + n_units >= total_tiles) pdl_trigger();   // last tile of this CTA (a non-issuing CTA releases on exit)
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -845,6 +849,7 @@ static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA ep
 static int g_direct_store = 0; // TMA epilogue: 0 = smem chunk + TMA store (default); 1 = direct register -> global stores. EXPERIMENTAL:
                                // +1.3 % on the step but an intermittent mismatch (one warp's 32x16 block of one launch in ~100) on
                                // multi-tile CTAs when the epilogue warps drift apart without the per-chunk barrier - not yet explained
+static int g_pdl_late = 0;    // PDL trigger placement of the GEMM kernel (GemmEpi::pdl_late); cb_debug_gemm_pdl_late
 static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
@@ -1026,6 +1031,7 @@ extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
 extern "C" void cb_debug_gemm_direct_store(int on) { cb::g_direct_store = on ? 1 : 0; }
+extern "C" void cb_debug_gemm_pdl_late(int on) { cb::g_pdl_late = on ? 1 : 0; }
 extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? (n < 2 ? 2 : n & ~1) : 0; }   // even: CTA pairs
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
@@ -1060,6 +1066,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.seed = d.dropout_seed;
   epi.dbg = g_gemm_timeline;
   epi.direct = g_direct_store;
+  epi.pdl_late = g_pdl_late;
   if (d.dropout_p > 0.0f) {
     double t = static_cast<double>(d.dropout_p) * 4294967296.0;
     epi.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);

@@ -98,6 +98,11 @@ def set_direct_store(on):
     L.lib().cb_debug_gemm_direct_store(int(bool(on)))
 
 
+def set_pdl_late(on):
+    """Tuning hook (with set_pdl(1)): the GEMM kernel releases its dependents when a CTA starts its last tile instead of at entry."""
+    L.lib().cb_debug_gemm_pdl_late(int(bool(on)))
+
+
 def set_sm_limit(n):
     """Tuning hook: cap the persistent GEMM grid at ``n`` CTAs (0 = every SM): leaves SMs to a co-resident NCCL kernel so
     that the static tile schedule does not spill into a second wave while a gradient all-reduce overlaps the backward."""
