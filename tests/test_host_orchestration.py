@@ -263,3 +263,40 @@ def test_training_step_clip_loop_vs_batched_pass_on_emulated_ops(weights):
     bad = [(n, relerr(g_batched[n], g_loop[n])) for n in g_loop
            if float(g_loop[n].abs().sum()) > 0 and not (relerr(g_batched[n], g_loop[n]) < 2e-2 and cosine(g_batched[n], g_loop[n]) > 0.999)]
     assert not bad, bad[:8]
+
+
+def test_bf16_operand_refresh_contract_on_emulated_ops(weights):
+    """When the bf16 operand copy is refreshed ("Weight updates"): after a backward (reference AdamW edits
+    p.data in place), on version-counted writes, on mark_weights_updated(); an unannounced p.data edit between two
+    forward-only passes is the documented exception."""
+    from oracle import synth
+    model = _clipbert(weights).eval()
+    batch = synth.synth_batch(1, 1, n_ex=1, size=64, seed=5)
+
+    def fwd():
+        with torch.no_grad():
+            return model({k: (v.clone() if torch.is_tensor(v) else list(v)) for k, v in batch.items()})["logits"]
+
+    w_cls = model.transformer.classifier[2].weight
+    w_ge = model.cnn.grid_encoder[0].weight
+    with emulated_transformer_ops():
+        base = fwd()
+        with torch.no_grad():
+            w_cls.mul_(1.5)                      # version-counted write: picked up
+            w_ge.mul_(1.5)
+        a = fwd()
+        assert not torch.equal(a, base)
+        w_cls.data.mul_(2.0)                     # p.data edit, no backward in between: NOT seen ...
+        w_ge.data.mul_(2.0)
+        assert torch.equal(fwd(), a)
+        model.cnn.mark_weights_updated()         # ... until announced
+        model.transformer.mark_weights_updated()
+        b = fwd()
+        assert not torch.equal(b, a)
+        model.train()                            # reference training order: forward, backward, p.data update, forward
+        out = model({k: (v.clone() if torch.is_tensor(v) else list(v)) for k, v in batch.items()})
+        out["loss"].mean().backward()
+        w_cls.data.mul_(0.5)
+        w_ge.data.mul_(0.5)
+        model.eval()
+        assert torch.allclose(fwd(), a, atol=1e-6)
