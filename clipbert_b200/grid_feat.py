@@ -154,6 +154,10 @@ class GridFeatBackbone(nn.Module):
         self._s2d_ld = 16        # 16: overlapping tensor-map rows; 64: explicit windows (set automatically if the driver refuses)
         self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
         # d2 FREEZE_AT: stem (1) and res2 (2) get no gradient
+        if freeze_at < 1:
+            # the reference ships FREEZE_AT: 2 (Base-RCNN-grid.yaml) and only ever freezes more (freeze_cnn_backbone); the
+            # backward of the stem (max-pool scatter + 7x7 wgrad) is not built, and silently returning no gradient is worse
+            raise NotImplementedError("GridFeatBackbone: FREEZE_AT = 0 (trainable stem) is not supported on the B200 path")
         bb = self.feature.backbone
         if freeze_at >= 1:
             for p in bb.stem.parameters():

@@ -300,3 +300,38 @@ def test_bf16_operand_refresh_contract_on_emulated_ops(weights):
         w_ge.data.mul_(0.5)
         model.eval()
         assert torch.allclose(fwd(), a, atol=1e-6)
+
+
+@pytest.mark.parametrize("freeze_at", [1, 3])
+def test_cnn_engine_other_freeze_points_on_emulated_ops(weights, freeze_at):
+    """detectron2's BACKBONE.FREEZE_AT other than the shipped 2: res2 trainable (1) / res3 frozen too (3). FREEZE_AT = 0 (a
+    trainable stem) has no backward on this path and must be refused rather than return a silent zero gradient."""
+    import clipbert_b200 as cb
+    from model_util import cnn_patterns
+    from oracle import clipbert_ref as R, synth
+    cfg = make_cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    with pytest.raises(NotImplementedError):
+        cb.GridFeatBackbone(detectron2_model_cfg="R-50-grid.yaml", config=cfg, freeze_at=0)
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", freeze_at=freeze_at)
+    model.load_state_dict(weights)
+    model.train()
+    x = synth.synth_images(1, 2, size=64, seed=6)
+    sd = {k: (v.clone().requires_grad_(True) if (k.endswith(".weight") and "norm" not in k and k.startswith("cnn.")) else v)
+          for k, v in weights.items()}
+    with emulated_transformer_ops():
+        model.cnn._capture = {}
+        grid = model.cnn(x)
+        cap, model.cnn._capture = model.cnn._capture, None
+        ref = R.grid_feat_backbone(x, sd, rnd=cnn_patterns(cap["stash"], grid), freeze_at=freeze_at)
+        dg = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+        ref.backward(dg)
+        grid.backward(dg.to(grid.dtype))
+    checked = 0
+    for name, p in model.cnn.named_parameters():
+        r = sd["cnn." + name].grad
+        if not p.requires_grad:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0
+            continue
+        assert cosine(p.grad, r) > 0.999 and relerr(p.grad, r) < TOL_GRAD, name
+        checked += 1
+    assert checked == {1: 53, 3: 30}[freeze_at]
