@@ -87,7 +87,18 @@ class ClipBert(nn.Module):
             batch["sample_size"] = len(repeat_counts)  # batch size
         return self.transformer(_repeat_counts=list(repeat_counts), **batch)
 
-    def forward_clips(self, batch, num_clips):
+    def encode_clips(self, visual_inputs, num_clips):
+        """CNN half only: ``(B, num_clips * num_frm, 3, H, W)`` frames -> the grid features of the ``B * num_clips``
+        (video, clip) units, ``(B * num_clips, num_frm, h, w, 768)``, to be handed to ``forward_clips(..., grid=...)``.
+
+        The reference's ``inference_retrieval`` re-runs the CNN on the same clip for every caption mini-batch of a video
+        (1000 captions / eval_bsz times, src/tasks/run_video_retrieval.py:639-666); computing the grid once per video is
+        the same arithmetic."""
+        bsz, frames = visual_inputs.shape[0], visual_inputs.shape[1]
+        assert frames % num_clips == 0, "visual_inputs must hold num_clips * num_frm frames per video"
+        return self.cnn(visual_inputs.reshape((bsz * num_clips, frames // num_clips) + tuple(visual_inputs.shape[2:])))
+
+    def forward_clips(self, batch, num_clips, grid=None):
         """All ``num_clips`` clips of a step in ONE pass ("clip batching").
 
         The reference loops ``for clip_idx in range(num_clips): model(mini_batch)`` over
@@ -99,12 +110,21 @@ class ClipBert(nn.Module):
         ``(B, num_clips * num_frm, 3, H, W)``; returns ``dict(logits=(num_clips, B', C))`` - the tensor the
         reference builds with ``torch.stack(logits)`` - for the caller's clip aggregation + loss. Only the
         dropout streams differ from the loop (one seed per pass instead of one per clip).
+
+        ``grid``: features from ``encode_clips`` of the same videos; the CNN is then skipped and ``batch`` needs no
+        ``visual_inputs`` (caption mini-batches of one video at inference).
         """
-        vis = batch["visual_inputs"]
         counts = [int(c) for c in batch["n_examples_list"]]
-        bsz, frames = vis.shape[0], vis.shape[1]
-        assert frames % num_clips == 0, "visual_inputs must hold num_clips * num_frm frames per video"
-        key = (tuple(counts), num_clips, str(vis.device))
+        if grid is not None:
+            assert grid.shape[0] == len(counts) * num_clips, "grid must come from encode_clips of the same videos"
+            vis, bsz = None, len(counts)
+            dev = grid.device
+        else:
+            vis = batch["visual_inputs"]
+            bsz, frames = vis.shape[0], vis.shape[1]
+            assert frames % num_clips == 0, "visual_inputs must hold num_clips * num_frm frames per video"
+            dev = vis.device
+        key = (tuple(counts), num_clips, str(dev))
         plan = getattr(self, "_clip_plan", None)
         if plan is None or plan[0] != key:
             # text rows of unit (b, c) = the rows of video b; output row (c, b, e) <- pass row (b, c, e)
@@ -114,16 +134,19 @@ class ClipBert(nn.Module):
             gather = [starts[b] + e for b in range(bsz) for _c in range(num_clips) for e in range(counts[b])]
             unit0 = [num_clips * starts[b] for b in range(bsz)]
             scatter = [unit0[b] + c * counts[b] + e for c in range(num_clips) for b in range(bsz) for e in range(counts[b])]
-            dev = vis.device
             plan = (key, torch.tensor(gather, dtype=torch.int64, device=dev), torch.tensor(scatter, dtype=torch.int64, device=dev),
                     [counts[b] for b in range(bsz) for _c in range(num_clips)])
             self._clip_plan = plan
         _, gather, scatter, unit_counts = plan
-        mb = dict(visual_inputs=vis.reshape((bsz * num_clips, frames // num_clips) + tuple(vis.shape[2:])),
-                  text_input_ids=batch["text_input_ids"].index_select(0, gather),
-                  text_input_mask=batch["text_input_mask"].index_select(0, gather),
-                  labels=None, n_examples_list=unit_counts)
-        logits = self.forward(mb)["logits"]
+        mb = dict(text_input_ids=batch["text_input_ids"].index_select(0, gather),
+                  text_input_mask=batch["text_input_mask"].index_select(0, gather), labels=None)
+        if grid is None:
+            mb.update(visual_inputs=vis.reshape((bsz * num_clips, frames // num_clips) + tuple(vis.shape[2:])), n_examples_list=unit_counts)
+            logits = self.forward(mb)["logits"]
+        else:
+            if self.retrieval:
+                mb["sample_size"] = len(unit_counts)
+            logits = self.transformer(visual_inputs=grid, _repeat_counts=list(unit_counts), **mb)["logits"]
         if logits.shape[0] == scatter.shape[0]:
             return dict(logits=logits.index_select(0, scatter).view(num_clips, -1, logits.shape[-1]))
         # multiple choice: calc_loss already folded the options of a unit into one row (modeling.py:436-437)

@@ -335,3 +335,33 @@ def test_cnn_engine_other_freeze_points_on_emulated_ops(weights, freeze_at):
         assert cosine(p.grad, r) > 0.999 and relerr(p.grad, r) < TOL_GRAD, name
         checked += 1
     assert checked == {1: 53, 3: 30}[freeze_at]
+
+
+def test_inference_retrieval_grid_reuse_on_emulated_ops(weights):
+    """inference_retrieval (src/tasks/run_video_retrieval.py:628-666): one video, its captions in mini-batches, every clip
+    scored per mini-batch. encode_clips once + forward_clips(grid=...) per mini-batch must equal the reference-order loop
+    (which re-runs the CNN for every mini-batch and clip) bit for bit, and the oracle within bf16 tolerance."""
+    from oracle import clipbert_ref as R, synth
+    model = _clipbert(weights).eval()
+    n_clips, T, size, n_caps, eval_bsz = 3, 1, 64, 5, 2
+    vis = synth.synth_images(1, n_clips * T, size=size, seed=31)
+    ids, mask = synth.synth_text(n_caps, 10, seed=32)
+    clips = vis.view(1, n_clips, T, 3, size, size)
+    with emulated_transformer_ops() as calls, torch.no_grad():
+        loop = []
+        for i in range(0, n_caps, eval_bsz):
+            per_clip = [model(dict(visual_inputs=clips[:, c], text_input_ids=ids[i:i + eval_bsz], text_input_mask=mask[i:i + eval_bsz],
+                                   labels=None, n_examples_list=[len(ids[i:i + eval_bsz])]))["logits"] for c in range(n_clips)]
+            loop.append(torch.stack(per_clip))
+        stems_loop = calls["stem_s2d"]
+        grid = model.encode_clips(vis, n_clips)
+        fast = [model.forward_clips(dict(text_input_ids=ids[i:i + eval_bsz], text_input_mask=mask[i:i + eval_bsz],
+                                         n_examples_list=[len(ids[i:i + eval_bsz])]), n_clips, grid=grid)["logits"]
+                for i in range(0, n_caps, eval_bsz)]
+        assert stems_loop == 9 and calls["stem_s2d"] == 10          # 3 mini-batches x 3 clips vs one CNN pass
+        ref = torch.stack([R.clipbert_forward(dict(visual_inputs=clips[:, c], text_input_ids=ids, text_input_mask=mask, n_examples_list=[n_caps]),
+                                              weights, rnd=R.Rounding.bf16())["logits"] for c in range(n_clips)])
+    assert grid.shape == (n_clips, T, 1, 1, 768)
+    for a, b in zip(fast, loop):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert relerr(torch.cat(fast, dim=1), ref) < TOL_LOGITS
