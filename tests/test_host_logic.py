@@ -189,3 +189,34 @@ def test_forward_clips_index_plan_reproduces_the_reference_clip_loop(counts, mon
                         for c in range(n_clips)])
     out = model.forward_clips(dict(visual_inputs=vis, text_input_ids=ids, text_input_mask=mask, n_examples_list=list(counts)), n_clips)["logits"]
     assert out.shape == (n_clips, sum(counts), 2) and torch.equal(out, loop)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/optimization"), reason="reference tree not present (GPU box)")
+def test_reference_setup_e2e_optimizer_runs_unchanged_on_this_model():
+    """The reference's own setup_e2e_optimizer (src/optimization/utils.py:96-161), imported where it lies, builds its 8
+    parameter groups from THIS package's ClipBert by parameter name alone - the drop-in contract of SURVEY.md §8b."""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, "/root/reference")
+    from src.optimization.utils import setup_e2e_optimizer
+    import clipbert_b200 as cb
+    from util import make_cfg
+    model = cb.ClipBert(make_cfg(), detectron2_model_cfg="R-50-grid.yaml", transformer_cls=cb.ClipBertForVideoTextRetrieval)
+    opts = types.SimpleNamespace(learning_rate=5e-5, weight_decay=1e-3, transformer_lr_mul=1.0, transformer_lr_mul_prefix="",
+                                 cnn_learning_rate=5e-5, cnn_weight_decay=1e-3, cnn_lr_mul=1.0, cnn_lr_mul_prefix="grid_encoder",
+                                 optim="adamw", betas=(0.9, 0.98))
+    opt = setup_e2e_optimizer(model, opts)
+    groups = opt.param_groups
+    assert len(groups) == 8                                      # run_video_retrieval.py:455 indexes exactly eight
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    grouped = [p for g in groups for p in g["params"]]
+    assert len(grouped) == len(trainable) and {id(p) for p in grouped} == {id(p) for p in trainable}
+    names = {id(p): n for n, p in model.named_parameters()}
+    # transformer: [top decay, top no-decay, rest decay, rest no-decay] with an empty prefix -> the two "top" groups are empty
+    assert not groups[0]["params"] and not groups[1]["params"]
+    assert all(names[id(p)].startswith("transformer.") for p in groups[2]["params"] + groups[3]["params"])
+    assert all(any(nd in names[id(p)] for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight")) for p in groups[3]["params"])
+    assert groups[3]["weight_decay"] == 0.0 and groups[2]["weight_decay"] == 1e-3
+    # cnn: the grid_encoder is the "top" group (cnn_lr_mul_prefix), res3-5 conv weights the rest; no biases in the CNN
+    assert [names[id(p)] for p in groups[4]["params"]] == ["cnn.grid_encoder.0.weight"] and not groups[5]["params"] and not groups[7]["params"]
+    assert len(groups[6]["params"]) == 3 * 13 + 3 and all(".res" in names[id(p)] for p in groups[6]["params"])
