@@ -4,6 +4,8 @@ same attribute names (``.cnn``, ``.transformer``, ``.retrieval``), so ``src/task
 use it unchanged; parameter names still contain "cnn" / "grid_encoder" / "transformer" so that
 ``setup_e2e_optimizer`` (src/optimization/utils.py:96-161) yields its 8 parameter groups.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -197,14 +199,18 @@ class ClipBert(nn.Module):
         ``cnn_buckets``: also exchange the tail of the CNN buffer (res5 + grid_encoder, 78 % of it) as soon as the
         res5 backward has enqueued its last weight gradient, leaving only res3/res4 (33 MB) for the final exchange.
         The collective is issued from the wgrad side stream, which is the stream those gradients are written on."""
-        self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None)
+        self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True)
 
         def hook(flat_grad):
+            if not self._dp["sync"]:
+                return
             self._dp["works"] += allreduce_flat([flat_grad], group, average, async_op=True)
             self._dp["tf_started"] = True
         self.transformer._grad_ready_hook = hook
 
         def cnn_hook(flat_grad, lo, side_stream):
+            if not self._dp["sync"]:
+                return
             if side_stream is not None:
                 with torch.cuda.stream(side_stream):
                     self._dp["works"] += allreduce_flat([flat_grad[lo:]], group, average, async_op=True)
@@ -213,12 +219,31 @@ class ClipBert(nn.Module):
             self._dp["cnn_lo"] = lo
         self.cnn._bucket_hook = cnn_hook if cnn_buckets else None
 
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: inside this context backward passes only accumulate into the flat buffers - no hook starts
+        an exchange and ``allreduce_grads()`` does nothing - so that the buffers are exchanged ONCE, by the last micro-step
+        run outside it. (The reference synchronizes on every micro-step, src/tasks/run_video_retrieval.py:425-432: with
+        ``gradient_accumulation_steps = k`` that is k times the traffic for the same result)"""
+        dp = getattr(self, "_dp", None)
+        if dp is None:
+            dp = self._dp_nosync = dict(sync=True)
+        prev, dp["sync"] = dp["sync"], False
+        try:
+            yield
+        finally:
+            dp["sync"] = prev
+
     def allreduce_grads(self, group=None, average=True, async_op=False):
         """Average the flat fp32 gradient buffers over the data-parallel group (NCCL) - the replacement of
         ``optimizer.synchronize()`` (src/tasks/run_video_retrieval.py:432)."""
         dp = getattr(self, "_dp", None)
         if dp is None:
+            if not getattr(self, "_dp_nosync", dict(sync=True))["sync"]:
+                return []
             return allreduce_flat(self.flat_grads(), group, average, async_op)
+        if not dp["sync"]:
+            return []
         works, dp["works"] = dp["works"], []
         tf_started, dp["tf_started"] = dp["tf_started"], False
         lo, dp["cnn_lo"] = dp["cnn_lo"], None

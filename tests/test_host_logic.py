@@ -1,5 +1,6 @@
 """CPU tests of the host-side logic around the kernels: flat parameter storage, state_dict contract,
 the world_size-2 gradient exchange (gloo), synthetic-workload and FLOP accounting helpers."""
+import contextlib
 import os
 import sys
 
@@ -120,6 +121,27 @@ def _dp_bucket_worker(rank, world, port, q):
             ClipBert.allreduce_grads(m)
             assert m._dp["works"] == [] and m._dp["cnn_lo"] is None and m._dp["tf_started"] is False
             out[(case, step)] = (float(tf._flat.grad[0]), float(tf._flat.grad[-1]), cnn._flat.grad.tolist())
+    # gradient accumulation: two micro-steps under no_sync() + one outside = ONE exchange of the accumulated buffers
+    for hooks in (True, False):
+        m = ClipBert.__new__(ClipBert)
+        tf = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.zeros(100)), _grad_ready_hook=None, _pending_backward=0)
+        cnn = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.zeros(64)), _bucket_hook=None, _pending_backward=0)
+        object.__setattr__(m, "transformer", tf)
+        object.__setattr__(m, "cnn", cnn)
+        if hooks:
+            ClipBert.enable_overlapped_allreduce(m, cnn_buckets=True)
+        n_exchanged = []
+        for micro in range(3):
+            ctx = ClipBert.no_sync(m) if micro < 2 else contextlib.nullcontext()
+            with ctx:
+                tf._flat.grad += float(rank + 1)                # this rank's micro-step gradient
+                cnn._flat.grad += float(10 * (rank + 1))
+                if hooks:
+                    tf._grad_ready_hook(tf._flat.grad)
+                    cnn._bucket_hook(cnn._flat.grad, 32, None)
+                ClipBert.allreduce_grads(m)
+            n_exchanged.append((float(tf._flat.grad[0]), float(cnn._flat.grad[0]), float(cnn._flat.grad[-1])))
+        out[("accum", hooks)] = n_exchanged
     q.put((rank, out))
     dist.destroy_process_group()
 
@@ -137,8 +159,15 @@ def test_bucketed_gradient_exchange_bookkeeping_world_size_2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for _, out in res:
-        for (case, step), (t0, t1, c) in out.items():
+    for rank, out in res:
+        for key, val in out.items():
+            if key[0] == "accum":
+                local = float(rank + 1)
+                assert val[0] == pytest.approx((local, 10 * local, 10 * local))            # micro-step 1: untouched local sums
+                assert val[1] == pytest.approx((2 * local, 20 * local, 20 * local))        # micro-step 2: still local
+                assert val[2] == pytest.approx((4.5, 45.0, 45.0))                          # last: mean over ranks of 3 micro-steps
+                continue
+            (case, step), (t0, t1, c) = key, val
             assert t0 == pytest.approx(1.5 * (step + 1)) and t1 == pytest.approx(1.5 * (step + 1)), (case, step)
             assert c == pytest.approx([1.5 * i for i in range(640)]), (case, step)
 
