@@ -397,7 +397,8 @@ def run_b200(args):
     # ---- instrumented pass: device time of the step's tcgen05 GEMM launches ----
     roof = None
     cpu = None
-    if True:      # every rank runs the instrumented pass (it contains the collectives); rank 0 reports
+    try:          # every rank runs the instrumented pass (it contains the collectives); rank 0 reports. Guarded: the primary
+                  # metric above must reach the JSON line even if the secondary figures cannot be produced
         # Device time of the tcgen05 GEMM launches of one step: the cb_gemm descriptors of one eager step are recorded (their
         # operand tensors stay referenced), then exactly those launches are replayed back to back from a CUDA graph on ONE
         # stream (no wgrad overlap, no PDL) and timed with CUDA events around the replay. Bracketing every launch with its own
@@ -457,6 +458,18 @@ def run_b200(args):
                          "timed (two-stream) step, so wgrad/dgrad overlap can push it towards or past 1",
                     whole_step_frac=round((algo_tf * world / (ms_dev / args.steps / 1e3)) / (peaks["tflops"] * world), 4),
                     hbm_bound_launch=hbm_roof)
+    except Exception as e:
+        if rank == 0:
+            print("[bench] roofline pass failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
+        roof = dict(bound="tensor", error="%s: %s" % (type(e).__name__, e), achieved=None, peak=peaks["tflops"], unit="TFLOP/s", frac=None,
+                    traffic=None, whole_step_frac=round((fl_clip * B * n_clips / 1e12 / (ms_dev / args.steps / 1e3)) / peaks["tflops"], 4))
+        ops._gemm_record = None
+        ops.set_pdl(args.pdl)
+        ops.overlap_wgrad = bool(args.overlap_wgrad)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
     # Ranks > 0 are done: nothing below is collective. They leave with os._exit after a last barrier - tearing the NCCL process
     # group down while CUDA graphs that captured its kernels are alive hung the run (seen at N = 2), and nothing needs cleanup.
     if world > 1:
@@ -465,11 +478,15 @@ def run_b200(args):
             sys.stdout.flush()
             sys.stderr.flush()
             os._exit(0)
-    if True:
-        cpu = None if (args.no_cpu or rank != 0) else cpu_baseline(args)
+    try:          # rank 0 at N = 1 only (the contract's cpu_baseline leg); never at the cost of the bench line
+        cpu = None if (args.no_cpu or rank != 0 or world > 1) else cpu_baseline(args)
+    except Exception as e:
+        print("[bench] cpu_baseline failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
+        cpu = None
     # ---- informational: the fused optimizer step that follows fwd+bwd in training (not part of the metric) ----
     opt_info = None
-    if args.optimizer:
+    if args.optimizer and world == 1:
+      try:
         named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
         if opt is None:
             opt = make_optimizer(model)
@@ -488,6 +505,9 @@ def run_b200(args):
         n_el = sum(p_.numel() for _, p_ in named)
         opt_info = dict(ms_per_step=round(opt_ms, 4), params=n_el, gbytes_per_s=round(n_el * 38.0 / opt_ms / 1e6, 1),
                         note="clip_grad_norm + AdamW + zero_grad + bf16 operand emission, 3 launches per flat buffer; 38 B per parameter")
+      except Exception as e:
+        print("[bench] fused optimizer timing failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
+        opt_info = None
 
     if rank == 0:
         out = dict(metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=round(value, 2), unit="clips/s", n_gpus=world,
