@@ -60,6 +60,14 @@ def load_peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback")
 
 
+def _device(local_rank):
+    return torch.device("cuda", local_rank)
+
+
+def _pin(t):
+    return t.pin_memory()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -163,7 +171,7 @@ def make_host_batch(args, rank):
     ids, mask = synth.synth_text(B * args.n_ex, args.txt_len, seed=42 + rank)
     g = torch.Generator().manual_seed(1000 + rank)
     labels = torch.randint(0, 2, (B * args.n_ex,), generator=g)
-    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    pin = _pin if torch.cuda.is_available() else (lambda t: t)
     return dict(visual_inputs=pin(u8), text_input_ids=pin(ids), text_input_mask=pin(mask), labels=pin(labels))
 
 
@@ -193,7 +201,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus)
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev = _device(local_rank)
     if world > 1:
         if args.nccl_ctas:      # experiment: fewer NCCL CTAs leave more SMs to the persistent GEMMs the exchange overlaps with
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
@@ -226,7 +234,7 @@ def run_b200(args):
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
     dbuf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_host = _pin(torch.zeros(1, dtype=torch.float32))
     loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def h2d():
@@ -316,6 +324,7 @@ def run_b200(args):
                 print("[bench] FusedAdamW could not be attached before the loop (%s: %s); weights are re-cast inside the step"
                       % (type(e).__name__, e), file=sys.stderr)
             opt = None
+    recast_attached = opt is not None
     # ---- optional whole-step CUDA graph (fwd + bwd of all clips): removes ~900 launch latencies ----
     if args.graph:
         try:
@@ -519,7 +528,7 @@ def run_b200(args):
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), pdl_late=bool(args.pdl_late), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
                                fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
-                               weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if (opt is not None and not args.recast_in_step) else "inside every step (no optimizer attached)",
+                               weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
                             h2d_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host.values())), d2h_bytes_per_step=4,

@@ -13,6 +13,11 @@ import torch
 import torch.nn.functional as F
 
 F32 = torch.float32
+IGNORE_DROPOUT = False      # emulated_ops(ignore_dropout=True): dropout arguments are accepted and treated as p = 0 (dry runs)
+
+
+def _no_dropout(p):
+    assert IGNORE_DROPOUT or not p, "emulator: dropout must be off"
 
 
 def _mat(t, rows, cols, ld):
@@ -67,7 +72,7 @@ def _out_rows(kw, m):
 def gemm(**kw):
     mode, m, n, k = kw.get("mode", 0), kw["m"], kw["n"], kw["k"]
     ntaps, tap_w, tap_sign = kw.get("ntaps", 1), kw.get("tap_w", 0), kw.get("tap_sign", 1)
-    assert not kw.get("dropout_p"), "emulator: dropout must be off"
+    _no_dropout(kw.get("dropout_p"))
     a, b, out = kw["a"], kw["b"], kw["out"]
     if mode == 1:                                       # WGRAD: out[m, t*N + n] += rowscale[m] * sum_p A[p, m] B[p + shift_t, n]
         A = _mat(a, k, m, kw["a_ld"]).to(F32)
@@ -142,7 +147,7 @@ def layernorm_fwd(x, gamma, beta, y, stats, eps):
 
 
 def layernorm_bwd(dy, x, stats, gamma, dx, dx_drop, dgamma, dbeta, dbias_drop, p, seed):
-    assert not p
+    _no_dropout(p)
     d, dg, db = _ln_bwd(dy.to(F32), x.to(F32), stats[:, 0], stats[:, 1], gamma)
     dx.copy_(d)
     if dx_drop is not None:
@@ -154,7 +159,7 @@ def layernorm_bwd(dy, x, stats, gamma, dx, dx_drop, dgamma, dbeta, dbias_drop, p
 
 
 def embed_text_fwd(ids, word, pos, typ, gamma, beta, out, stats, nseq, lt, l, eps, p, seed):
-    assert not p
+    _no_dropout(p)
     v = word[ids] + pos[:lt][None] + typ[0][None, None]
     o, mean, rstd = _ln_fwd(v.reshape(nseq * lt, -1), gamma, beta, eps)
     out.view(nseq, l, -1)[:, :lt].copy_(o.view(nseq, lt, -1))
@@ -162,7 +167,7 @@ def embed_text_fwd(ids, word, pos, typ, gamma, beta, out, stats, nseq, lt, l, ep
 
 
 def embed_text_bwd(dh, ids, word, pos, typ, gamma, stats, dword, dpos, dtyp, dgamma, dbeta, nseq, lt, l, p, seed):
-    assert not p
+    _no_dropout(p)
     h = word.shape[1]
     v = (word[ids] + pos[:lt][None] + typ[0][None, None]).reshape(nseq * lt, h)
     dy = dh.view(nseq, l, h)[:, :lt].reshape(nseq * lt, h).to(F32)
@@ -184,7 +189,7 @@ def _visual_pre(grid, seq2vid, n_ex, rowemb, colemb, typ, nseq, t, gh, gw):
 
 
 def embed_visual_fwd(grid, seq2vid, n_ex, rowemb, colemb, typ, gamma, beta, out, stats, nseq, t, gh, gw, lt, l, eps, p, seed):
-    assert not p
+    _no_dropout(p)
     v, _, _ = _visual_pre(grid, seq2vid, n_ex, rowemb, colemb, typ, nseq, t, gh, gw)
     o, mean, rstd = _ln_fwd(v, gamma, beta, eps)
     out.view(nseq, l, -1)[:, lt:].copy_(o.view(nseq, gh * gw, -1))
@@ -193,7 +198,7 @@ def embed_visual_fwd(grid, seq2vid, n_ex, rowemb, colemb, typ, gamma, beta, out,
 
 def embed_visual_bwd(dh, grid, seq2vid, vid_start, n_ex, rowemb, colemb, typ, gamma, stats, dv_tmp, dgrid, drow, dcol, dtyp,
                      dgamma, dbeta, nseq, nvid, t, gh, gw, lt, l, p, seed):
-    assert not p
+    _no_dropout(p)
     h = grid.shape[-1]
     lv = gh * gw
     v, vid, j = _visual_pre(grid, seq2vid, n_ex, rowemb, colemb, typ, nseq, t, gh, gw)
@@ -221,7 +226,7 @@ def _attention(qkv, text_mask, nseq, l, lt, heads):
 
 
 def attention_fwd(qkv, text_mask, ctx, lse, nseq, l, lt, heads, p, seed):
-    assert not p
+    _no_dropout(p)
     o, ls = _attention(qkv.double(), text_mask, nseq, l, lt, heads)
     ctx.copy_(o)
     if lse is not None:
@@ -229,7 +234,7 @@ def attention_fwd(qkv, text_mask, ctx, lse, nseq, l, lt, heads, p, seed):
 
 
 def attention_bwd(qkv, text_mask, ctx, dctx, lse, dqkv, nseq, l, lt, heads, p, seed):
-    assert not p
+    _no_dropout(p)
     x = qkv.to(F32).clone().requires_grad_(True)
     with torch.enable_grad():
         o, _ = _attention(x, text_mask, nseq, l, lt, heads)
@@ -242,7 +247,7 @@ def colsum(x, out, m, n, ld=None):
 
 
 def dropout(x, y, p, seed):
-    assert not p
+    _no_dropout(p)
     y.copy_(x)
 
 
@@ -353,16 +358,20 @@ _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_tex
 
 
 @contextlib.contextmanager
-def emulated_ops():
+def emulated_ops(ignore_dropout=False):
     """Swap the wrappers of clipbert_b200.ops (and the device checks of modeling.py / grid_feat.py) for the torch code above."""
     from clipbert_b200 import grid_feat, modeling, ops
     saved = {n: getattr(ops, n) for n in _NAMES}
     saved_overlap, saved_req, saved_req_cnn = ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda
     calls = {n: 0 for n in _NAMES}
+    global IGNORE_DROPOUT
+    saved_drop, IGNORE_DROPOUT = IGNORE_DROPOUT, bool(ignore_dropout)
 
     def counted(name, fn):
         def f(*a, **k):
             calls[name] += 1
+            if name == "gemm" and ops._gemm_record is not None:     # the recording hook of ops.gemm (bench.py's roofline pass)
+                ops._gemm_record.append(dict(k))
             return fn(*a, **k)
         return f
     try:
@@ -375,6 +384,7 @@ def emulated_ops():
         for n, f in saved.items():
             setattr(ops, n, f)
         ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda = saved_overlap, saved_req, saved_req_cnn
+        IGNORE_DROPOUT = saved_drop
 
 
 emulated_transformer_ops = emulated_ops
