@@ -102,3 +102,48 @@ def calls_per_step_expected(flags):
     # the per-clip loop runs the whole thing once per clip
     per_pass = 291
     return per_pass * (2 if "--clip_batching" in flags else 1)
+
+
+def _mg_worker(rank, world, port, flags, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import bench
+    from ops_emulator import emulated_ops
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    cpu = torch.device("cpu")
+    for name, val in (("Stream", _Stream), ("Event", _Event), ("CUDAGraph", _Graph), ("graph", _ctx), ("stream", _ctx),
+                      ("current_stream", lambda *a: _Stream()), ("synchronize", lambda *a: None), ("set_device", lambda *a: None),
+                      ("is_available", lambda: False)):
+        setattr(torch.cuda, name, val)
+    bench._device, bench._pin = (lambda r: cpu), (lambda t: t)
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, **kw: real_init("gloo")        # NCCL -> gloo, no device_id
+    sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1", "--batch", "1", "--n_clips", "2", "--n_frm", "1",
+                "--size", "64", "--txt_len", "12", "--overlap_wgrad", "0", "--graph", "0"] + flags
+    sys.stdout = open(os.path.join(outdir, "rank%d.out" % rank), "w")
+    sys.stderr = open(os.path.join(outdir, "rank%d.err" % rank), "w")
+    with emulated_ops(ignore_dropout=True):
+        bench.main()          # ends in os._exit(0) on every rank at world > 1
+
+
+@pytest.mark.parametrize("flags", [[], ["--cnn_buckets", "1", "--fused_loss", "1"]])
+def test_bench_control_flow_two_ranks_over_gloo(tmp_path, flags):
+    """The N > 1 flow of bench.py (overlapped exchange hooks through the real engines, collectives in the timed region, rank 0
+    reporting, every rank leaving through os._exit) with NCCL swapped for gloo, plus the mid-backward CNN bucket."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = 29500 + (os.getpid() + 733 + len(flags)) % 1000
+    procs = [ctx.Process(target=_mg_worker, args=(r, 2, port, flags, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0, (open(os.path.join(str(tmp_path), "rank0.err")).read()[-2000:], open(os.path.join(str(tmp_path), "rank1.err")).read()[-2000:])
+    out0 = open(os.path.join(str(tmp_path), "rank0.out")).read()
+    assert not open(os.path.join(str(tmp_path), "rank1.out")).read().strip()          # only rank 0 prints
+    d = json.loads([l for l in out0.splitlines() if l.startswith("{")][-1])
+    assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "dp2" and d["config"]["clips_per_step_per_gpu"] == 2
+    assert d["cpu_baseline"] is None and d["fused_optimizer"] is None
+    assert "error" not in d["roofline"] and d["config"]["cnn_buckets"] == ("--cnn_buckets" in flags)
