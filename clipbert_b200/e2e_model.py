@@ -77,7 +77,6 @@ class ClipBert(nn.Module):
                                     freeze_at=freeze_at)
         self.transformer = transformer_cls(config)
         self.retrieval = transformer_cls == ClipBertForVideoTextRetrieval
-        self._comm_stream = None
 
     def forward(self, batch):
         # used to make visual feature copies (repeat_tensor_rows is fused into the visual-embedding kernel)

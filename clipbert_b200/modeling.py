@@ -767,9 +767,6 @@ class ClipBertForPreTraining(_ClipBertHeadModel):
     def _num_head_outputs(self):
         return 2
 
-    def named_parameters(self, *a, **k):            # the tied decoder weight must not be listed twice
-        return super().named_parameters(*a, **k)
-
     @torch.no_grad()
     def _repack(self):
         super()._repack()
@@ -877,5 +874,6 @@ class ClipBertForPreTraining(_ClipBertHeadModel):
 
 
 def _gelu_bwd(dy, u, out):
-    """out = dy * gelu'(u) via the GEMM epilogue machinery is overkill for one [R,768] tensor: reuse cb_layernorm-free path."""
+    """out = dy * gelu'(u) for the MLM transform (BertPredictionHeadTransform, transformers.py:486-495): an elementwise kernel
+    on one [R, 768] tensor - the GEMM that follows reads it as an operand, so no epilogue can carry this product."""
     ops.gelu_bwd(dy, u, out)
