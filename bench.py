@@ -218,6 +218,7 @@ def run_b200(args):
     model = model.to(dev).train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
+    model.cnn.overlap_shortcut = bool(args.overlap_shortcut)
     if world > 1:
         model.enable_overlapped_allreduce(cnn_buckets=bool(args.cnn_buckets))
 
@@ -527,7 +528,7 @@ def run_b200(args):
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), pdl_late=bool(args.pdl_late), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
-                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               fused_loss=bool(args.fused_loss), overlap_shortcut=bool(args.overlap_shortcut), cnn_buckets=bool(args.cnn_buckets), sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -651,6 +652,7 @@ def main():
     ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
+    ap.add_argument("--overlap_shortcut", type=int, default=0, help="forward: the four projection shortcuts on the side stream beside conv1 -> conv2")
     ap.add_argument("--pdl_late", type=int, default=0, help="with --pdl 1: GEMM CTAs release their dependents at their last tile, not at entry")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
