@@ -419,7 +419,11 @@ int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
 int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
                      const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
                      cudaStream_t stream);
+int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
+                           int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream);
 int g_attention_force_general = 0;   // test knob: 1 = always use the general (any L) kernels
+int g_attention_flash = 0;           // 1 = forward of sequences longer than 64 tokens on the tensor-core online-softmax kernel
+                                     // (attention_tc.cu); off until it has been checked on a B200
 
 }  // namespace cb
 
@@ -428,6 +432,7 @@ using namespace cb;
 extern "C" {
 
 void cb_debug_attention_general(int on) { cb::g_attention_force_general = on; }
+void cb_debug_attention_flash(int on) { cb::g_attention_flash = on; }
 
 /* qkv: bf16 [nseq*L, 3*heads*64] (Q | K | V); text_mask: int64 [nseq, Lt]; ctx: bf16 [nseq*L, heads*64];
  * lse: fp32 [nseq, heads, L] (saved for the backward; may be NULL for inference). */
@@ -438,6 +443,8 @@ int cb_attention_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
   CB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0, "cb_attention_fwd: row pitches must be multiples of 8");
   if (l <= 64 && !g_attention_force_general)
     return attention_tc_fwd(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, static_cast<cudaStream_t>(stream));
+  if (l > 64 && g_attention_flash && !g_attention_force_general)
+    return attention_tc_fwd_flash(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, static_cast<cudaStream_t>(stream));
   static bool once = false;
   const int smem = 4 * TILE_FLOATS * sizeof(float);
   if (!once) {

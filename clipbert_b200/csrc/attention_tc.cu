@@ -208,6 +208,108 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
   tc_store_tile(Qs, ctx + row0 * ld_ctx + h * 64, ld_ctx, L);
 }
 
+// ------------------------------------------------------------------------------------------------ forward, any L
+// The same tensor-core forward for sequences longer than one tile (448 px frames: L = 69; paragraph-retrieval inference:
+// L = 512 + 9): one CTA = 64 query rows of one (sequence, head), looping over 64-key tiles with the online-softmax
+// recurrence (running row max m, running sum, accumulator rescaled by exp(m_old - m_new)). Mask, dropout stream
+// (index = ((b*H + h)*L + query)*L + key) and the saved log-sum-exp follow attn_fwd_kernel (attention.cu), so the general
+// backward kernels consume its output unchanged. At L = 521 the CUDA-core kernel spends 0.83 GFLOP per (sequence, layer)
+// on fp32 FMAs - more than the whole layer's tcgen05 GEMM time; this path puts those products on mma.sync.
+__global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                       const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
+                                                                       const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
+                                                                       int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
+                                                                       TcDrop dc) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t tc_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
+  __nv_bfloat16* Ks = Qs + TC_TILE;
+  __nv_bfloat16* Vs = Ks + TC_TILE;
+  float* madd = reinterpret_cast<float*>(Vs + TC_TILE);     // [64] additive key mask of the current key tile (-inf beyond L)
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = qb * 64;
+  const int64_t row0 = static_cast<int64_t>(b) * L;
+  tc_load_tile(Qs, q + (row0 + q0) * ld_qkv + h * 64, ld_qkv, L - q0);
+  const int r0 = warp * 16;
+  const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
+  float m0 = -INFINITY, m1 = -INFINITY, sum0 = 0.f, sum1 = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+  const int nkb = (L + 63) / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * 64;
+    __syncthreads();                     // the previous tile's K / V / mask have been consumed by every warp
+    tc_load_tile(Ks, k + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+    tc_load_tile(Vs, v + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+    if (threadIdx.x < 64) {
+      const int j = k0 + threadIdx.x;
+      float m = -INFINITY;
+      if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
+      madd[threadIdx.x] = m;
+    }
+    __syncthreads();
+    float s[8][4];
+    tc_mm_abt(s, Qs, Ks, r0, lane);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a0 = madd[j * 8 + cq], a1 = madd[j * 8 + cq + 1];
+      s[j][0] = s[j][0] * scale + a0; s[j][1] = s[j][1] * scale + a1;
+      s[j][2] = s[j][2] * scale + a0; s[j][3] = s[j][3] * scale + a1;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = quad_max(mx0);
+    mx1 = quad_max(mx1);
+    const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);       // finite: every key tile holds at least one key < L
+    const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);     // exp(-inf) = 0 on the first tile
+    float t0 = 0.f, t1 = 0.f;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p0 = __expf(s[j][0] - n0), p1 = __expf(s[j][1] - n0), p2 = __expf(s[j][2] - n1), p3 = __expf(s[j][3] - n1);
+      t0 += p0 + p1;
+      t1 += p2 + p3;
+      if (dc.thresh) {
+        const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + (q0 + rq)) * L + k0 + j * 8 + cq;
+        const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
+        p0 *= dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
+        p1 *= dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
+        p2 *= dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
+        p3 *= dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+      }
+      pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    t0 = quad_sum(t0);
+    t1 = quad_sum(t1);
+    sum0 = sum0 * c0 + t0;
+    sum1 = sum1 * c1 + t1;
+    m0 = n0;
+    m1 = n1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+    tc_mm_ab_reg(o, pf, Vs, lane);
+  }
+  const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] *= i0; o[j][1] *= i0; o[j][2] *= i1; o[j][3] *= i1; }
+  if (lse && (lane & 3) == 0) {
+    float* lrow = lse + (static_cast<int64_t>(b) * H + h) * L;
+    if (q0 + rq < L) lrow[q0 + rq] = m0 + __logf(sum0);
+    if (q0 + rq + 8 < L) lrow[q0 + rq + 8] = m1 + __logf(sum1);
+  }
+  __syncthreads();                       // everyone is done reading Qs: reuse it to stage the output
+  tc_acc_to_smem(o, Qs, r0, lane, 1.0f);
+  __syncthreads();
+  tc_store_tile(Qs, ctx + (row0 + q0) * ld_ctx + h * 64, ld_ctx, L - q0);
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                  const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
@@ -347,6 +449,23 @@ int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
                                                                        static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f,
                                                                        make_tc_drop(dropout_p, seed));
   return check_launch("cb_attention_fwd(tc)");
+}
+
+// called from cb_attention_fwd (attention.cu) for l > 64 when the tensor-core path for long sequences is enabled
+int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
+                           int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  const int smem = 3 * TC_TILE * 2 + 64 * 4;
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("attention_tc_fwd_flash smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    once = true;
+  }
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  const int hid = heads * 64;
+  launch_k(attn_tc_fwd_flash_kernel, dim3(ceil_div(l, 64), heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv,
+           text_mask, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f, make_tc_drop(dropout_p, seed));
+  return check_launch("cb_attention_fwd(tc, flash)");
 }
 
 int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,

@@ -98,6 +98,12 @@ def set_direct_store(on):
     L.lib().cb_debug_gemm_direct_store(int(bool(on)))
 
 
+def set_attention_flash(on):
+    """Forward attention of sequences longer than 64 tokens on the tensor-core online-softmax kernel (off by default until
+    verified on a B200; the CUDA-core kernel is the default for L > 64)."""
+    L.lib().cb_debug_attention_flash(int(bool(on)))
+
+
 def set_pdl_late(on):
     """Tuning hook (with set_pdl(1)): the GEMM kernel releases its dependents when a CTA starts its last tile instead of at entry."""
     L.lib().cb_debug_gemm_pdl_late(int(bool(on)))

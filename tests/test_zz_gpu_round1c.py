@@ -157,6 +157,48 @@ def test_fused_clip_lse_loss_kernel(cuda):
             assert abs(float(cb.clip_lse_loss(z.to(cuda), y.to(cuda))) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
 
 
+@pytest.mark.parametrize("dims", [(2, 69, 20), (2, 150, 100), (1, 521, 512), (3, 128, 64), (1, 65, 0)])
+def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
+    """The mma.sync online-softmax forward for L > 64 (attn_tc_fwd_flash_kernel; 448 px frames L = 69, paragraph retrieval
+    L = 521) against fp32 torch attention and against the CUDA-core kernel it replaces: context, saved log-sum-exp (the general
+    backward consumes it), and the same dropout stream. Off by default (ops.set_attention_flash) until this has passed."""
+    from clipbert_b200 import ops
+    from util import TOL_BF16_OP
+    nseq, L, lt = dims
+    heads = 12
+    g = torch.Generator().manual_seed(31)
+    qkv = (torch.randn(nseq * L, 3 * 768, generator=g)).to(cuda).to(torch.bfloat16)
+    mask = torch.ones(nseq, max(lt, 1), dtype=torch.int64, device=cuda)
+    if lt > 4:
+        mask[0, lt - 3:] = 0
+        mask[-1, lt // 2:] = 0
+    ref_mask = mask[:, :lt]
+    outs = {}
+    try:
+        for flash in (0, 1):
+            ops.set_attention_flash(flash)
+            for p, seed in ((0.0, 0), (0.1, 5)):
+                ctx = torch.zeros(nseq * L, 768, device=cuda, dtype=torch.bfloat16)
+                lse = torch.zeros(nseq, heads, L, device=cuda)
+                ops.attention_fwd(qkv, mask, ctx, lse, nseq, L, lt, heads, p, seed)
+                outs[(flash, p)] = (ctx, lse)
+    finally:
+        ops.set_attention_flash(0)
+    x = qkv.float().view(nseq, L, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    full = torch.cat([ref_mask, torch.ones(nseq, L - lt, dtype=torch.int64, device=cuda)], 1)
+    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - full[:, None, None, :].float()) * -10000.0
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nseq * L, 768)
+    ref_lse = torch.logsumexp(s, -1)
+    ctx, lse = outs[(1, 0.0)]
+    assert relerr(ctx, ref) < TOL_BF16_OP, relerr(ctx, ref)
+    assert float((lse - ref_lse).abs().max()) < 2e-2 and relerr(lse, outs[(0, 0.0)][1]) < 1e-3
+    assert relerr(ctx, outs[(0, 0.0)][0]) < 2 * TOL_BF16_OP
+    # same (seed, element) dropout stream as the general kernel: P is rounded to bf16 here and kept fp32 there
+    assert relerr(outs[(1, 0.1)][0], outs[(0, 0.1)][0]) < 3 * TOL_BF16_OP
+    assert relerr(outs[(1, 0.1)][1], outs[(0, 0.1)][1]) < 1e-3
+
+
 def test_forward_error_sits_at_the_bf16_noise_floor_of_the_reference_ops(cuda, weights):
     """How far may a correct bf16 implementation be from the fp32 reference? Run the ORACLE's own ops (plain torch: cuDNN /
     cuBLAS bf16 under autocast, fp32 LayerNorm / softmax - the mixed precision the reference trains in) on the same GPU and
