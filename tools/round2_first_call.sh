@@ -20,4 +20,5 @@ bash tools/gpu_ab.sh 10 \
   "direct:--direct_store 1"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/r02_launches.csv \
   python bench.py --steps 2 --warmup 1 --no_cpu 1 --optimizer 0 > gpurun_out/r02_ncu_bench.log 2>&1
+for f in 0 1; do timeout 300 python tools/bench_inference.py --flash $f > gpurun_out/r02_infer_flash$f.json 2> gpurun_out/r02_infer_flash$f.err; tail -1 gpurun_out/r02_infer_flash$f.json; done
 python tools/summarize_ncu.py gpurun_out/r02_launches.csv > gpurun_out/r02_launch_list_summary.txt 2>&1; head -30 gpurun_out/r02_launch_list_summary.txt
