@@ -249,3 +249,45 @@ def test_reference_setup_e2e_optimizer_runs_unchanged_on_this_model():
     # cnn: the grid_encoder is the "top" group (cnn_lr_mul_prefix), res3-5 conv weights the rest; no biases in the CNN
     assert [names[id(p)] for p in groups[4]["params"]] == ["cnn.grid_encoder.0.weight"] and not groups[5]["params"] and not groups[7]["params"]
     assert len(groups[6]["params"]) == 3 * 13 + 3 and all(".res" in names[id(p)] for p in groups[6]["params"])
+
+
+def test_online_softmax_recurrence_of_the_long_sequence_attention_kernel():
+    """The arithmetic of attn_tc_fwd_flash_kernel (csrc/attention_tc.cu) restated tile by tile in torch - 64-key tiles, running
+    row max / sum, accumulator rescaled by exp(m_old - m_new), probabilities rounded to bf16 before the P V product, -inf mask
+    beyond L, -10000 on masked text keys - against plain softmax attention. (The CUDA kernel itself is checked on a B200.)"""
+    g = torch.Generator().manual_seed(0)
+    for L, lt in ((69, 20), (150, 100), (521, 512), (65, 0)):
+        q, k, v = (torch.randn(L, 64, generator=g).bfloat16().float() for _ in range(3))
+        mask = torch.ones(lt, dtype=torch.int64)
+        if lt > 4:
+            mask[lt // 2:] = 0
+        add = torch.cat([(1.0 - mask.float()) * -10000.0, torch.zeros(L - lt)])
+        s_full = q @ k.t() * 0.125 + add[None]
+        ref = torch.softmax(s_full, -1) @ v
+        ref_lse = torch.logsumexp(s_full, -1)
+        out = torch.zeros(L, 64)
+        lse = torch.zeros(L)
+        for q0 in range(0, L, 64):
+            qt = torch.zeros(64, 64)
+            nq = min(64, L - q0)
+            qt[:nq] = q[q0:q0 + nq]
+            m = torch.full((64,), float("-inf"))
+            ssum = torch.zeros(64)
+            o = torch.zeros(64, 64)
+            for k0 in range(0, L, 64):
+                kt, vt = torch.zeros(64, 64), torch.zeros(64, 64)
+                nk = min(64, L - k0)
+                kt[:nk], vt[:nk] = k[k0:k0 + nk], v[k0:k0 + nk]
+                madd = torch.full((64,), float("-inf"))
+                madd[:nk] = add[k0:k0 + nk]
+                s = qt @ kt.t() * 0.125 + madd[None]
+                n = torch.maximum(m, s.max(-1).values)
+                c = torch.exp(m - n)
+                p = torch.exp(s - n[:, None])
+                ssum = ssum * c + p.sum(-1)
+                o = o * c[:, None] + p.bfloat16().float() @ vt
+                m = n
+            out[q0:q0 + nq] = (o / ssum[:, None])[:nq]
+            lse[q0:q0 + nq] = (m + torch.log(ssum))[:nq]
+        assert torch.isfinite(out).all()
+        assert float((out - ref).norm() / ref.norm()) < 4e-3 and float((lse - ref_lse).abs().max()) < 1e-4, (L, lt)
