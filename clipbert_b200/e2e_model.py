@@ -36,6 +36,16 @@ def allreduce_flat(grads, group=None, average=True, async_op=False):
     return works
 
 
+class _StreamWork:
+    """``Work.wait()`` for an exchange enqueued on a side stream: the caller's stream waits for its end."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class _ClipLseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels):
@@ -189,7 +199,49 @@ class ClipBert(nn.Module):
             if m._flat is not None and m._flat.grad is not None:
                 m._flat.grad.zero_()
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False):
+    # ---- NVLS exchange: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) -------------------------------
+    def _nvls_exchange(self, tensors):
+        """All-reduce slices of the symmetric-memory gradient buffers on the communication stream. Each slice: cross-rank
+        barrier (every rank has finished writing it - stream order on each rank), cb_nvls_allreduce_f32, barrier (every
+        rank's 1/world slice has been stored everywhere)."""
+        from . import ops
+        import torch.distributed._symmetric_memory as symm
+        dp = self._dp
+        group = dp["group"] if dp["group"] is not None else dist.group.WORLD
+        world = dist.get_world_size(group)
+        comm = dp.get("comm_stream")
+        if comm is None:
+            comm = dp["comm_stream"] = torch.cuda.Stream()
+        comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(comm):
+            for t in tensors:
+                key = t.untyped_storage().data_ptr()
+                hdl = dp["handles"].get(key)
+                if hdl is None:                      # first use (an eager warm-up step, never under graph capture): collective
+                    owner = next(m._flat.grad for m in (self.transformer, self.cnn)
+                                 if m._flat is not None and m._flat.grad.untyped_storage().data_ptr() == key)
+                    hdl = dp["handles"][key] = symm.rendezvous(owner, group)
+                    if not hdl.multicast_ptr:
+                        raise RuntimeError("NVLS exchange: this system exposes no multicast mapping (use exchange='nccl')")
+                hdl.barrier(channel=0)
+                ops.nvls_allreduce(hdl.multicast_ptr + 4 * t.storage_offset(), t.numel(), hdl.rank, world,
+                                   1.0 / world if dp["average"] else 1.0, dp["max_ctas"])
+                hdl.barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(comm)
+        return [_StreamWork(ev)]
+
+    def _exchange(self, tensors):
+        dp = self._dp
+        if not tensors:
+            return []
+        if dp.get("exchange") == "nvls":
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(dp["group"]) == 1:
+                return []
+            return self._nvls_exchange(tensors)
+        return allreduce_flat(tensors, dp["group"], dp["average"], async_op=True)
+
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=24):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
@@ -198,12 +250,23 @@ class ClipBert(nn.Module):
         ``cnn_buckets``: also exchange the tail of the CNN buffer (res5 + grid_encoder, 78 % of it) as soon as the
         res5 backward has enqueued its last weight gradient, leaving only res3/res4 (33 MB) for the final exchange.
         The collective is issued from the wgrad side stream, which is the stream those gradients are written on."""
-        self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True)
+        assert exchange in ("nccl", "nvls")
+        self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True, exchange=exchange,
+                        max_ctas=int(max_ctas), handles={})
+        if exchange == "nvls":
+            # ``exchange="nvls"``: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) instead of NCCL. The flat
+            # gradient buffers must then live in symmetric memory, so call this BEFORE the first forward (buffers that already
+            # exist are dropped and rebuilt). Experimental until it has run on a multi-GPU box.
+            import torch.distributed._symmetric_memory as symm
+            from .params import FlatGroup
+            FlatGroup.grad_factory = staticmethod(lambda n, dev: symm.empty(n, dtype=torch.float32, device=dev).zero_())
+            for m in (self.transformer, self.cnn):
+                m._flat = None
 
         def hook(flat_grad):
             if not self._dp["sync"]:
                 return
-            self._dp["works"] += allreduce_flat([flat_grad], group, average, async_op=True)
+            self._dp["works"] += self._exchange([flat_grad])
             self._dp["tf_started"] = True
         self.transformer._grad_ready_hook = hook
 
@@ -212,9 +275,9 @@ class ClipBert(nn.Module):
                 return
             if side_stream is not None:
                 with torch.cuda.stream(side_stream):
-                    self._dp["works"] += allreduce_flat([flat_grad[lo:]], group, average, async_op=True)
+                    self._dp["works"] += self._exchange([flat_grad[lo:]])
             else:
-                self._dp["works"] += allreduce_flat([flat_grad[lo:]], group, average, async_op=True)
+                self._dp["works"] += self._exchange([flat_grad[lo:]])
             self._dp["cnn_lo"] = lo
         self.cnn._bucket_hook = cnn_hook if cnn_buckets else None
 
@@ -255,7 +318,7 @@ class ClipBert(nn.Module):
             g = cf.grad if lo is None else cf.grad[:lo]                    # the tail [lo:) is already in flight (cnn_buckets)
             if g.numel():
                 rest.append(g)
-        works += allreduce_flat(rest, dp["group"], dp["average"], async_op=True)
+        works += self._exchange(rest)
         for w in works:
             w.wait()
         return []

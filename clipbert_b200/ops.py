@@ -28,6 +28,7 @@ _SIGS = {
     "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
     "cb_cast_scale_segments": [_vp, _vp, _vp, _i, _vp, _vp],
+    "cb_nvls_allreduce_f32": [_vp, _i64, _i, _i, _f, _i, _vp],
     "cb_clip_lse_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_attention_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _u64, _vp],
@@ -286,6 +287,11 @@ def embed_visual_bwd(dh, grid, seq2vid, vid_start, n_ex, rowemb, colemb, type0, 
     _call("cb_embed_visual_bwd", _p(dh), _p(grid), _p(seq2vid), _p(vid_start), n_ex, _p(rowemb), _p(colemb), _p(type0),
           _p(gamma), _p(stats), _p(dv_tmp), _p(dgrid), _p(drow), _p(dcol), _p(dtype0), _p(dgamma), _p(dbeta), nseq, nvid, t,
           gh, gw, lt, l, rowemb.shape[1], p, seed, _s())
+
+
+def nvls_allreduce(multicast_ptr, n, rank, world, scale, max_ctas=0):
+    """All-reduce n fp32 elements at a multicast (symmetric-memory) address through the NVSwitch; see cb_nvls_allreduce_f32."""
+    _call("cb_nvls_allreduce_f32", multicast_ptr, n, rank, world, scale, max_ctas, _s())
 
 
 def clip_lse_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, grad_scale=1.0):

@@ -21,6 +21,10 @@ def _round_up(n, a=ALIGN):
 
 
 class FlatGroup:
+    # Optional allocator of the gradient buffer, ``f(numel, device) -> zero-filled fp32 tensor``: the NVLS exchange
+    # (ClipBert.enable_overlapped_allreduce(exchange="nvls")) needs it in symmetric memory. None = torch.zeros.
+    grad_factory = None
+
     def __init__(self, device):
         self.device = device
         self.entries = []      # dict(name, param, offset, numel, slot, kind, meta)
@@ -55,7 +59,8 @@ class FlatGroup:
     def materialize(self):
         dev = self.device
         self.master = torch.zeros(self.total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        make = FlatGroup.grad_factory
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev) if make is None else make(self.total, dev)
         self.packed = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
         for e in self.entries:
             p = e["param"]

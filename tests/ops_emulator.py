@@ -343,6 +343,20 @@ def clip_lse_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, grad_scale
     loss.copy_(val.detach().reshape(1))
 
 
+NVLS_BUFFERS = {}       # data_ptr of a "symmetric" buffer -> tensor (registered by the test's stand-in for rendezvous())
+
+
+def nvls_allreduce(multicast_ptr, n, rank, world, scale, max_ctas=0):
+    """cb_nvls_allreduce_f32 over torch.distributed (gloo): the element range [ptr, ptr + n) of a registered buffer."""
+    import torch.distributed as dist
+    base, buf = next((b, t) for b, t in NVLS_BUFFERS.items() if b <= multicast_ptr < b + 4 * t.numel())
+    off = (multicast_ptr - base) // 4
+    assert (multicast_ptr - base) % 16 == 0 and n % 4 == 0 and off + n <= buf.numel()
+    view = buf[off: off + n]
+    dist.all_reduce(view, op=dist.ReduceOp.SUM)
+    view.mul_(scale)
+
+
 def cast_scale_segments(master, packed, segments, scales):
     for off, numel, row_len, soff in segments.tolist():
         v = master[off: off + numel].view(-1, row_len)
@@ -354,7 +368,7 @@ def cast_scale_segments(master, packed, segments, scales):
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
-          "cast_scale_segments", "clip_lse_loss")
+          "cast_scale_segments", "clip_lse_loss", "nvls_allreduce")
 
 
 @contextlib.contextmanager

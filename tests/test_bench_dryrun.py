@@ -120,6 +120,20 @@ def _mg_worker(rank, world, port, flags, outdir):
     bench._device, bench._pin = (lambda r: cpu), (lambda t: t)
     real_init = dist.init_process_group
     dist.init_process_group = lambda backend=None, **kw: real_init("gloo")        # NCCL -> gloo, no device_id
+    # symmetric memory stand-ins for --exchange nvls: plain tensors, a handle whose "multicast pointer" is the local address,
+    # barriers over gloo; ops_emulator.nvls_allreduce resolves the address back to the registered tensor
+    import torch.distributed._symmetric_memory as symm
+    import ops_emulator
+
+    class _Handle:
+        def __init__(self, t):
+            self.multicast_ptr, self.rank, self.world_size = t.data_ptr(), rank, world
+            ops_emulator.NVLS_BUFFERS[t.data_ptr()] = t
+
+        def barrier(self, channel=0, timeout_ms=0):
+            dist.barrier()
+    symm.empty = lambda *size, dtype=None, device=None: torch.zeros(*size, dtype=dtype)
+    symm.rendezvous = lambda t, group: _Handle(t)
     sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1", "--batch", "1", "--n_clips", "2", "--n_frm", "1",
                 "--size", "64", "--txt_len", "12", "--overlap_wgrad", "0", "--graph", "0"] + flags
     sys.stdout = open(os.path.join(outdir, "rank%d.out" % rank), "w")
@@ -128,7 +142,7 @@ def _mg_worker(rank, world, port, flags, outdir):
         bench.main()          # ends in os._exit(0) on every rank at world > 1
 
 
-@pytest.mark.parametrize("flags", [[], ["--cnn_buckets", "1", "--fused_loss", "1"]])
+@pytest.mark.parametrize("flags", [[], ["--cnn_buckets", "1", "--fused_loss", "1"], ["--exchange", "nvls", "--cnn_buckets", "1"]])
 def test_bench_control_flow_two_ranks_over_gloo(tmp_path, flags):
     """The N > 1 flow of bench.py (overlapped exchange hooks through the real engines, collectives in the timed region, rank 0
     reporting, every rank leaving through os._exit) with NCCL swapped for gloo, plus the mid-backward CNN bucket."""
@@ -147,3 +161,4 @@ def test_bench_control_flow_two_ranks_over_gloo(tmp_path, flags):
     assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "dp2" and d["config"]["clips_per_step_per_gpu"] == 2
     assert d["cpu_baseline"] is None and d["fused_optimizer"] is None
     assert "error" not in d["roofline"] and d["config"]["cnn_buckets"] == ("--cnn_buckets" in flags)
+    assert d["config"]["exchange"] == ("nvls" if "nvls" in flags else "nccl")

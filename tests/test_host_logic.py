@@ -291,3 +291,89 @@ def test_online_softmax_recurrence_of_the_long_sequence_attention_kernel():
             lse[q0:q0 + nq] = (m + torch.log(ssum))[:nq]
         assert torch.isfinite(out).all()
         assert float((out - ref).norm() / ref.norm()) < 4e-3 and float((lse - ref_lse).abs().max()) < 1e-4, (L, lt)
+
+
+def _nvls_worker(rank, world, port, q):
+    """The NVLS exchange path of ClipBert (symmetric-memory handles, slice offsets into the multicast mapping, communication
+    stream, barriers) with the CUDA-only pieces replaced: symmetric memory by plain tensors, cb_nvls_allreduce_f32 by its
+    gloo restatement (tests/ops_emulator.py), streams / events by inert objects."""
+    import contextlib as cl
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed._symmetric_memory as symm
+    import ops_emulator
+    from clipbert_b200 import ops
+    from clipbert_b200.e2e_model import ClipBert
+    from clipbert_b200.params import FlatGroup
+
+    class _S:
+        def wait_stream(self, s):
+            pass
+
+        def wait_event(self, e):
+            pass
+
+    class _E:
+        def record(self, s=None):
+            pass
+
+    for name, val in (("Stream", _S), ("Event", _E), ("current_stream", lambda *a: _S()), ("stream", lambda s: cl.nullcontext())):
+        setattr(torch.cuda, name, val)
+    barriers = []
+
+    class _Handle:
+        def __init__(self, t):
+            self.multicast_ptr, self.rank, self.world_size = t.data_ptr(), rank, world
+            ops_emulator.NVLS_BUFFERS[t.data_ptr()] = t
+
+        def barrier(self, channel=0, timeout_ms=0):
+            barriers.append(channel)
+            dist.barrier()
+    symm.empty = lambda *size, dtype=None, device=None: torch.empty(*size, dtype=dtype)
+    symm.rendezvous = lambda t, group: _Handle(t)
+    ops.nvls_allreduce = ops_emulator.nvls_allreduce
+    m = ClipBert.__new__(ClipBert)
+    tf = types.SimpleNamespace(_flat=None, _grad_ready_hook=None, _pending_backward=0)
+    cnn = types.SimpleNamespace(_flat=None, _bucket_hook=None, _pending_backward=0)
+    object.__setattr__(m, "transformer", tf)
+    object.__setattr__(m, "cnn", cnn)
+    ClipBert.enable_overlapped_allreduce(m, cnn_buckets=True, exchange="nvls", max_ctas=8)
+    # the gradient buffers now come from the symmetric allocator
+    tf._flat = types.SimpleNamespace(grad=FlatGroup.grad_factory(1000, "cpu"))
+    cnn._flat = types.SimpleNamespace(grad=FlatGroup.grad_factory(640, "cpu"))
+    assert float(tf._flat.grad.abs().sum()) == 0.0                 # zero-filled
+    out = []
+    for step in range(2):
+        tf._flat.grad.fill_(float(rank + 1) * (step + 1))
+        tf._grad_ready_hook(tf._flat.grad)
+        cnn._flat.grad.zero_()
+        cnn._flat.grad[256:] = torch.arange(256.0, 640.0) * (rank + 1)
+        cnn._bucket_hook(cnn._flat.grad, 256, None)
+        cnn._flat.grad[:256] = torch.arange(256.0) * (rank + 1)
+        ClipBert.allreduce_grads(m)
+        out.append((float(tf._flat.grad[0]), float(tf._flat.grad[-1]), cnn._flat.grad.tolist()))
+    FlatGroup.grad_factory = None
+    q.put((rank, out, len(barriers), len(m._dp["handles"])))
+    dist.destroy_process_group()
+
+
+def test_nvls_exchange_plumbing_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 613) % 1000
+    procs = [ctx.Process(target=_nvls_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out, n_barriers, n_handles in res:
+        assert n_handles == 2 and n_barriers == 2 * 3 * 2          # one rendezvous per buffer; barrier before + after each of 3 slices, 2 steps
+        for step, (t0, t1, c) in enumerate(out):
+            assert t0 == pytest.approx(1.5 * (step + 1)) and t1 == pytest.approx(1.5 * (step + 1))
+            assert c == pytest.approx([1.5 * i for i in range(640)])

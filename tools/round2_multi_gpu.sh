@@ -14,3 +14,6 @@ run buckets "--cnn_buckets 1"
 run ctas16 "--nccl_ctas 16 --sm_limit 132"
 run ctas8 "--nccl_ctas 8 --sm_limit 140"
 run buckets_ctas16 "--cnn_buckets 1 --nccl_ctas 16 --sm_limit 132"
+run nvls "--exchange nvls"
+run nvls_buckets "--exchange nvls --cnn_buckets 1"
+run nvls_ctas8 "--exchange nvls --nvls_ctas 8 --sm_limit 140 --cnn_buckets 1"
