@@ -142,7 +142,7 @@ def _mg_worker(rank, world, port, flags, outdir):
         bench.main()          # ends in os._exit(0) on every rank at world > 1
 
 
-@pytest.mark.parametrize("flags", [[], ["--cnn_buckets", "1", "--fused_loss", "1"], ["--exchange", "nvls", "--cnn_buckets", "1"]])
+@pytest.mark.parametrize("flags", [[], ["--exchange", "nvls", "--cnn_buckets", "1", "--fused_loss", "1"]])
 def test_bench_control_flow_two_ranks_over_gloo(tmp_path, flags):
     """The N > 1 flow of bench.py (overlapped exchange hooks through the real engines, collectives in the timed region, rank 0
     reporting, every rank leaving through os._exit) with NCCL swapped for gloo, plus the mid-backward CNN bucket."""
