@@ -650,7 +650,7 @@ def main():
     ap.add_argument("--fused_loss", type=int, default=0, help="1: clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss) instead of ~45 ATen launches (off until its GPU test has run)")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, or this library's NVLS all-reduce (csrc/nvls.cu; experimental until run on a multi-GPU box)")
-    ap.add_argument("--nvls_ctas", type=int, default=24, help="CTAs of the NVLS all-reduce kernel")
+    ap.add_argument("--nvls_ctas", type=int, default=64, help="CTAs of the NVLS all-reduce kernel")
     ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")

@@ -15,20 +15,43 @@
 
 namespace cb {
 
-__global__ void __launch_bounds__(256) nvls_allreduce_f32_kernel(float* __restrict__ mc, int64_t v4_begin, int64_t v4_end, float scale) {
+// 128-thread CTAs with ~30 registers per thread: small enough to share an SM with one of this library's persistent GEMM CTAs
+// (608 threads x 96 registers), so the exchange pins no SM of its own. Four independent 16-byte multicast loads are in flight
+// per thread before the first dependent store (the loads cross the NVSwitch: ~2-3 us each).
+constexpr int NVLS_THREADS = 128;
+constexpr int NVLS_UNROLL = 4;
+
+__device__ __forceinline__ float4 mc_ld_reduce(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(NVLS_THREADS) nvls_allreduce_f32_kernel(float* __restrict__ mc, int64_t v4_begin, int64_t v4_end, float scale) {
   pdl_wait();
   pdl_trigger();
-  for (int64_t i = v4_begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < v4_end;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float* p = mc + i * 4;
-    float4 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p)
-                 : "memory");
-    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * NVLS_THREADS;
+  for (int64_t i0 = v4_begin + static_cast<int64_t>(blockIdx.x) * NVLS_THREADS + threadIdx.x; i0 < v4_end; i0 += stride * NVLS_UNROLL) {
+    float4 v[NVLS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NVLS_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < v4_end) v[u] = mc_ld_reduce(mc + i * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < NVLS_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < v4_end) {
+        v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
+        mc_st(mc + i * 4, v[u]);
+      }
+    }
   }
 }
 
@@ -46,9 +69,9 @@ extern "C" int cb_nvls_allreduce_f32(void* multicast_ptr, int64_t n, int rank, i
   const int64_t begin = rank * per < v4 ? rank * per : v4;
   const int64_t end = begin + per < v4 ? begin + per : v4;
   if (end <= begin) return CB_OK;                      // nothing in this rank's slice (tiny buffers)
-  int grid = ceil_div(end - begin, 256);
-  const int cap = max_ctas > 0 ? max_ctas : 32;
+  int grid = ceil_div(end - begin, static_cast<int64_t>(NVLS_THREADS) * NVLS_UNROLL);
+  const int cap = max_ctas > 0 ? max_ctas : 64;
   if (grid > cap) grid = cap;
-  launch_k(nvls_allreduce_f32_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<float*>(multicast_ptr), begin, end, scale);
+  launch_k(nvls_allreduce_f32_kernel, grid, NVLS_THREADS, 0, static_cast<cudaStream_t>(stream), static_cast<float*>(multicast_ptr), begin, end, scale);
   return check_launch("cb_nvls_allreduce_f32");
 }

@@ -241,7 +241,7 @@ class ClipBert(nn.Module):
             return self._nvls_exchange(tensors)
         return allreduce_flat(tensors, dp["group"], dp["average"], async_op=True)
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=24):
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges

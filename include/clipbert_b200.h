@@ -256,7 +256,7 @@ int cb_clip_lse_loss(const float* logits, const int64_t* labels, float* loss, fl
  * (src/tasks/run_video_retrieval.py:299-301,432) for a flat fp32 buffer that every rank has mapped at the same MULTICAST
  * address (symmetric memory): rank r reduces the r-th 1/world slice in the switch (multimem.ld_reduce.add), scales it
  * (1/world = average) and stores it into every rank's copy (multimem.st). n: elements (multiple of 4); max_ctas: CTAs this
- * launch may occupy (0 = 32). The caller places a cross-rank barrier before (all gradients written) and after (all slices stored).
+ * launch may use (0 = 64; 128 threads each, small enough to share an SM with a GEMM CTA). The caller places a cross-rank barrier before (all gradients written) and after (all slices stored).
  * ------------------------------------------------------------------------------------------ */
 int cb_nvls_allreduce_f32(void* multicast_ptr, int64_t n, int rank, int world, float scale, int max_ctas, void* stream);
 
