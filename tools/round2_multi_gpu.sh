@@ -17,3 +17,6 @@ run buckets_ctas16 "--cnn_buckets 1 --nccl_ctas 16 --sm_limit 132"
 run nvls "--exchange nvls"
 run nvls_buckets "--exchange nvls --cnn_buckets 1"
 run nvls_ctas8 "--exchange nvls --nvls_ctas 8 --sm_limit 140 --cnn_buckets 1"
+# stand-alone correctness + bandwidth of the NVLS kernel against NCCL (run FIRST if the nvls lines above fail)
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) \
+  tools/test_nvls.py > gpurun_out/mg_${N}_nvls_probe.json 2> gpurun_out/mg_${N}_nvls_probe.err; echo "nvls probe rc=$?"; tail -1 gpurun_out/mg_${N}_nvls_probe.json
