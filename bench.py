@@ -500,18 +500,18 @@ def run_b200(args):
         named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
         if opt is None:
             opt = make_optimizer(model)
-        for _ in range(3):
+        for _ in range(min(3, args.opt_steps)):
             opt.clip_grad_norm(1.0)
             opt.step(zero_grad=True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
+        for _ in range(args.opt_steps):
             opt.clip_grad_norm(1.0)
             opt.step(zero_grad=True)
         e1.record()
         torch.cuda.synchronize()
-        opt_ms = e0.elapsed_time(e1) / 10
+        opt_ms = e0.elapsed_time(e1) / args.opt_steps
         n_el = sum(p_.numel() for _, p_ in named)
         opt_info = dict(ms_per_step=round(opt_ms, 4), params=n_el, gbytes_per_s=round(n_el * 38.0 / opt_ms / 1e6, 1),
                         note="clip_grad_norm + AdamW + zero_grad + bf16 operand emission, 3 launches per flat buffer; 38 B per parameter")
@@ -658,6 +658,7 @@ def main():
     ap.add_argument("--pdl_late", type=int, default=0, help="with --pdl 1: GEMM CTAs release their dependents at their last tile, not at entry")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
+    ap.add_argument("--opt_steps", type=int, default=10, help="timed iterations of the informational fused-optimizer leg")
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

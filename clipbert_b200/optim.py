@@ -33,6 +33,39 @@ def _fn(name, argtypes):
     return f
 
 
+_cfuncs = {}
+
+
+def _cfn(name):
+    import ctypes
+    f = _cfuncs.get(name)
+    if f is None:
+        vp, i, i64, fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+        sigs = {"cb_sumsq": [vp, i64, vp, i, vp, vp], "cb_adamw_step": [vp, vp, vp, vp, vp, vp, i, vp, vp, vp, fl, i, vp]}
+        f = _cfuncs[name] = _fn(name, sigs[name])
+    return f
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def sumsq(x, chunks, nchunks, out):
+    """cb_sumsq: out[0] += sum of x^2 over the chunk table's elements (include/clipbert_b200.h)."""
+    L.check(_cfn("cb_sumsq")(_p(x), x.numel(), _p(chunks), nchunks, _p(out), torch.cuda.current_stream().cuda_stream), "cb_sumsq")
+
+
+def adamw_step(master, grad, exp_avg, exp_avg_sq, packed, chunks, nchunks, hyper, scales, grad_sumsq, max_norm, zero_grad):
+    """cb_adamw_step: clip + AdamW + zero_grad + bf16 operand emission on every element named by the chunk table."""
+    L.check(_cfn("cb_adamw_step")(_p(master), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(packed), _p(chunks), nchunks, _p(hyper), _p(scales),
+                                  _p(grad_sumsq), float(max_norm), int(bool(zero_grad)), torch.cuda.current_stream().cuda_stream),
+            "cb_adamw_step")
+
+
+def _require_cuda(dev):
+    assert dev.type == "cuda", "FusedAdamW runs on CUDA only (no CPU fallback)"
+
+
 class FusedAdamW(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True, model=None):
         if lr < 0.0:
@@ -59,7 +92,7 @@ class FusedAdamW(Optimizer):
     def _build_plan(self):
         import ctypes
         dev = next(self.model.parameters()).device
-        assert dev.type == "cuda", "FusedAdamW runs on CUDA only (no CPU fallback)"
+        _require_cuda(dev)
         group_of = {}
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
@@ -97,12 +130,11 @@ class FusedAdamW(Optimizer):
                                exp_avg=m_buf, exp_avg_sq=v_buf, scales=mod.optimizer_scales(), params=[p for p, _ in views]))
             mod._optimizer_emits_packed = True
         ng = len(self.param_groups)
-        self._hyper_host = torch.zeros(ng, 8, dtype=torch.float32).pin_memory()
+        self._hyper_host = torch.zeros(ng, 8, dtype=torch.float32)
+        if dev.type == "cuda":
+            self._hyper_host = self._hyper_host.pin_memory()
         self._hyper_dev = torch.zeros(ng, 8, dtype=torch.float32, device=dev)
         self._gsq = torch.zeros(1, dtype=torch.float32, device=dev)
-        vp, i, i64, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
-        self._c_sumsq = _fn("cb_sumsq", [vp, i64, vp, i, vp, vp])
-        self._c_step = _fn("cb_adamw_step", [vp, vp, vp, vp, vp, vp, i, vp, vp, vp, f, i, vp])
         self._plan = halves
         # per-group step count (every parameter of a group steps together); restored from a loaded state_dict
         self._group_steps = [max([int(self.state[p].get("step", 0)) for p in g["params"] if p in self.state] or [0])
@@ -121,11 +153,9 @@ class FusedAdamW(Optimizer):
         scaled by max_norm / (norm + 1e-6) when that is < 1 (torch.nn.utils.clip_grad_norm_) - is folded into the next
         ``step()``; the .grad buffers are left unscaled (they are zeroed by that step)."""
         plan = self._ensure_plan()
-        st = torch.cuda.current_stream().cuda_stream
         self._gsq.zero_()
         for h in plan:
-            g = h["flat"].grad
-            L.check(self._c_sumsq(g.data_ptr(), g.numel(), h["chunks"].data_ptr(), h["nchunks"], self._gsq.data_ptr(), st), "cb_sumsq")
+            sumsq(h["flat"].grad, h["chunks"], h["nchunks"], self._gsq)
         self._pending_max_norm = float(max_norm)
         self.last_grad_norm = self._gsq.sqrt()
         return self.last_grad_norm
@@ -143,16 +173,12 @@ class FusedAdamW(Optimizer):
                 step_size = step_size * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
             self._hyper_host[gi] = torch.tensor([g["lr"], step_size, g["weight_decay"], b1, b2, g["eps"], 0.0, 0.0])
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
-        st = torch.cuda.current_stream().cuda_stream
         clip = self._pending_max_norm > 0
         for h in plan:
             f = h["flat"]
             f.attach_grads()
-            sc = h["scales"]
-            L.check(self._c_step(f.master.data_ptr(), f.grad.data_ptr(), h["exp_avg"].data_ptr(), h["exp_avg_sq"].data_ptr(),
-                                 f.packed.data_ptr(), h["chunks"].data_ptr(), h["nchunks"], self._hyper_dev.data_ptr(),
-                                 None if sc is None else sc.data_ptr(), self._gsq.data_ptr() if clip else None,
-                                 self._pending_max_norm if clip else -1.0, int(bool(zero_grad)), st), "cb_adamw_step")
+            adamw_step(f.master, f.grad, h["exp_avg"], h["exp_avg_sq"], f.packed, h["chunks"], h["nchunks"], self._hyper_dev, h["scales"],
+                       self._gsq if clip else None, self._pending_max_norm if clip else -1.0, zero_grad)
             for p in h["params"]:
                 self.state[p]["step"] += 1
             h["mod"].packed_written_by_optimizer()

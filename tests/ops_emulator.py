@@ -365,6 +365,41 @@ def cast_scale_segments(master, packed, segments, scales):
         packed[off: off + numel].copy_(v.reshape(-1))
 
 
+# ---------------------------------------------------------------------------------------------------
+# fused optimizer step (clipbert_b200/optim.py calls these with tensors)
+# ---------------------------------------------------------------------------------------------------
+def opt_sumsq(x, chunks, nchunks, out):
+    acc = torch.zeros((), dtype=torch.float64)
+    for off, n, *_ in chunks[:nchunks].tolist():
+        acc += (x[off: off + n].double() ** 2).sum()
+    out[0] += acc.float()
+
+
+def opt_adamw_step(master, grad, exp_avg, exp_avg_sq, packed, chunks, nchunks, hyper, scales, grad_sumsq, max_norm, zero_grad):
+    """cb_adamw_step (csrc/optim.cu): AdamW of src/optimization/adamw.py:40-103 per chunk-table row, clip coefficient from the
+    total gradient norm, optional gradient zeroing and bf16 operand emission (FrozenBN row scale folded in)."""
+    coef = 1.0
+    if grad_sumsq is not None and max_norm > 0:
+        coef = min(1.0, max_norm / (float(grad_sumsq.sqrt()) + 1e-6))
+    for off, n, grp, row_len, soff, flags, elem0, _ in chunks[:nchunks].tolist():
+        lr, step_size, wd, b1, b2, eps = (float(x) for x in hyper[grp][:6])
+        sl = slice(off, off + n)
+        g = grad[sl] * coef
+        exp_avg[sl] = exp_avg[sl] * b1 + (1.0 - b1) * g
+        exp_avg_sq[sl] = exp_avg_sq[sl] * b2 + (1.0 - b2) * g * g
+        p = master[sl] - step_size * (exp_avg[sl] / (exp_avg_sq[sl].sqrt() + eps))
+        if wd > 0:
+            p = p - lr * wd * p
+        master[sl] = p
+        if zero_grad:
+            grad[sl] = 0
+        if (flags & 1) and packed is not None:
+            if soff >= 0:
+                rows = (elem0 + torch.arange(n)) // row_len
+                p = p * scales[soff + rows]
+            packed[sl] = p.to(packed.dtype)
+
+
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
@@ -374,8 +409,9 @@ _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_tex
 @contextlib.contextmanager
 def emulated_ops(ignore_dropout=False):
     """Swap the wrappers of clipbert_b200.ops (and the device checks of modeling.py / grid_feat.py) for the torch code above."""
-    from clipbert_b200 import grid_feat, modeling, ops
+    from clipbert_b200 import grid_feat, modeling, ops, optim
     saved = {n: getattr(ops, n) for n in _NAMES}
+    saved_opt = (optim.sumsq, optim.adamw_step, optim._require_cuda)
     saved_overlap, saved_req, saved_req_cnn = ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda
     calls = {n: 0 for n in _NAMES}
     global IGNORE_DROPOUT
@@ -393,12 +429,14 @@ def emulated_ops(ignore_dropout=False):
             setattr(ops, n, counted(n, globals()[n]))
         ops.overlap_wgrad = False
         modeling._require_cuda = grid_feat._require_cuda = lambda t: None
+        optim.sumsq, optim.adamw_step, optim._require_cuda = opt_sumsq, opt_adamw_step, (lambda dev: None)
         yield calls
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
         ops.overlap_wgrad, modeling._require_cuda, grid_feat._require_cuda = saved_overlap, saved_req, saved_req_cnn
         IGNORE_DROPOUT = saved_drop
+        optim.sumsq, optim.adamw_step, optim._require_cuda = saved_opt
 
 
 emulated_transformer_ops = emulated_ops

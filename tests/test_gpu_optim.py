@@ -54,7 +54,7 @@ def test_fused_adamw_matches_reference_optimizer(cuda):
     p0 = {i: named[i][1].detach().float().cpu().clone() for i in sel}
     steps, max_norm = 3, 1.0
     grads_cpu, norms = [], []
-    gen = torch.Generator(device="cuda").manual_seed(17)
+    gen = torch.Generator(device=cuda).manual_seed(17)
     for t in range(steps):
         for m, scale in ((model.transformer, 3e-3 if t == 1 else 3e-5), (model.cnn, 1e-3 if t == 1 else 1e-5)):   # step 1 clips, 0 and 2 do not
             m._flat.attach_grads()
@@ -68,7 +68,8 @@ def test_fused_adamw_matches_reference_optimizer(cuda):
         n = opt.clip_grad_norm(max_norm)
         assert abs(float(n) - float(total)) < 1e-4 * float(total)
         opt.step(zero_grad=(t == steps - 1))
-    torch.cuda.synchronize()
+    if cuda.type == "cuda":
+        torch.cuda.synchronize()
     assert norms[1] > max_norm > norms[0], norms           # the test really exercises both branches of the clip
     assert float(model.transformer._flat.grad.abs().max()) == 0.0 and float(model.cnn._flat.grad.abs().max()) == 0.0
     # ---- oracle trajectories ----
@@ -117,7 +118,8 @@ def test_fused_adamw_matches_reference_optimizer(cuda):
         b = fresh(mb2)["logits"]
         n2 = ops.launch_count()
     assert torch.equal(a, b)
-    assert (n2 - n1) - (n1 - n0) >= 2, "the freshly loaded model re-casts its weights, the optimized one must not"
+    if cuda.type == "cuda":      # (the CPU replay of this test through the ABI emulator launches no kernels)
+        assert (n2 - n1) - (n1 - n0) >= 2, "the freshly loaded model re-casts its weights, the optimized one must not"
     # ---- state_dict carries the reference's keys ----
     osd = opt.state_dict()
     some = next(iter(osd["state"].values()))

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import test_gpu_model as G
+import test_gpu_optim as GO
 from ops_emulator import emulated_ops
 
 
@@ -36,3 +37,10 @@ def test_gpu_model_test_body_on_emulated_ops(weights, name, kw):
     with emulated_ops() as calls:
         getattr(G, name)(cuda=CPU, weights=weights, **kw)
     assert calls["gemm"] > 0
+
+
+def test_fused_adamw_gpu_test_body_on_emulated_ops():
+    """tests/test_gpu_optim.py replayed on CPU: FusedAdamW's host logic (chunk planning over the flat buffers, the eight
+    reference groups, clip bookkeeping, state views, operand emission flags) with cb_sumsq / cb_adamw_step restated in torch."""
+    with emulated_ops():
+        GO.test_fused_adamw_matches_reference_optimizer(cuda=CPU)
