@@ -136,7 +136,7 @@ def _mg_worker(rank, world, port, flags, outdir):
     symm.empty = lambda *size, dtype=None, device=None: torch.zeros(*size, dtype=dtype)
     symm.rendezvous = lambda t, group: _Handle(t)
     sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1", "--batch", "1", "--n_clips", "2", "--n_frm", "1",
-                "--size", "64", "--txt_len", "12", "--overlap_wgrad", "0", "--graph", "0"] + flags
+                "--size", "64", "--txt_len", "12", "--overlap_wgrad", "0", "--graph", "0", "--optimizer", "0"] + flags
     sys.stdout = open(os.path.join(outdir, "rank%d.out" % rank), "w")
     sys.stderr = open(os.path.join(outdir, "rank%d.err" % rank), "w")
     with emulated_ops(ignore_dropout=True):

@@ -19,8 +19,7 @@ def weights():
 
 CPU = torch.device("cpu")
 CASES = [
-    ("test_cnn_forward_stages", dict(size=96)),
-    ("test_cnn_backward", {}),
+    ("test_cnn_backward", {}),                       # (224 px; forward stages and 64 px variants: tests/test_host_orchestration.py)
     ("test_transformer_forward_backward", dict(n_ex=2)),
     ("test_clipbert_end_to_end_two_clips_lse", {}),
     ("test_multiple_choice_and_classification_heads", {}),
