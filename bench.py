@@ -231,6 +231,8 @@ def run_b200(args):
         ops.set_sm_limit(args.sm_limit)
     if args.pdl_late:
         ops.set_pdl_late(1)
+    if args.mn3d:
+        ops.set_mn3d(1)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
@@ -527,7 +529,7 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), pdl_late=bool(args.pdl_late), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), pdl_late=bool(args.pdl_late), mn3d=bool(args.mn3d), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
                                fused_loss=bool(args.fused_loss), overlap_shortcut=bool(args.overlap_shortcut), cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
@@ -655,6 +657,7 @@ def main():
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
     ap.add_argument("--overlap_shortcut", type=int, default=0, help="forward: the four projection shortcuts on the side stream beside conv1 -> conv2")
+    ap.add_argument("--mn3d", type=int, default=0, help="dgrad / wgrad GEMMs: MN-major operands as one 3-D TMA box per k-chunk (off until measured)")
     ap.add_argument("--pdl_late", type=int, default=0, help="with --pdl 1: GEMM CTAs release their dependents at their last tile, not at entry")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")

@@ -103,6 +103,48 @@ const CUtensorMap* get_tmap_2d(const void* base, uint64_t inner, uint64_t rows, 
   return m;
 }
 
+// The same [rows, cols] row-major bf16 matrix seen as 3-D {64 columns, rows, cols / 64 column blocks}: ONE box of
+// {64, box_rows, nblk} lands as nblk consecutive 128B-swizzled [box_rows x 64] slabs - exactly what nblk separate 2-D boxes of an
+// MN-major UMMA operand produce - so the producer issues one cp.async.bulk.tensor instead of nblk. cols must be a multiple of 64.
+const CUtensorMap* get_tmap_3d_mn(const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, uint32_t nblk) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap*, TmapKeyHash> cache;
+  TmapKey key{reinterpret_cast<uint64_t>(base), cols, rows, ld, 0x80000000u | (nblk << 16) | 64u, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return nullptr;
+  }
+  if ((reinterpret_cast<uint64_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0 || (cols & 63) != 0 || nblk == 0 || nblk > 8) {
+    set_error("3-D MN-major tensor map: base %p, row pitch %llu, cols %llu (must be a multiple of 64), %u blocks", base,
+              (unsigned long long)ld, (unsigned long long)cols, nblk);
+    return nullptr;
+  }
+  CUtensorMap* m = static_cast<CUtensorMap*>(aligned_alloc(64, sizeof(CUtensorMap)));
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {ld * 2, 128};             // bytes: next row, next 64-column block
+  cuuint32_t box[3] = {64, box_rows, nblk};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d) cols=%llu rows=%llu ld=%llu box=64x%ux%u", (int)r, (unsigned long long)cols,
+              (unsigned long long)rows, (unsigned long long)ld, box_rows, nblk);
+    free(m);
+    return nullptr;
+  }
+  if (cache.size() > 65536) {
+    for (auto& kv : cache) free(kv.second);
+    cache.clear();
+  }
+  cache.emplace(key, m);
+  return m;
+}
+
 }  // namespace cb
 
 extern "C" {

@@ -56,6 +56,8 @@ struct GemmEpi {
   int pdl_late;     // programmatic dependent launch: 0 = release the dependents at kernel entry; 1 = when this CTA starts its
                     // LAST tile, so that a dependent's CTAs (200 KB of shared memory each) are not parked on freed SMs for the
                     // whole launch - which is what kept the wgrad side stream off those SMs (include/clipbert_b200.h, cb_set_pdl)
+  int mn3d;         // MN-major operands (B of NN mode, A and B of WGRAD mode) arrive as ONE 3-D TMA box per k-chunk instead of
+                    // BN/64 (BM/64) 2-D boxes: tmA / tmB are then the {64, rows, cols/64} maps of get_tmap_3d_mn (CG = 1 only)
   long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
 };
 
@@ -334,10 +336,15 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
               int shift = 0;
               if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
               const int p = kit * BK;
+              if (CG == 1 && epi.mn3d) {
+                tma_load_3d(sa, &tmA, &full_bar[s], 0, p, t.m0 >> 6);
+                tma_load_3d(sb, &tmB, &full_bar[s], 0, p + shift, t.nb0 >> 6);
+              } else {
 #pragma unroll
-              for (int j = 0; j < A_BOXES; ++j) load(sa + j * (BK * 128), &tmA, t.m0 + j * 64, p);
+                for (int j = 0; j < A_BOXES; ++j) load(sa + j * (BK * 128), &tmA, t.m0 + j * 64, p);
 #pragma unroll
-              for (int j = 0; j < B_BOXES; ++j) load(sb + j * (BK * 128), &tmB, t.nb0 + j * 64, p + shift);
+                for (int j = 0; j < B_BOXES; ++j) load(sb + j * (BK * 128), &tmB, t.nb0 + j * 64, p + shift);
+              }
             } else {
               int shift = 0;
               if (ntaps == 9) shift = tap_sign * ((tp / 3 - 1) * tap_w + (tp % 3 - 1));
@@ -345,6 +352,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
               load(sa, &tmA, kc * BK, t.m0 + shift);
               if (MODE == 0) {
                 load(sb, &tmB, tp * K + kc * BK, t.nb0);
+              } else if (CG == 1 && epi.mn3d) {
+                tma_load_3d(sb, &tmB, &full_bar[s], 0, kc * BK, (tp * N + t.nb0) >> 6);
               } else {
 #pragma unroll
                 for (int j = 0; j < B_BOXES; ++j) load(sb + j * (BK * 128), &tmB, tp * N + t.nb0 + j * 64, kc * BK);
@@ -849,6 +858,7 @@ static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA ep
 static int g_direct_store = 0; // TMA epilogue: 0 = smem chunk + TMA store (default); 1 = direct register -> global stores. EXPERIMENTAL:
                                // +1.3 % on the step but an intermittent mismatch (one warp's 32x16 block of one launch in ~100) on
                                // multi-tile CTAs when the epilogue warps drift apart without the per-chunk barrier - not yet explained
+static int g_mn3d = 0;        // 1 = MN-major operands through one 3-D TMA box per k-chunk (GemmEpi::mn3d); cb_debug_gemm_mn3d
 static int g_pdl_late = 0;    // PDL trigger placement of the GEMM kernel (GemmEpi::pdl_late); cb_debug_gemm_pdl_late
 static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
@@ -889,7 +899,8 @@ static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_a
 }
 
 template <int BN, int MODE, int EPI, int CG, int EW = 8>
-static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t stream) {
+static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_t stream) {
+  GemmEpi epi = epi_in;
   using Cfg = GemmCfg<BN, CG>;
   constexpr int GEMM_THREADS = gemm_threads(EW);
   static bool attr_set = false;
@@ -903,6 +914,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     attr_set = true;
   }
   const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr, *tc2 = nullptr;
+  bool mn3d = false;
   int iters_per_split = 0;
   const int tiles_m = ceil_div(d.m, BM * CG), tiles_n = ceil_div(d.n, BN);
   int total = tiles_m * tiles_n;
@@ -913,11 +925,22 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else if (MODE == 2) {
     ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
-    tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
+    mn3d = g_mn3d && CG == 1 && d.n % 64 == 0;
+    tb = mn3d ? get_tmap_3d_mn(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, BK, BN / 64) : nullptr;
+    if (!tb) {      // not asked for, or the driver refused the 3-D view: the 2-D boxes always work
+      mn3d = false;
+      tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
+    }
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else {
-    ta = get_tmap_2d(d.a, d.m, d.a_rows, d.a_ld, 64, BK);
-    tb = get_tmap_2d(d.b, d.n, d.b_rows, d.b_ld, 64, BK);
+    mn3d = g_mn3d && CG == 1 && d.m % 64 == 0 && d.n % 64 == 0;
+    ta = mn3d ? get_tmap_3d_mn(d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) : nullptr;
+    tb = mn3d ? get_tmap_3d_mn(d.b, d.n, d.b_rows, d.b_ld, BK, BN / 64) : nullptr;
+    if (!ta || !tb) {
+      mn3d = false;
+      ta = get_tmap_2d(d.a, d.m, d.a_rows, d.a_ld, 64, BK);
+      tb = get_tmap_2d(d.b, d.n, d.b_rows, d.b_ld, 64, BK);
+    }
     const int kc = ceil_div(d.k, BK);
     int splits = d.split_k < 1 ? 1 : d.split_k;
     if (splits > kc) splits = kc;
@@ -939,6 +962,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi, cudaStream_t s
   if (!tr) tr = ta;
   if (!tx) tx = ta;
   if (!tc2) tc2 = ta;
+  epi.mn3d = mn3d ? 1 : 0;
   const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15);
   const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, n_rbuf = sp.n_rbuf, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
@@ -1031,6 +1055,7 @@ extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
 extern "C" void cb_debug_gemm_direct_store(int on) { cb::g_direct_store = on ? 1 : 0; }
+extern "C" void cb_debug_gemm_mn3d(int on) { cb::g_mn3d = on ? 1 : 0; }
 extern "C" void cb_debug_gemm_pdl_late(int on) { cb::g_pdl_late = on ? 1 : 0; }
 extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? (n < 2 ? 2 : n & ~1) : 0; }   // even: CTA pairs
 
@@ -1067,6 +1092,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.dbg = g_gemm_timeline;
   epi.direct = g_direct_store;
   epi.pdl_late = g_pdl_late;
+  epi.mn3d = 0;
   if (d.dropout_p > 0.0f) {
     double t = static_cast<double>(d.dropout_p) * 4294967296.0;
     epi.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);

@@ -56,6 +56,9 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 const CUtensorMap* get_tmap_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
                                uint32_t box_inner, uint32_t box_rows);
 
+// the same matrix as {64, rows, cols / 64}: one box = nblk swizzled [box_rows x 64] slabs (MN-major UMMA operands)
+const CUtensorMap* get_tmap_3d_mn(const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, uint32_t nblk);
+
 #define CB_REQUIRE(cond, ...)        \
   do {                               \
     if (!(cond)) {                   \

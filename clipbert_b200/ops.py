@@ -105,6 +105,12 @@ def set_attention_flash(on):
     L.lib().cb_debug_attention_flash(int(bool(on)))
 
 
+def set_mn3d(on):
+    """Tuning hook: MN-major GEMM operands (B of the dgrad mode, both operands of the wgrad mode) through ONE 3-D TMA box per
+    k-chunk instead of BN/64 2-D boxes (the single producer lane issues 2 instead of 5-6 TMA instructions per chunk)."""
+    L.lib().cb_debug_gemm_mn3d(int(bool(on)))
+
+
 def set_pdl_late(on):
     """Tuning hook (with set_pdl(1)): the GEMM kernel releases its dependents when a CTA starts its last tile instead of at entry."""
     L.lib().cb_debug_gemm_pdl_late(int(bool(on)))

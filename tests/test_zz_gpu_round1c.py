@@ -201,6 +201,86 @@ def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
     assert relerr(outs[(1, 0.1)][1], outs[(0, 0.1)][1]) < 1e-3
 
 
+def test_gemm_mn_major_operands_through_3d_tma_boxes(cuda):
+    """ops.set_mn3d(1): the MN-major operands of the dgrad (NN) and wgrad GEMMs arrive as one 3-D TMA box per k-chunk instead of
+    BN/64 2-D boxes. Same bytes in the same shared-memory layout, so NN results must be bit-identical to the 2-D path and the
+    wgrad (fp32 red.add, order not deterministic) equal to accumulation noise; also against fp32 torch. Shapes whose column
+    count is not a multiple of 64 keep the 2-D boxes automatically."""
+    import torch.nn.functional as F
+    from clipbert_b200 import ops
+    from util import TOL_BF16_OP, TOL_FP32_OP
+    g = torch.Generator().manual_seed(2)
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g) * scale).to(cuda).to(torch.bfloat16)
+
+    def both(fn):
+        outs = []
+        try:
+            for on in (0, 1):
+                ops.set_mn3d(on)
+                outs.append(fn())
+        finally:
+            ops.set_mn3d(0)
+        return outs
+
+    # ---- NN (dgrad of Linear / 1x1 conv): out [M, N] = A [M, K] @ B [K, N] ----
+    for M, N, K, bn in ((500, 384, 256, 0), (1312, 2304, 768, 256), (2624, 768, 3072, 128), (64, 768, 3072, 64), (700, 264, 512, 0)):
+        A, B = rnd(M, K), rnd(K, N, scale=0.1)
+
+        def run():
+            C = torch.zeros(M, N, device=cuda)
+            ops.gemm(mode=ops.CB_GEMM_NN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=K, b_ld=N, out=C, out_ld=N, out_fp32=1, block_n=bn)
+            return C
+        c2d, c3d = both(run)
+        assert relerr(c3d, A.float() @ B.float()) < TOL_FP32_OP, (M, N, K)
+        assert torch.equal(c2d, c3d), (M, N, K)
+    # ---- NN with 9 taps: dgrad of a 3x3 conv over the zero-bordered layout, bf16 output through the UNPAD row map ----
+    for NB, H, W, Cin, Cout in ((2, 7, 7, 64, 128), (3, 14, 14, 256, 256), (1, 3, 5, 512, 64)):
+        x = rnd(NB, H, W, Cin)
+        wf = rnd(Cin, Cout, 3, 3, scale=0.05)
+        xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
+        xp[:, 1:-1, 1:-1] = x
+        P = NB * (H + 2) * (W + 2)
+        wfk = wf.permute(0, 2, 3, 1).contiguous().view(Cin, 9 * Cout)
+
+        def run():
+            y = torch.zeros(NB * H * W, Cout, device=cuda, dtype=torch.bfloat16)
+            ops.gemm(mode=ops.CB_GEMM_NN, m=P, n=Cout, k=Cin, a=xp, a_rows=P, a_ld=Cin, b=wfk, b_rows=Cin, b_ld=9 * Cout, ntaps=9,
+                     tap_w=W + 2, tap_sign=-1, out=y, out_ld=Cout, rowmap=ops.ROWMAP_UNPAD, map_h=H, map_w=W)
+            return y
+        y2d, y3d = both(run)
+        ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wf.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+        assert relerr(y3d, ref) < TOL_BF16_OP and torch.equal(y2d, y3d), (NB, H, W, Cin, Cout)
+    # ---- WGRAD: dW [Mo, No] += dY^T X (both operands MN-major), plain and 9-tap ----
+    for P, Mo, No, bn, sk in ((1312, 768, 768, 128, 1), (2624, 3072, 768, 0, 0), (5000, 256, 256, 128, 7), (50176, 512, 128, 0, 0), (333, 136, 72, 64, 1)):
+        dY, X = rnd(P, Mo), rnd(P, No)
+
+        def run():
+            dW = torch.zeros(Mo, No, device=cuda)
+            ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, split_k=sk, out=dW, out_ld=No,
+                     out_fp32=1, block_n=bn)
+            return dW
+        w2d, w3d = both(run)
+        assert relerr(w3d, dY.float().t() @ X.float()) < TOL_FP32_OP and relerr(w3d, w2d) < TOL_FP32_OP, (P, Mo, No)
+    for NB, H, W, Cin, Cout, sk in ((2, 7, 7, 64, 128, 1), (4, 14, 14, 128, 128, 3)):
+        x, dy = rnd(NB, H, W, Cin), rnd(NB, H, W, Cout)
+        xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
+        dyp = torch.zeros(NB, H + 2, W + 2, Cout, device=cuda, dtype=torch.bfloat16)
+        xp[:, 1:-1, 1:-1], dyp[:, 1:-1, 1:-1] = x, dy
+        P = NB * (H + 2) * (W + 2)
+
+        def run():
+            dW = torch.zeros(Cout, 9 * Cin, device=cuda)
+            ops.gemm(mode=ops.CB_GEMM_WGRAD, m=Cout, n=Cin, k=P, a=dyp, a_rows=P, a_ld=Cout, b=xp, b_rows=P, b_ld=Cin, ntaps=9, tap_w=W + 2,
+                     tap_sign=1, split_k=sk, out=dW, out_ld=9 * Cin, out_fp32=1)
+            return dW
+        w2d, w3d = both(run)
+        wz = torch.zeros(Cout, Cin, 3, 3, device=cuda, requires_grad=True)
+        F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        assert relerr(w3d, wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)) < TOL_FP32_OP and relerr(w3d, w2d) < TOL_FP32_OP
+
+
 def test_forward_error_sits_at_the_bf16_noise_floor_of_the_reference_ops(cuda, weights):
     """How far may a correct bf16 implementation be from the fp32 reference? Run the ORACLE's own ops (plain torch: cuDNN /
     cuBLAS bf16 under autocast, fp32 LayerNorm / softmax - the mixed precision the reference trains in) on the same GPU and

@@ -15,6 +15,7 @@ bash tools/gpu_ab.sh 10 \
   "fusedloss_pdl:--fused_loss 1 --pdl 1" \
   "pdl_late:--fused_loss 1 --pdl 1 --pdl_late 1" \
   "pdl_late_1stream:--fused_loss 1 --pdl 1 --pdl_late 1 --overlap_wgrad 0" \
+  "mn3d:--mn3d 1" \
   "shortcut:--overlap_shortcut 1" \
   "sm144:--sm_limit 144" \
   "direct:--direct_store 1"
