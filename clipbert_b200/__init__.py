@@ -6,5 +6,5 @@ host-side mirrors of the reference module interface (``ClipBert``, ``GridFeatBac
 """
 from .e2e_model import ClipBert, clip_lse_loss  # noqa: F401
 from .grid_feat import GridFeatBackbone  # noqa: F401
-from .modeling import (ClipBertForMultipleChoice, ClipBertForPreTraining, ClipBertForSequenceClassification,  # noqa: F401
-                       ClipBertForVideoTextRetrieval)
+from .modeling import (ClipBertForMultipleChoice, ClipBertForPreTraining, ClipBertForRegression,  # noqa: F401
+                       ClipBertForSequenceClassification, ClipBertForVideoTextRetrieval)

@@ -15,6 +15,20 @@ import types
 from . import amp, horovod_torch
 
 
+def alias_reference_modules():
+    """Make the reference's own import lines resolve to this package (src/tasks/run_*.py:7-11, src/pretrain/run_pretrain.py:7-8):
+    ``from src.modeling.e2e_model import ClipBert``, ``from src.modeling.modeling import ClipBertFor...`` and
+    ``from src.modeling.grid_feat import GridFeatBackbone`` then import the B200 modules - the scripts stay byte-identical.
+    Call it before the script's imports run, with the reference root on ``sys.path`` (its ``src`` package must be importable)."""
+    import clipbert_b200.e2e_model as e2e
+    import clipbert_b200.grid_feat as gf
+    import clipbert_b200.modeling as mod
+    sys.modules["src.modeling.e2e_model"] = e2e
+    sys.modules["src.modeling.modeling"] = mod
+    sys.modules["src.modeling.grid_feat"] = gf
+    return ["src.modeling.e2e_model", "src.modeling.modeling", "src.modeling.grid_feat"]
+
+
 def install(force=False):
     """Register the stand-ins under the names the reference imports. Real installations win unless ``force``."""
     def have(name):

@@ -11,8 +11,8 @@ import torch.distributed as dist
 from torch import nn
 
 from .grid_feat import GridFeatBackbone
-from .modeling import (ClipBertForMultipleChoice, ClipBertForSequenceClassification,  # noqa: F401
-                       ClipBertForVideoTextRetrieval)
+from .modeling import (ClipBertForMultipleChoice, ClipBertForPreTraining, ClipBertForRegression,  # noqa: F401
+                       ClipBertForSequenceClassification, ClipBertForVideoTextRetrieval)
 
 
 def allreduce_flat(grads, group=None, average=True, async_op=False):

@@ -715,6 +715,16 @@ class ClipBertForMultipleChoice(_MlpHeadMixin, _ClipBertHeadModel):
         return logits, loss
 
 
+class ClipBertForRegression(nn.Module):
+    """src/modeling/modeling.py:454-507. The reference's task scripts import this name (run_video_qa.py:7-10,
+    e2e_model.py:1-6) but never instantiate it - no task configuration selects it - so only the name exists here: its
+    ELU + BatchNorm1d regressor has no kernels on this path, and constructing it says so instead of running something else."""
+
+    def __init__(self, config):
+        super().__init__()
+        raise NotImplementedError("ClipBertForRegression is not built on the B200 path (unused by every reference task script)")
+
+
 class BertPredictionHeadTransform(nn.Module):
     def __init__(self, config):
         super().__init__()

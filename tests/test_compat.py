@@ -112,3 +112,29 @@ def test_install_leaves_real_packages_alone(monkeypatch):
     monkeypatch.setitem(sys.modules, "apex", types.ModuleType("apex"))
     assert compat.install() == []
     assert sys.modules["horovod"] is fake
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "modeling")), reason="reference tree not present (GPU box)")
+def test_reference_import_lines_resolve_to_this_package(monkeypatch):
+    """The import lines of the reference's task scripts, verbatim (run_video_qa.py:7-11, run_pretrain.py:7-8,
+    e2e_model.py:7), after compat.alias_reference_modules(): the scripts can stay byte-identical."""
+    sys.path.insert(0, ROOT)
+    import clipbert_b200 as cb
+    import clipbert_b200.compat as compat
+    for name in ("src.modeling.e2e_model", "src.modeling.modeling", "src.modeling.grid_feat"):
+        monkeypatch.setitem(sys.modules, name, sys.modules.get(name) or __import__("types").ModuleType(name))
+    monkeypatch.syspath_prepend(REF)
+    assert compat.alias_reference_modules() == ["src.modeling.e2e_model", "src.modeling.modeling", "src.modeling.grid_feat"]
+    from src.modeling.modeling import (  # noqa: F401  (run_video_qa.py:7-10)
+        ClipBertForSequenceClassification,
+        ClipBertForMultipleChoice,
+        ClipBertForRegression)
+    from src.modeling.e2e_model import ClipBert                          # run_video_qa.py:11
+    from src.modeling.modeling import ClipBertForPreTraining             # run_pretrain.py:7
+    from src.modeling.modeling import ClipBertForVideoTextRetrieval      # run_video_retrieval.py:7
+    from src.modeling.grid_feat import GridFeatBackbone                  # e2e_model.py:7
+    assert ClipBert is cb.ClipBert and ClipBertForMultipleChoice is cb.ClipBertForMultipleChoice
+    assert ClipBertForSequenceClassification is cb.ClipBertForSequenceClassification and ClipBertForPreTraining is cb.ClipBertForPreTraining
+    assert ClipBertForVideoTextRetrieval is cb.ClipBertForVideoTextRetrieval and GridFeatBackbone is cb.GridFeatBackbone
+    with pytest.raises(NotImplementedError):       # imported by the scripts, never constructed by them
+        ClipBertForRegression(None)
