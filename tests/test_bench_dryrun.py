@@ -54,8 +54,9 @@ def _ctx(*a, **k):
     yield
 
 
-@pytest.mark.parametrize("flags", [["--graph", "1", "--size", "128"], ["--graph", "0", "--prefetch", "0", "--fused_loss", "1", "--recast_in_step", "1"],
-                                   ["--graph", "0", "--clip_batching", "0", "--stem", "im2col", "--size", "128"]])
+@pytest.mark.parametrize("flags", [["--graph", "1", "--size", "128"],
+                                   ["--graph", "0", "--prefetch", "0", "--fused_loss", "1", "--recast_in_step", "1", "--clip_batching", "0",
+                                    "--stem", "im2col", "--overlap_shortcut", "1", "--mn3d", "1", "--pdl_late", "1"]])
 def test_bench_control_flow_on_cpu(monkeypatch, capsys, flags):
     import bench
     from ops_emulator import emulated_ops

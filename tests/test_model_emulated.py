@@ -18,14 +18,13 @@ def weights():
 
 
 CPU = torch.device("cpu")
+# (the golden-vector, multiple-choice and 448 px / 521-token bodies also pass through the emulator; they are left to the GPU run
+# to keep this suite short - tests/test_host_orchestration.py covers the same engines at small sizes)
 CASES = [
     ("test_cnn_backward", {}),                       # (224 px; forward stages and 64 px variants: tests/test_host_orchestration.py)
     ("test_transformer_forward_backward", dict(n_ex=2)),
     ("test_clipbert_end_to_end_two_clips_lse", {}),
-    ("test_multiple_choice_and_classification_heads", {}),
     ("test_ragged_repeat_counts_and_eval_determinism", {}),
-    ("test_against_reference_generated_golden_vectors", {}),
-    ("test_native_resolution_448_and_long_text", {}),
     ("test_pretraining_heads_mlm_itm", {}),
     ("test_forward_clips_equals_the_reference_clip_loop", {}),
 ]
