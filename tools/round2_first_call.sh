@@ -4,9 +4,10 @@
 # 1. the GPU suites (the late-sorted file holds the tests that have never run on a GPU), 2. the default bench line,
 # 3. A/B of the switches that are off until measured, 4. a fresh launch list. Results land in gpurun_out/.
 set -u
+unset CB_EXPERIMENTAL          # 1st pass: the suite as the round-end driver runs it; 2nd pass adds the off-by-default kernels
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02_pytest_gpu.txt
-timeout 300 python -m pytest tests/test_zz_gpu_round1c.py -m gpu -q -s > gpurun_out/r02_pytest_zz.txt 2>&1; echo "zz rc=$?"; tail -5 gpurun_out/r02_pytest_zz.txt
+CB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_gpu_round1c.py -m gpu -q -s > gpurun_out/r02_pytest_zz.txt 2>&1; echo "zz rc=$?"; tail -5 gpurun_out/r02_pytest_zz.txt
 timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; echo "bench rc=$?"
 bash tools/gpu_ab.sh 10 \
   "recast:--recast_in_step 1" \
