@@ -218,7 +218,6 @@ def run_b200(args):
     model = model.to(dev).train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
-    model.cnn.overlap_shortcut = bool(args.overlap_shortcut)
     if world > 1:
         model.enable_overlapped_allreduce(cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, max_ctas=args.nvls_ctas)
 
@@ -226,13 +225,10 @@ def run_b200(args):
     ops.set_pdl(args.pdl)
     ops.set_epi_warps(args.epi_warps)
     ops.set_cbuf(args.cbuf)
-    ops.set_direct_store(args.direct_store)
     if args.sm_limit:
         ops.set_sm_limit(args.sm_limit)
-    if args.pdl_late:
-        ops.set_pdl_late(1)
-    if args.mn3d:
-        ops.set_mn3d(1)
+    ops.set_mn3d(args.mn3d)
+    ops.set_occ2(args.occ2, args.occ2_gflop)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
@@ -529,8 +525,8 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), pdl_late=bool(args.pdl_late), mn3d=bool(args.mn3d), overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps, direct_store=bool(args.direct_store),
-                               fused_loss=bool(args.fused_loss), overlap_shortcut=bool(args.overlap_shortcut), cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps,
+                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -643,22 +639,21 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
-    ap.add_argument("--direct_store", type=int, default=0, help="GEMM epilogue output: 1 direct register->global stores, 0 smem chunk + TMA store")
     ap.add_argument("--cbuf", type=int, default=0, choices=[0, 2, 4], help="TMA-store chunk buffers of the GEMM epilogue (0 = library default)")
     ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
     ap.add_argument("--prefetch", type=int, default=1, help="e2e: upload batch i+1 on a copy stream while batch i computes (0: copy on the compute stream)")
-    ap.add_argument("--fused_loss", type=int, default=0, help="1: clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss) instead of ~45 ATen launches (off until its GPU test has run)")
+    ap.add_argument("--fused_loss", type=int, default=1, help="1 (default): clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss); 0: ~45 ATen launches")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, or this library's NVLS all-reduce (csrc/nvls.cu; experimental until run on a multi-GPU box)")
     ap.add_argument("--nvls_ctas", type=int, default=64, help="CTAs of the NVLS all-reduce kernel")
     ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
-    ap.add_argument("--overlap_shortcut", type=int, default=0, help="forward: the four projection shortcuts on the side stream beside conv1 -> conv2")
-    ap.add_argument("--mn3d", type=int, default=0, help="dgrad / wgrad GEMMs: MN-major operands as one 3-D TMA box per k-chunk (off until measured)")
-    ap.add_argument("--pdl_late", type=int, default=0, help="with --pdl 1: GEMM CTAs release their dependents at their last tile, not at entry")
+    ap.add_argument("--mn3d", type=int, default=1, help="dgrad / wgrad GEMMs: MN-major operands as one 3-D TMA box per k-chunk (default) or BN/64 2-D boxes")
+    ap.add_argument("--occ2", type=int, default=1, help="two GEMM CTAs per SM: 0 never, 1 only launches the tuning table marks, 2 every eligible launch up to --occ2_gflop")
+    ap.add_argument("--occ2_gflop", type=float, default=0.0, help="with --occ2 2: largest launch (GFLOP) that runs two CTAs per SM (0 = no limit)")
     ap.add_argument("--cpu_batch", type=int, default=4)
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
     ap.add_argument("--opt_steps", type=int, default=10, help="timed iterations of the informational fused-optimizer leg")

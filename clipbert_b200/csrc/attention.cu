@@ -17,11 +17,7 @@ constexpr int LDS = 65;    // padded smem row stride (floats)
 constexpr int ATT_THREADS = 256;
 constexpr int TILE_FLOATS = TS * LDS;
 
-struct AttnDrop {
-  uint32_t thresh;
-  float inv_keep;
-  uint64_t seed;
-};
+using AttnDrop = DropCfg;   // (thresh, inv_keep, seed, device-side seed offset): drop_cfg.h
 
 // load a [TS x 64] bf16 tile (rows r0.., row pitch ld elements) into fp32 smem; rows >= nrows are zero
 __device__ __forceinline__ void load_tile(float* dst, const __nv_bfloat16* src, int64_t ld, int r0, int nrows) {
@@ -138,8 +134,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
                                                                const int64_t* __restrict__ text_mask,
                                                                __nv_bfloat16* __restrict__ ctx, int64_t ld_ctx,
                                                                float* __restrict__ lse, int L, int Lt, int H, float scale,
-                                                               AttnDrop dc) {
+                                                               AttnDrop dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const AttnDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ float sm[];
   float* Qs = sm;
@@ -290,8 +287,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kv_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     int64_t ld_qkv, const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
     const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dk,
-    __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc) {
+    __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const AttnDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ float sm[];
   float* Ks = sm;
@@ -345,8 +343,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_q_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     int64_t ld_qkv, const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
     const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
-    int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc) {
+    int64_t ld_dqkv, int L, int Lt, int H, float scale, AttnDrop dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const AttnDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ float sm[];
   float* Qs = sm;
@@ -388,20 +387,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_q_kernel(
   store_tile(dSs, dq + row0 * ld_dqkv + h * HD, ld_dqkv, q0, L);
 }
 
-static AttnDrop make_attn_drop(float p, uint64_t seed) {
-  AttnDrop d;
-  d.seed = seed;
-  if (p > 0.0f) {
-    double t = static_cast<double>(p) * 4294967296.0;
-    d.thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
-    if (d.thresh == 0) d.thresh = 1;
-    d.inv_keep = 1.0f / (1.0f - p);
-  } else {
-    d.thresh = 0;
-    d.inv_keep = 1.0f;
-  }
-  return d;
-}
+static AttnDrop make_attn_drop(float p, uint64_t seed) { return make_drop(p, seed); }
 
 template <typename K>
 static int set_smem(K kern, int bytes) {
@@ -422,7 +408,7 @@ int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
 int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
                            int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream);
 int g_attention_force_general = 0;   // test knob: 1 = always use the general (any L) kernels
-int g_attention_flash = 0;           // 1 = forward of sequences longer than 64 tokens on the tensor-core online-softmax kernel
+int g_attention_flash = 1;           // 1 = forward of sequences longer than 64 tokens on the tensor-core online-softmax kernel
                                      // (attention_tc.cu); off until it has been checked on a B200
 
 }  // namespace cb

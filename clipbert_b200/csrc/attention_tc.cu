@@ -17,11 +17,7 @@ constexpr int TC_LD = 72;                 // bf16 elements per smem row (144 B: 
 constexpr int TC_TILE = 64 * TC_LD;       // elements per 64-row tile
 constexpr int TC_THREADS = 128;
 
-struct TcDrop {
-  uint32_t thresh;
-  float inv_keep;
-  uint64_t seed;
-};
+using TcDrop = DropCfg;   // (thresh, inv_keep, seed, device-side seed offset): drop_cfg.h
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -132,8 +128,9 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
                                                                  const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
                                                                  int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
-                                                                 TcDrop dc) {
+                                                                 TcDrop dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const TcDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
@@ -178,10 +175,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
     if (dc.thresh) {
       const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + rq) * L + j * 8 + cq;
       const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
-      p0 *= dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
-      p1 *= dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
-      p2 *= dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
-      p3 *= dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+      { float m0_, m1_; dropout_mult2(dc.seed, base0, dc.thresh, dc.inv_keep, m0_, m1_); p0 *= m0_; p1 *= m1_; }
+      { float m0_, m1_; dropout_mult2(dc.seed, base1, dc.thresh, dc.inv_keep, m0_, m1_); p2 *= m0_; p3 *= m1_; }
     }
     pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
     pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
@@ -219,8 +214,9 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __n
                                                                        const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
                                                                        const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
                                                                        int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
-                                                                       TcDrop dc) {
+                                                                       TcDrop dc_in) {
   pdl_wait();
+  const TcDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
@@ -278,10 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __n
       if (dc.thresh) {
         const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + (q0 + rq)) * L + k0 + j * 8 + cq;
         const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
-        p0 *= dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
-        p1 *= dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
-        p2 *= dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
-        p3 *= dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+        { float m0_, m1_; dropout_mult2(dc.seed, base0, dc.thresh, dc.inv_keep, m0_, m1_); p0 *= m0_; p1 *= m1_; }
+        { float m0_, m1_; dropout_mult2(dc.seed, base1, dc.thresh, dc.inv_keep, m0_, m1_); p2 *= m0_; p3 *= m1_; }
       }
       pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
@@ -317,8 +311,9 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx,
                                                                  const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
                                                                  __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int64_t ld_dqkv,
-                                                                 int L, int Lt, int H, float scale, TcDrop dc) {
+                                                                 int L, int Lt, int H, float scale, TcDrop dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const TcDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
@@ -382,10 +377,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
     if (dc.thresh) {
       const uint64_t base0 = ((static_cast<uint64_t>(b) * H + h) * L + rq) * L + j * 8 + cq;
       const uint64_t base1 = base0 + static_cast<uint64_t>(8) * L;
-      r_0 = dropout_mult(dc.seed, base0, dc.thresh, dc.inv_keep);
-      r_1 = dropout_mult(dc.seed, base0 + 1, dc.thresh, dc.inv_keep);
-      r_2 = dropout_mult(dc.seed, base1, dc.thresh, dc.inv_keep);
-      r_3 = dropout_mult(dc.seed, base1 + 1, dc.thresh, dc.inv_keep);
+      dropout_mult2(dc.seed, base0, dc.thresh, dc.inv_keep, r_0, r_1);
+      dropout_mult2(dc.seed, base1, dc.thresh, dc.inv_keep, r_2, r_3);
     }
     const float ds0 = p0 * (dp[j][0] * r_0 - D0), ds1 = p1 * (dp[j][1] * r_1 - D0);
     const float ds2 = p2 * (dp[j][2] * r_2 - D1), ds3 = p3 * (dp[j][3] * r_3 - D1);
@@ -418,20 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
   tc_store_tile(dSs, dk + row0 * ld_dqkv + h * 64, ld_dqkv, L);
 }
 
-static TcDrop make_tc_drop(float p, uint64_t seed) {
-  TcDrop d;
-  d.seed = seed;
-  if (p > 0.0f) {
-    double t = static_cast<double>(p) * 4294967296.0;
-    d.thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
-    if (d.thresh == 0) d.thresh = 1;
-    d.inv_keep = 1.0f / (1.0f - p);
-  } else {
-    d.thresh = 0;
-    d.inv_keep = 1.0f;
-  }
-  return d;
-}
+static TcDrop make_tc_drop(float p, uint64_t seed) { return make_drop(p, seed); }
 
 // called from cb_attention_fwd / cb_attention_bwd (attention.cu) when l <= 64
 int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,

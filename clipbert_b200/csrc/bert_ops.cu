@@ -11,26 +11,6 @@ constexpr int HID = 768;          // hidden size (src/configs/base_model.json)
 constexpr int CH = HID / 256;     // uint4 (8 x bf16) chunks per lane
 constexpr int ROWS_PER_BLOCK = 4; // one warp per row
 
-struct DropCfg {
-  uint32_t thresh;
-  float inv_keep;
-  uint64_t seed;
-};
-static DropCfg make_drop(float p, uint64_t seed) {
-  DropCfg d;
-  d.seed = seed;
-  if (p > 0.0f) {
-    double t = static_cast<double>(p) * 4294967296.0;
-    d.thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
-    if (d.thresh == 0) d.thresh = 1;
-    d.inv_keep = 1.0f / (1.0f - p);
-  } else {
-    d.thresh = 0;
-    d.inv_keep = 1.0f;
-  }
-  return d;
-}
-
 // lane-local view of one row: element (c, j) is column c*256 + lane*8 + j
 __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* row, int lane, float (&x)[CH][8]) {
 #pragma unroll
@@ -103,9 +83,12 @@ __device__ __forceinline__ void apply_dropout_row(float (&x)[CH][8], const DropC
 #pragma unroll
   for (int c = 0; c < CH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      x[c][j] *= dropout_mult(dc.seed, static_cast<uint64_t>(row) * HID + c * 256 + lane * 8 + j, dc.thresh,
-                              dc.inv_keep);
+    for (int j = 0; j < 8; j += 4) {      // 4-aligned runs: one hash per four elements
+      float m[4];
+      dropout_mult4(dc.seed, static_cast<uint64_t>(row) * HID + c * 256 + lane * 8 + j, dc.thresh, dc.inv_keep, m);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) x[c][j + t] *= m[t];
+    }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma. On return x holds xhat, dy holds dx.
@@ -170,8 +153,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      const __nv_bfloat16* __restrict__ x,
                                                      const float* __restrict__ stats, const float* gamma,
                                                      __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
-                                                     float* dgamma, float* dbeta, float* dbias_drop, int M, DropCfg dc) {
+                                                     float* dgamma, float* dbeta, float* dbias_drop, int M, DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,8 +213,9 @@ __global__ void __launch_bounds__(128) embed_text_fwd_kernel(const int64_t* __re
                                                              const float* pos, const float* type0,
                                                              const float* gamma, const float* beta,
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
-                                                             int nseq, int Lt, int L, int vocab, float eps, DropCfg dc) {
+                                                             int nseq, int Lt, int L, int vocab, float eps, DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp;
@@ -262,8 +247,9 @@ __global__ void __launch_bounds__(128) embed_text_bwd_kernel(const __nv_bfloat16
                                                              const float* pos, const float* type0, const float* gamma,
                                                              const float* __restrict__ stats, float* dword, float* dpos,
                                                              float* dtype0, float* dgamma, float* dbeta, int nseq, int Lt,
-                                                             int L, int vocab, DropCfg dc) {
+                                                             int L, int vocab, DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,8 +312,9 @@ __global__ void __launch_bounds__(128) embed_visual_fwd_kernel(const __nv_bfloat
                                                                const float* type0, const float* gamma, const float* beta,
                                                                __nv_bfloat16* __restrict__ out, float* __restrict__ stats,
                                                                int nseq, int T, int gh, int gw, int Lt, int L, float eps,
-                                                               DropCfg dc) {
+                                                               DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lv = gh * gw;
@@ -377,8 +364,9 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_kernel(const __nv_bfloat
                                                                const float* __restrict__ stats, float* __restrict__ dv_tmp,
                                                                float* drow, float* dcol, float* dtype0, float* dgamma,
                                                                float* dbeta, int nseq, int T, int gh, int gw, int Lt, int L,
-                                                               DropCfg dc) {
+                                                               DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   __shared__ float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,8 +506,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 // ------------------------------------------------------------------------------------------------
 // small elementwise helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, DropCfg dc) {
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, DropCfg dc_in) {
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
@@ -531,7 +520,12 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
   t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] *= dropout_mult(dc.seed, static_cast<uint64_t>(i + j), dc.thresh, dc.inv_keep);
+  for (int j = 0; j < 8; j += 4) {
+    float m[4];
+    dropout_mult4(dc.seed, static_cast<uint64_t>(i + j), dc.thresh, dc.inv_keep, m);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) f[j + t] *= m[t];
+  }
   uint4 o;
   o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
   o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);

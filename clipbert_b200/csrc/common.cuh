@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "drop_cfg.h"
+
 namespace cb {
 
 // ---------------------------------------------------------------------------------------
@@ -303,19 +305,51 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Counter-based dropout RNG: keep-decision is a pure function of (seed, element index), so the
-// backward pass regenerates the identical mask without storing it.
-__device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
-  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+// Counter-based dropout RNG: the keep decision is a pure function of (seed, element index), so the backward pass
+// regenerates the identical mask without storing it. ONE 64-bit hash serves the four consecutive elements
+// 4g .. 4g+3 (g = index >> 2): element e keeps iff the 16-bit lane (e & 3) of hash(seed, e >> 2) is >= thresh16 =
+// round(p * 65536) (|p_effective - p| < 1.6e-5). Every mask consumer of the library (GEMM epilogue, LayerNorm backward,
+// embeddings, attention probabilities, cb_dropout) goes through these helpers; the ones that own 4-aligned runs of
+// elements hash once per run (the splitmix64 finaliser is ~25 integer instructions - it made the dropout GEMM epilogues
+// issue-bound when it ran once per element).
+//
+// The seed a kernel uses is  seed_argument + (*offset) * odd constant  where `offset` is an optional device pointer
+// (cb_dropout_offset_bind): a captured CUDA graph advances that word on the device at every replay, so replays draw
+// fresh masks although the seed ARGUMENT is baked into the graph (forward and backward of one step read the same word).
+// call once per thread AFTER griddepcontrol.wait (the word is written by an earlier kernel of the same stream)
+__device__ __forceinline__ uint64_t drop_seed(uint64_t seed, const uint64_t* offset) {
+  return offset ? seed + __ldg(reinterpret_cast<const unsigned long long*>(offset)) * 0xD1342543DE82EF95ull : seed;
+}
+__device__ __forceinline__ DropCfg drop_resolve(DropCfg dc) {
+  if (dc.thresh) dc.seed = drop_seed(dc.seed, dc.offset);
+  dc.offset = nullptr;
+  return dc;
+}
+__device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint64_t group) {
+  uint64_t z = group * 0x9E3779B97F4A7C15ull + seed;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return static_cast<uint32_t>(z >> 32);
+  return z ^ (z >> 31);
 }
-// returns the multiplier (0 or 1/(1-p)); thresh = p * 2^32
-__device__ __forceinline__ float dropout_mult(uint64_t seed, uint64_t idx, uint32_t thresh,
-                                              float inv_keep) {
-  return mix32(seed, idx) >= thresh ? inv_keep : 0.0f;
+__device__ __forceinline__ float drop_lane(uint64_t h, int lane, uint32_t thresh, float inv_keep) {
+  return (static_cast<uint32_t>(h >> (16 * lane)) & 0xFFFFu) >= thresh ? inv_keep : 0.0f;
+}
+// multiplier (0 or 1/(1-p)) of ONE element; thresh = p * 2^16
+__device__ __forceinline__ float dropout_mult(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
+  return drop_lane(drop_hash(seed, idx >> 2), static_cast<int>(idx & 3), thresh, inv_keep);
+}
+// multipliers of the four elements idx .. idx+3, idx a multiple of 4: one hash
+__device__ __forceinline__ void dropout_mult4(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep, float (&m)[4]) {
+  const uint64_t h = drop_hash(seed, idx >> 2);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = drop_lane(h, j, thresh, inv_keep);
+}
+// two consecutive elements idx, idx+1 at any alignment (attention probabilities): one hash unless they straddle a group
+__device__ __forceinline__ void dropout_mult2(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep, float& m0, float& m1) {
+  const uint64_t h0 = drop_hash(seed, idx >> 2);
+  const int l0 = static_cast<int>(idx & 3);
+  m0 = drop_lane(h0, l0, thresh, inv_keep);
+  m1 = l0 == 3 ? drop_lane(drop_hash(seed, (idx >> 2) + 1), 0, thresh, inv_keep) : drop_lane(h0, l0 + 1, thresh, inv_keep);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

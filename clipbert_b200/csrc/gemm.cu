@@ -51,11 +51,7 @@ struct GemmEpi {
   uint32_t drop_thresh;
   float drop_inv_keep;
   uint64_t seed;
-  int direct;       // TMA epilogue only: 1 = every thread stores its own row segment straight from registers (no smem staging,
-                    // no chunk barrier, no TMA store); 0 = swizzled smem chunk + TMA store / cooperative re-mapped copy
-  int pdl_late;     // programmatic dependent launch: 0 = release the dependents at kernel entry; 1 = when this CTA starts its
-                    // LAST tile, so that a dependent's CTAs (200 KB of shared memory each) are not parked on freed SMs for the
-                    // whole launch - which is what kept the wgrad side stream off those SMs (include/clipbert_b200.h, cb_set_pdl)
+  const uint64_t* seed_off;   // device word folded into the seed at run time (cb_dropout_offset_bind), or nullptr
   int mn3d;         // MN-major operands (B of NN mode, A and B of WGRAD mode) arrive as ONE 3-D TMA box per k-chunk instead of
                     // BN/64 (BM/64) 2-D boxes: tmA / tmB are then the {64, rows, cols/64} maps of get_tmap_3d_mn (CG = 1 only)
   long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
@@ -76,7 +72,7 @@ struct GemmCfg {
 
 // fused elementwise epilogue on 32 consecutive columns [nb, nb+32) of one output row
 template <int NC>
-__device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi, int nb, int N, int64_t orow,
+__device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi, uint64_t dseed, int nb, int N, int64_t orow,
                                               const uint32_t* res16, const uint32_t* aux16, uint32_t* o2_16) {
   if (nb >= N) return;
   if (epi.scale) {
@@ -98,9 +94,14 @@ __device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi
     }
   }
   if (epi.drop_thresh) {
+    // N % 8 == 0 and nb % 16 == 0: the run starts on a 4-element group boundary -> one hash per four columns
     const uint64_t base = static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb;
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] *= dropout_mult(epi.seed, base + j, epi.drop_thresh, epi.drop_inv_keep);
+    for (int j = 0; j < NC; j += 4) {
+      float m[4];
+      dropout_mult4(dseed, base + j, epi.drop_thresh, epi.drop_inv_keep, m);
+      f[j] *= m[0]; f[j + 1] *= m[1]; f[j + 2] *= m[2]; f[j + 3] *= m[3];
+    }
   }
   if (res16) {
 #pragma unroll
@@ -234,8 +235,8 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles
   return t;
 }
 
-template <int BN, int MODE, int EPI, int CG, int EW>
-__global__ void __launch_bounds__(gemm_threads(EW), 1)
+template <int BN, int MODE, int EPI, int CG, int EW, int OCC>
+__global__ void __launch_bounds__(gemm_threads(EW), OCC)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
   constexpr int EPI_THREADS = EW * 32;
   constexpr int NGRP = EW / 4;                  // warps sharing one TMEM lane quarter
   static_assert(EW == 8 || (EW == 16 && EPI == 1), "16 epilogue warps only with the TMA epilogue");
+  static_assert(OCC == 1 || (OCC == 2 && CG == 1 && EW == 8 && BN <= 128), "two CTAs per SM: single-CTA tiles, 8 epilogue warps, 2 x BN <= 256 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = KCH * Cfg::STAGE_BYTES;           // a stage holds KCH consecutive 64-deep k-chunks (one barrier round trip)
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
   const int unit = blockIdx.x / CG;                                     // persistent work unit (CTA or CTA pair)
   const int n_units = gridDim.x / CG;
   if (threadIdx.x == 0) dbg_stamp(epi, 0);   // (debug-only buffer, not produced by any kernel: safe before pdl_wait)
-  if (!epi.pdl_late) pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
+  pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -378,7 +380,6 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
         const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
-        if (epi.pdl_late && tile + n_units >= total_tiles) pdl_trigger();   // last tile of this CTA (a non-issuing CTA releases on exit)
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
       if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
       else mbar_arrive(bar);
     };
+    const uint64_t dseed = epi.drop_thresh ? drop_seed(epi.seed, epi.seed_off) : 0ull;   // after pdl_wait: the word is device data
     const int ew = warp - 3;          // 0 .. EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = ew >> 2;          // two warps share each lane quarter and split the columns
@@ -470,7 +472,6 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
                      : (epi.shift != nullptr && !has_aux && (epi.act == CB_ACT_NONE || epi.act == CB_ACT_RELU)) ? 1
                      : (epi.shift == nullptr && has_aux && epi.aux_mode == CB_AUX_RELU_MASK && epi.act == CB_ACT_NONE) ? 2 : 0;
       const bool kind_relu = epi.act == CB_ACT_RELU;
-      const bool direct = epi.direct != 0;
       int g = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
         const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
@@ -481,108 +482,82 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
         tc_fence_after();
         if (elected && local == 0) dbg_stamp(epi, 7);
         const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-        // direct stores: this thread's output row (re-mapped between compact and zero-bordered pixel rows if asked)
-        bool drow_ok = orow < M;
-        int64_t drow = orow;
-        if (direct && remap) {
-          const int m = static_cast<int>(orow);
-          if (epi.rowmap == CB_ROWMAP_PAD) {
-            const int hw = epi.H * epi.W;
-            const int img = m / hw;
-            const int rr = m - img * hw;
-            const int y = rr / epi.W, x = rr - y * epi.W;
-            drow = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
-          } else {
-            const int wp = epi.W + 2, hp = epi.H + 2;
-            const int img = m / (hp * wp);
-            const int rr = m - img * (hp * wp);
-            const int y = rr / wp, x = rr - y * wp;
-            drow_ok = drow_ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
-            drow = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
-          }
-        }
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++g) {
-          constexpr int NC = 64 / NGRP;                 // columns of a 64-column chunk owned by this thread: 32 (8 warps) or 16
-          constexpr int NU = NC / 8;                    // ... in 16-byte units
+          // columns of a 64-column chunk owned by this thread: NCW = 32 (8 warps) or 16 (16 warps), worked off NC at a time:
+          // the two-CTAs-per-SM variant (OCC = 2: 88 registers per thread) takes its 32 columns in two passes of 16
+          constexpr int NCW = 64 / NGRP;
+          constexpr int NC = (OCC == 2 && NCW == 32) ? 16 : NCW;
+          constexpr int NSUB = NCW / NC;
+          constexpr int NU = NC / 8;                    // columns of one pass in 16-byte units
           const int b = g & (n_rbuf - 1);
           const uint32_t bph = (g / n_rbuf) & 1;
-          const int nb = t.n0 + c * 64 + grp * NC;      // this thread's columns
-          uint32_t v[NC];
-          __syncwarp();
-          if constexpr (NC == 32) tmem_ld32(trow + c * 64 + grp * NC, reinterpret_cast<uint32_t(&)[32]>(v));
-          else tmem_ld16(trow + c * 64 + grp * NC, reinterpret_cast<uint32_t(&)[16]>(v));
-          tmem_ld_wait();
-          if (c == CPT - 1) {                           // last TMEM read of this tile
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc(&tempty_bar[acc]);
-          }
-          uint32_t res16[NC / 2], aux16[NC / 2];
-          if (has_in) mbar_wait(&rfull_bar[b], bph);
-          if (has_res) {
-            const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rr + (((grp * NU + j) ^ swz) << 4));
-              res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
-            }
-          }
-          if (has_aux) {
-            const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(xr + (((grp * NU + j) ^ swz) << 4));
-              aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
-            }
-          }
-          if (has_in) {                                 // this warp has its residual / aux values in registers: hand the buffer back
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rempty_bar[b]);
-          }
-          float f[NC];
-#pragma unroll
-          for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
-          uint32_t o2_16[NC / 2];
-          if (kind == 1) epilogue_shift_act<NC>(f, epi.shift + nb, has_res ? res16 : nullptr, kind_relu);
-          else if (kind == 2) epilogue_relu_mask<NC>(f, has_res ? res16 : nullptr, aux16);
-          else epilogue_math<NC>(f, epi, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
-          if (direct) {
-            // 16 (or 32) contiguous bf16 of one output row per thread: full 32-byte sectors; the four warps of a lane quarter
-            // complete every 128-byte line within the same chunk, so L2 writes whole lines back
-            if (drow_ok) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + drow * epi.out_ld + nb;
-#pragma unroll
-              for (int j = 0; j < NU; ++j)
-                if (nb + 8 * j + 8 <= N)
-                  *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-              if (has_out2) {
-                __nv_bfloat16* o2 = epi.out2 + drow * epi.out2_ld + nb;
-#pragma unroll
-                for (int j = 0; j < NU; ++j)
-                  if (nb + 8 * j + 8 <= N)
-                    *reinterpret_cast<uint4*>(o2 + 8 * j) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
-              }
-            }
-            continue;
-          }
           const int cb = g & (n_cbuf - 1);
           uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
-          if (has_out2) {
-            uint8_t* c2r = c2buf + cb * CHUNK_BYTES + row * 128;
+          uint8_t* c2r = c2buf + cb * CHUNK_BYTES + row * 128;
+          if (has_in) mbar_wait(&rfull_bar[b], bph);
+          if (n_cbuf == 1) {      // single output buffer: the previous chunk's TMA store (or cooperative copy) must be done with it
+            if (elected && !remap) tma_store_wait_read<0>();
+            __syncwarp();
+            named_bar_sync(2, EPI_THREADS);
+          }
+#pragma unroll 1
+          for (int sub = 0; sub < NSUB; ++sub) {
+            const int col0 = grp * NCW + sub * NC;      // first column of this pass inside the chunk
+            const int u0 = col0 >> 3;                   // ... as a 16-byte unit index of the 128-byte row
+            const int nb = t.n0 + c * 64 + col0;
+            uint32_t v[NC];
+            __syncwarp();
+            if constexpr (NC == 32) tmem_ld32(trow + c * 64 + col0, reinterpret_cast<uint32_t(&)[32]>(v));
+            else tmem_ld16(trow + c * 64 + col0, reinterpret_cast<uint32_t(&)[16]>(v));
+            tmem_ld_wait();
+            if (c == CPT - 1 && sub == NSUB - 1) {      // last TMEM read of this tile
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) release_acc(&tempty_bar[acc]);
+            }
+            uint32_t res16[NC / 2], aux16[NC / 2];
+            if (has_res) {
+              const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
+#pragma unroll
+              for (int j = 0; j < NU; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rr + (((u0 + j) ^ swz) << 4));
+                res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
+              }
+            }
+            if (has_aux) {
+              const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
+#pragma unroll
+              for (int j = 0; j < NU; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(xr + (((u0 + j) ^ swz) << 4));
+                aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
+              }
+            }
+            if (has_in && sub == NSUB - 1) {            // this warp has its residual / aux values in registers: hand the buffer back
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&rempty_bar[b]);
+            }
+            float f[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
+            uint32_t o2_16[NC / 2];
+            if (kind == 1) epilogue_shift_act<NC>(f, epi.shift + nb, has_res ? res16 : nullptr, kind_relu);
+            else if (kind == 2) epilogue_relu_mask<NC>(f, has_res ? res16 : nullptr, aux16);
+            else epilogue_math<NC>(f, epi, dseed, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
+            if (has_out2) {
+#pragma unroll
+              for (int j = 0; j < NU; ++j)
+                *reinterpret_cast<uint4*>(c2r + (((u0 + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+            }
 #pragma unroll
             for (int j = 0; j < NU; ++j)
-              *reinterpret_cast<uint4*>(c2r + (((grp * NU + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+              *reinterpret_cast<uint4*>(cr + (((u0 + j) ^ swz) << 4)) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           }
-#pragma unroll
-          for (int j = 0; j < NU; ++j)
-            *reinterpret_cast<uint4*>(cr + (((grp * NU + j) ^ swz) << 4)) =
-                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           if (!remap) {
             fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the TMA store
-            if (elected) {                              // the buffer the NEXT chunk writes must be free again
+            if (elected && n_cbuf > 1) {                // the buffer the NEXT chunk writes must be free again
               if (n_cbuf == 4) tma_store_wait_read<2>();
               else tma_store_wait_read<0>();
             }
@@ -759,7 +734,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
               const int nb = ncol + h * 32;
-              epilogue_math<32>(f, epi, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
+              epilogue_math<32>(f, epi, dseed, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
                             epi.out2 ? o2 + h * 16 : nullptr);
               if (epi.out_fp32) {
                 // fp32 output: stage 32 columns (128 B per row) and store coalesced right away
@@ -855,11 +830,7 @@ static int sm_count() {
 static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
 static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
-static int g_direct_store = 0; // TMA epilogue: 0 = smem chunk + TMA store (default); 1 = direct register -> global stores. EXPERIMENTAL:
-                               // +1.3 % on the step but an intermittent mismatch (one warp's 32x16 block of one launch in ~100) on
-                               // multi-tile CTAs when the epilogue warps drift apart without the per-chunk barrier - not yet explained
-static int g_mn3d = 0;        // 1 = MN-major operands through one 3-D TMA box per k-chunk (GemmEpi::mn3d); cb_debug_gemm_mn3d
-static int g_pdl_late = 0;    // PDL trigger placement of the GEMM kernel (GemmEpi::pdl_late); cb_debug_gemm_pdl_late
+static int g_mn3d = 1;        // 1 (default) = MN-major operands through one 3-D TMA box per k-chunk (GemmEpi::mn3d); cb_debug_gemm_mn3d
 static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
@@ -869,28 +840,43 @@ static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default
 struct SmemPlan {
   int epi_bytes, n_cbuf, n_rbuf, kch, stages, chunk_bytes;
 };
-static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0) {
+constexpr int SMEM_LIMIT_OCC2 = 113 * 1024;   // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0, int occ = 1) {
   SmemPlan p;
+  const int limit = occ == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
   p.chunk_bytes = BM * BK * 2 + (bn / cg) * BK * 2;
   p.n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
   p.n_rbuf = 2;
   const int n_in = (has_res ? 1 : 0) + (has_aux ? 1 : 0);
-  auto epi_bytes_for = [&](int n_rbuf) { return p.n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in; };
+  auto epi_bytes_for = [&](int n_cbuf, int n_rbuf) { return n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in; };
+  auto fit = [&](int n_cbuf, int n_rbuf) { return (limit - 1024 - 256 - epi_bytes_for(n_cbuf, n_rbuf)) / p.chunk_bytes; };
   if (tma_epi) {
-    // short K loops (the HBM-bound 1x1 convs) need little operand ring: spend the smem on a deeper residual / aux ring instead
-    // (4 x 16 KB per tensor in flight per SM against the ~2 us loaded HBM latency)
-    if (n_in > 0 && kiters <= 2 && (SMEM_LIMIT - 1024 - 256 - epi_bytes_for(4)) / p.chunk_bytes >= kiters + 1) p.n_rbuf = 4;
-    p.epi_bytes = epi_bytes_for(p.n_rbuf);
+    if (occ == 2) {
+      // half the shared memory: give up output / residual buffers (the co-resident CTA covers the exposed latency) until a
+      // two-chunk operand ring fits
+      static const int tries[4][2] = {{2, 2}, {1, 2}, {1, 1}, {1, 1}};
+      for (int t = 0; t < 3; ++t) {
+        p.n_cbuf = tries[t][0];
+        p.n_rbuf = tries[t][1];
+        if (fit(p.n_cbuf, p.n_rbuf) >= 2) break;
+      }
+    } else if (n_in > 0 && kiters <= 2 && fit(p.n_cbuf, 4) >= kiters + 1) {
+      // short K loops (the HBM-bound 1x1 convs) need little operand ring: spend the smem on a deeper residual / aux ring instead
+      // (4 x 16 KB per tensor in flight per SM against the ~2 us loaded HBM latency)
+      p.n_rbuf = 4;
+    }
+    p.epi_bytes = epi_bytes_for(p.n_cbuf, p.n_rbuf);
   } else {
     p.epi_bytes = (8 * STG_BYTES + 1023) & ~1023;     // staged epilogue: always 8 warps
   }
-  const int chunks_fit = (SMEM_LIMIT - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
+  const int chunks_fit = (limit - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
   p.kch = 1;
   if (force_kch > 0) p.kch = force_kch;
   else if (g_force_kch > 0) p.kch = g_force_kch;
   else if (kiters >= 4 && chunks_fit >= 8) p.kch = 4;
   else if (kiters >= 2 && chunks_fit >= 4) p.kch = 2;
   if (p.kch > kiters) p.kch = kiters;
+  if (p.kch > 1 && chunks_fit / p.kch < 2) p.kch = 1;
   p.stages = chunks_fit / p.kch;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int stage_iters = ceil_div(kiters, p.kch);
@@ -898,49 +884,47 @@ static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_a
   return p;
 }
 
-template <int BN, int MODE, int EPI, int CG, int EW = 8>
+template <int BN, int MODE, int EPI, int CG, int EW = 8, int OCC = 1>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_t stream) {
   GemmEpi epi = epi_in;
   using Cfg = GemmCfg<BN, CG>;
   constexpr int GEMM_THREADS = gemm_threads(EW);
+  constexpr int LIMIT = OCC == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE, EPI, CG, EW>;
+  auto kern = gemm_kernel<BN, MODE, EPI, CG, EW, OCC>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LIMIT);
+    if (e == cudaSuccess && OCC == 2)   // both CTAs of an SM need their 113 KB: ask for the full shared-memory carve-out
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", SMEM_LIMIT, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(smem=%d): %s", LIMIT, cudaGetErrorString(e));
       return CB_ERR_CUDA;
     }
     attr_set = true;
   }
-  const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr, *tx = nullptr, *tc2 = nullptr;
+  // Tensor maps are copied out of the cache into this frame (and from here into the kernel's parameter space)
+  alignas(64) CUtensorMap ta, tb, tc, tr, tx, tc2;
   bool mn3d = false;
   int iters_per_split = 0;
   const int tiles_m = ceil_div(d.m, BM * CG), tiles_n = ceil_div(d.n, BN);
   int total = tiles_m * tiles_n;
   int kiters;
+  bool ok;
   if (MODE == 0) {
-    ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
-    tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN / CG);
+    ok = get_tmap_2d(&ta, d.a, d.k, d.a_rows, d.a_ld, BK, BM) &&
+         get_tmap_2d(&tb, d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN / CG);
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else if (MODE == 2) {
-    ta = get_tmap_2d(d.a, d.k, d.a_rows, d.a_ld, BK, BM);
-    mn3d = g_mn3d && CG == 1 && d.n % 64 == 0;
-    tb = mn3d ? get_tmap_3d_mn(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, BK, BN / 64) : nullptr;
-    if (!tb) {      // not asked for, or the driver refused the 3-D view: the 2-D boxes always work
-      mn3d = false;
-      tb = get_tmap_2d(d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
-    }
+    ok = get_tmap_2d(&ta, d.a, d.k, d.a_rows, d.a_ld, BK, BM);
+    mn3d = g_mn3d && CG == 1 && d.n % 64 == 0 &&
+           get_tmap_3d_mn(&tb, d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, BK, BN / 64);
+    // not asked for, or the driver refused the 3-D view: the 2-D boxes always work
+    if (!mn3d) ok = ok && get_tmap_2d(&tb, d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else {
-    mn3d = g_mn3d && CG == 1 && d.m % 64 == 0 && d.n % 64 == 0;
-    ta = mn3d ? get_tmap_3d_mn(d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) : nullptr;
-    tb = mn3d ? get_tmap_3d_mn(d.b, d.n, d.b_rows, d.b_ld, BK, BN / 64) : nullptr;
-    if (!ta || !tb) {
-      mn3d = false;
-      ta = get_tmap_2d(d.a, d.m, d.a_rows, d.a_ld, 64, BK);
-      tb = get_tmap_2d(d.b, d.n, d.b_rows, d.b_ld, 64, BK);
-    }
+    mn3d = g_mn3d && CG == 1 && d.m % 64 == 0 && d.n % 64 == 0 && get_tmap_3d_mn(&ta, d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) &&
+           get_tmap_3d_mn(&tb, d.b, d.n, d.b_rows, d.b_ld, BK, BN / 64);
+    ok = mn3d || (get_tmap_2d(&ta, d.a, d.m, d.a_rows, d.a_ld, 64, BK) && get_tmap_2d(&tb, d.b, d.n, d.b_rows, d.b_ld, 64, BK));
     const int kc = ceil_div(d.k, BK);
     int splits = d.split_k < 1 ? 1 : d.split_k;
     if (splits > kc) splits = kc;
@@ -949,31 +933,26 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
     total *= splits * d.ntaps;
     kiters = iters_per_split;
   }
-  if (!ta || !tb) return CB_ERR_CUDA;
+  if (!ok) return CB_ERR_CUDA;
+  tc = tr = tx = tc2 = ta;   // placeholders for the maps this launch does not use (a __grid_constant__ parameter must be a valid object)
   if (EPI == 1) {
-    if (d.rowmap == CB_ROWMAP_NONE) tc = get_tmap_2d(d.out, d.n, d.m, d.out_ld, 64, BM);
-    else tc = ta;
-    if (d.residual) tr = get_tmap_2d(d.residual, d.n, d.m, d.res_ld, 64, BM);
-    if (d.aux) tx = get_tmap_2d(d.aux, d.n, d.m, d.aux_ld, 64, BM);
-    if (d.out2) tc2 = get_tmap_2d(d.out2, d.n, d.m, d.out2_ld, 64, BM);
-    if (!tc || (d.residual && !tr) || (d.aux && !tx) || (d.out2 && !tc2)) return CB_ERR_CUDA;
+    if (d.rowmap == CB_ROWMAP_NONE && !get_tmap_2d(&tc, d.out, d.n, d.m, d.out_ld, 64, BM)) return CB_ERR_CUDA;
+    if (d.residual && !get_tmap_2d(&tr, d.residual, d.n, d.m, d.res_ld, 64, BM)) return CB_ERR_CUDA;
+    if (d.aux && !get_tmap_2d(&tx, d.aux, d.n, d.m, d.aux_ld, 64, BM)) return CB_ERR_CUDA;
+    if (d.out2 && !get_tmap_2d(&tc2, d.out2, d.n, d.m, d.out2_ld, 64, BM)) return CB_ERR_CUDA;
   }
-  if (!tc) tc = ta;   // unused placeholders (a __grid_constant__ parameter must still be a valid object)
-  if (!tr) tr = ta;
-  if (!tx) tx = ta;
-  if (!tc2) tc2 = ta;
   epi.mn3d = mn3d ? 1 : 0;
-  const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15);
+  const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15, OCC);
   const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, n_rbuf = sp.n_rbuf, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
-    set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B)", BN, epi_bytes);
+    set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B, %d CTA(s) per SM)", BN, epi_bytes, OCC);
     return CB_ERR_INVALID;
   }
   const int smem_bytes = stages * kch * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
-  const int units = sm_count() / CG;
+  const int units = sm_count() * OCC / CG;
   const int grid = (total < units ? total : units) * CG;
   if (CG == 1) {
-    launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+    launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
              iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -988,7 +967,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ta, *tb, *tc, *tr, *tx, *tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
                                        tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
     if (e != cudaSuccess) {
       set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
@@ -1011,16 +990,27 @@ struct LaunchCfg {
   int bn, cg, splits;
 };
 
-static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi) {
-  const int sms = sm_count();
+// Two CTAs per SM (the OCC = 2 instantiations: 128 x <=128 tiles, 8 epilogue warps, <= 113 KB of shared memory, 2 x BN <= 256
+// TMEM columns each). One CTA's prologue / epilogue / barrier round trips run under the other's main loop, a launch of the
+// dgrad chain and a wgrad launch of the side stream can share an SM, and an HBM-bound 1x1 conv keeps two operand + residual
+// rings in flight per SM. The price is operand traffic: a 128 x 128 tile needs 128 B/clk of L2 -> SM ingest for a full-rate
+// tensor pipe against ~70 B/clk measured, so the compute-bound convs stay on 128 x 256 tiles with one CTA per SM.
+//   g_occ2_mode: 0 = never, 1 = only launches that ask for it (cb_gemm_desc.reserved bit 5), 2 = every eligible launch whose
+//   work is at most g_occ2_max_gflop (0 = no limit).
+static int g_occ2_mode = 1;
+static double g_occ2_max_gflop = 0.0;
+
+static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi, int occ = 1) {
+  const int sms = sm_count() * occ;
   const int kc = ceil_div(d.k, BK);
   const bool wgrad = d.mode == CB_GEMM_WGRAD;
   static const int cand[5][2] = {{64, 1}, {128, 1}, {256, 1}, {128, 2}, {256, 2}};
-  LaunchCfg best = {64, 1, 1};
+  LaunchCfg best = {0, 1, 1};      // bn = 0: no candidate fits (only possible with occ = 2)
   double best_cost = 1e30;
   for (int c = 0; c < 5; ++c) {
     const int bn = cand[c][0], cg = cand[c][1];
     if (cg != (force_cg ? force_cg : 1)) continue;
+    if (occ == 2 && (cg != 1 || bn > 128)) continue;
     if (d.block_n && bn != d.block_n) continue;
     if (bn > 64 && d.n <= bn / 2) continue;               // mostly padding
     if (cg == 2 && d.m <= BM) continue;
@@ -1032,10 +1022,10 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi
       const int real_sp = wgrad ? ceil_div(kc, ips) : 1;
       const int64_t tiles = base * real_sp;
       const double rounds = static_cast<double>((tiles + units - 1) / units);
-      const SmemPlan pl = plan_smem(bn, cg, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15);
+      const SmemPlan pl = plan_smem(bn, cg, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15, occ);
       if (pl.stages < 2) continue;
-      // per stage: ~450-cycle barrier round trip + bytes at ~60 B/clk; per tile: epilogue (fp32 red.add / staged bf16 / TMA bf16)
-      const double stage_cost = 450.0 + pl.kch * pl.chunk_bytes / 60.0;
+      // per stage: ~450-cycle barrier round trip + bytes at ~60 B/clk (shared by the CTAs of an SM); per tile: epilogue (fp32 red.add / staged bf16 / TMA bf16)
+      const double stage_cost = 450.0 + pl.kch * pl.chunk_bytes / (60.0 / occ);
       const double epi = wgrad ? bn * 24.0 : (tma_epi ? bn * 12.0 : bn * 30.0);
       const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
       if (cost < best_cost) {
@@ -1054,9 +1044,11 @@ extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline =
 extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
 extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
 extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
-extern "C" void cb_debug_gemm_direct_store(int on) { cb::g_direct_store = on ? 1 : 0; }
 extern "C" void cb_debug_gemm_mn3d(int on) { cb::g_mn3d = on ? 1 : 0; }
-extern "C" void cb_debug_gemm_pdl_late(int on) { cb::g_pdl_late = on ? 1 : 0; }
+extern "C" void cb_debug_gemm_occ2(int mode, double max_gflop) {
+  cb::g_occ2_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  cb::g_occ2_max_gflop = max_gflop;
+}
 extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? (n < 2 ? 2 : n & ~1) : 0; }   // even: CTA pairs
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
@@ -1090,17 +1082,12 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.W = d.map_w;
   epi.seed = d.dropout_seed;
   epi.dbg = g_gemm_timeline;
-  epi.direct = g_direct_store;
-  epi.pdl_late = g_pdl_late;
   epi.mn3d = 0;
-  if (d.dropout_p > 0.0f) {
-    double t = static_cast<double>(d.dropout_p) * 4294967296.0;
-    epi.drop_thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
-    if (epi.drop_thresh == 0) epi.drop_thresh = 1;
-    epi.drop_inv_keep = 1.0f / (1.0f - d.dropout_p);
-  } else {
-    epi.drop_thresh = 0;
-    epi.drop_inv_keep = 1.0f;
+  {
+    const DropCfg dc = make_drop(d.dropout_p, d.dropout_seed);
+    epi.drop_thresh = dc.thresh;
+    epi.drop_inv_keep = dc.inv_keep;
+    epi.seed_off = dc.offset;
   }
 
   if (d.mode == CB_GEMM_TN || d.mode == CB_GEMM_NN) {
@@ -1121,6 +1108,15 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
                          (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (!d.out2 || (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0) &&
                          (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) &&
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
+    // two CTAs per SM (see g_occ2_mode): TMA epilogue only (the staged bf16 epilogue needs 168 registers)
+    const double gflop = 2.0e-9 * d.m * d.n * d.k * d.ntaps;
+    const bool want_occ2 = tma_epi && force_cg != 2 && (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
+                           ((d.reserved & 32) ? g_occ2_mode >= 1 : (g_occ2_mode == 2 && (g_occ2_max_gflop <= 0.0 || gflop <= g_occ2_max_gflop)));
+    if (want_occ2) {
+      const LaunchCfg l2 = choose_config(d, 1, tma_epi, 2);
+      if (l2.bn == 64) return nn ? launch_gemm<64, 2, 1, 1, 8, 2>(d, epi, stream) : launch_gemm<64, 0, 1, 1, 8, 2>(d, epi, stream);
+      if (l2.bn == 128) return nn ? launch_gemm<128, 2, 1, 1, 8, 2>(d, epi, stream) : launch_gemm<128, 0, 1, 1, 8, 2>(d, epi, stream);
+    }
     const LaunchCfg lc = choose_config(d, force_cg, tma_epi);
 #define CB_DISPATCH(BN_, CG_, EW_)                                                                                                  \
   return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_, EW_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))            \
@@ -1152,6 +1148,16 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(d.out_ld % 4 == 0, "cb_gemm(WGRAD): out_ld must be a multiple of 4");
     CB_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "cb_gemm(WGRAD): out must be 16-byte aligned");
     const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
+    const double gflop = 2.0e-9 * d.m * d.n * d.k * d.ntaps;
+    const bool want_occ2 = force_cg != 2 && (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
+                           ((d.reserved & 32) ? g_occ2_mode >= 1 : (g_occ2_mode == 2 && (g_occ2_max_gflop <= 0.0 || gflop <= g_occ2_max_gflop)));
+    if (want_occ2) {
+      const LaunchCfg l2 = choose_config(d, 1, false, 2);
+      cb_gemm_desc d2 = d;
+      d2.split_k = l2.splits;
+      if (l2.bn == 64) return launch_gemm<64, 1, 0, 1, 8, 2>(d2, epi, stream);
+      if (l2.bn == 128) return launch_gemm<128, 1, 0, 1, 8, 2>(d2, epi, stream);
+    }
     const LaunchCfg lc = choose_config(d, force_cg, false);
     cb_gemm_desc d2 = d;
     d2.split_k = lc.splits;

@@ -52,12 +52,12 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 }
 
 // 2D bf16 row-major tensor [rows, inner] (row pitch ld elements), 128B-swizzled boxes.
-// Cached by value; returns nullptr (and sets the error) on failure.
-const CUtensorMap* get_tmap_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
-                               uint32_t box_inner, uint32_t box_rows);
+// Cached; the encoded map is COPIED into *out (the caller owns its copy). Returns false (and sets the error) on failure.
+bool get_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_rows);
 
 // the same matrix as {64, rows, cols / 64}: one box = nblk swizzled [box_rows x 64] slabs (MN-major UMMA operands)
-const CUtensorMap* get_tmap_3d_mn(const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, uint32_t nblk);
+bool get_tmap_3d_mn(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, uint32_t nblk);
 
 #define CB_REQUIRE(cond, ...)        \
   do {                               \

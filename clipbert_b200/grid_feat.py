@@ -151,7 +151,6 @@ class GridFeatBackbone(nn.Module):
         self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
         self.stem_mode = "s2d"   # "s2d": space-to-depth implicit GEMM (no patch matrix); "im2col": patch gather + GEMM
-        self.overlap_shortcut = False   # forward: projection shortcuts on the side queue beside conv1 -> conv2 (off until measured)
         self._s2d_ld = 16        # 16: overlapping tensor-map rows; 64: explicit windows (set automatically if the driver refuses)
         self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
         # d2 FREEZE_AT: stem (1) and res2 (2) get no gradient
@@ -410,20 +409,10 @@ class GridFeatBackbone(nn.Module):
                 else:
                     xs = x_in
                 rows = n * hh * ww
-                sq = None
-                if blk.has_shortcut and self.overlap_shortcut:
-                    # the projection shortcut only meets the main branch again in conv3's epilogue: run it on the side queue
-                    # beside conv1 -> conv2 (whose grids leave SMs idle at 28x28 and below)
-                    sq = ops.SideQueue()
-                    sc = torch.empty(rows, blk.shortcut.cout, dtype=bf16, device=dev)
-                    sq.run(lambda: self._conv1x1(blk.shortcut, xs, rows, ops.ACT_NONE, out=sc), xs, sc)
-                else:
-                    sc = self._conv1x1(blk.shortcut, xs, rows, ops.ACT_NONE) if blk.has_shortcut else xs
+                sc = self._conv1x1(blk.shortcut, xs, rows, ops.ACT_NONE) if blk.has_shortcut else xs
                 a_pad = self._pad_get(n * (hh + 2) * (ww + 2), blk.mid, dev)
                 self._conv1x1(blk.conv1, xs, rows, ops.ACT_RELU, rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=a_pad)
                 b = self._conv3x3(blk.conv2, a_pad, n, hh, ww, ops.ACT_RELU)
-                if sq is not None:
-                    sq.join()
                 if last:
                     y = self._pad_get(n * (hh + 2) * (ww + 2), blk.cout, dev)
                     self._conv1x1(blk.conv3, b, rows, ops.ACT_RELU, residual=sc, rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=y)

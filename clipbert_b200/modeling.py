@@ -188,6 +188,7 @@ class _ClipBertHeadModel(nn.Module):
         self._dirty = True
         self._call_count = 0
         self._seed_base = None
+        self._drop_counter = None   # uint64 device word: the dropout stream position, advanced ON THE DEVICE once per training forward
         self._capture = None     # tests set this to a dict to receive per-layer activations
         self._pending_backward = 0
         self._grad_ready_hook = None
@@ -316,6 +317,18 @@ class _ClipBertHeadModel(nn.Module):
         self._call_count += 1
         return (self._seed_base + self._call_count * 1000003) & 0xFFFFFFFFFFFFFFFF
 
+    def _advance_dropout_stream(self, dev):
+        """The reference draws fresh masks at every call (nn.Dropout, transformers.py:170,222,295,375). The seed above is a
+        host value - a captured CUDA graph would bake it in and replay the same masks - so the stream position also lives in
+        device memory: one tiny kernel increments the model's counter and writes the new value to a per-call word; every
+        mask-drawing launch of this forward AND of its backward reads that word when it runs (ops.dropout_offset_bind).
+        Returns the per-call word."""
+        if self._drop_counter is None or self._drop_counter.device != dev:
+            self._drop_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        word = torch.empty(1, dtype=torch.int64, device=dev)
+        ops.dropout_offset_advance(self._drop_counter, word)
+        return word
+
     # ---- forward ----------------------------------------------------------------------------------
     def _run(self, text_input_ids, visual_inputs, text_input_mask, repeat_counts=None):
         """Returns fp32 logits (B', num_outputs). visual_inputs: (B or B', T, h, w, 768)."""
@@ -390,8 +403,10 @@ class _ClipBertHeadModel(nn.Module):
             gh, gw = n_keep, 1
             L = lt + n_keep
             M = nseq * L
+        drop_word = self._advance_dropout_stream(dev) if (p_h > 0 or p_a > 0) else None
+        ops.dropout_offset_bind(drop_word)
         st = dict(ids=ids, mask=mask, grid=grid, repeat=repeat, seed=seed, p_h=p_h, p_a=p_a, dims=(nseq, nvid, T, gh, gw, lt, L), layers=[],
-                  sample=sample)
+                  sample=sample, drop_word=drop_word)
         # ---- embeddings: [text ; visual] written straight into one (B', L, 768) buffer ----
         x = new(M, H)
         st["stats_t"] = new(nseq * lt, 2, dtype=f32)
@@ -515,6 +530,7 @@ class _ClipBertHeadModel(nn.Module):
         def new(*shape, dtype=bf16):
             return torch.empty(*shape, dtype=dtype, device=dev)
 
+        ops.dropout_offset_bind(st.get("drop_word"))       # regenerate exactly this forward's masks
         sq = ops.SideQueue()                               # wgrad GEMMs / bias sums run beside the dgrad chain
         dpre = self._head_backward(st, dout, nseq, H)      # grad w.r.t. pooler pre-activation
         pl = self._lin["pooler"]

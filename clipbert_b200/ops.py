@@ -24,6 +24,7 @@ _SIGS = {
     "cb_embed_visual_bwd": [_vp, _vp, _vp, _vp, _i] + [_vp] * 12 + [_i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_colsum": [_vp, _i64, _vp, _i, _i, _vp],
     "cb_dropout": [_vp, _vp, _i64, _f, _u64, _vp],
+    "cb_dropout_offset_advance": [_vp, _vp, _vp],
     "cb_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
@@ -94,26 +95,42 @@ def set_epi_warps(n):
     L.lib().cb_debug_gemm_epi_warps(int(n))
 
 
-def set_direct_store(on):
-    """Tuning hook: GEMM TMA-epilogue output path: 1 = direct register -> global stores, 0 = smem chunk + TMA store."""
-    L.lib().cb_debug_gemm_direct_store(int(bool(on)))
-
-
 def set_attention_flash(on):
-    """Forward attention of sequences longer than 64 tokens on the tensor-core online-softmax kernel (off by default until
-    verified on a B200; the CUDA-core kernel is the default for L > 64)."""
+    """Forward attention of sequences longer than 64 tokens: 1 (default) = tensor-core online-softmax kernel (2.1x on config 5,
+    profiles/r02_ab_runs.txt), 0 = the CUDA-core kernel."""
     L.lib().cb_debug_attention_flash(int(bool(on)))
 
 
 def set_mn3d(on):
-    """Tuning hook: MN-major GEMM operands (B of the dgrad mode, both operands of the wgrad mode) through ONE 3-D TMA box per
-    k-chunk instead of BN/64 2-D boxes (the single producer lane issues 2 instead of 5-6 TMA instructions per chunk)."""
+    """MN-major GEMM operands (B of the dgrad mode, both operands of the wgrad mode) through ONE 3-D TMA box per k-chunk
+    (default) instead of BN/64 2-D boxes (the single producer lane issues 2 instead of 5-6 TMA instructions per chunk)."""
     L.lib().cb_debug_gemm_mn3d(int(bool(on)))
 
 
-def set_pdl_late(on):
-    """Tuning hook (with set_pdl(1)): the GEMM kernel releases its dependents when a CTA starts its last tile instead of at entry."""
-    L.lib().cb_debug_gemm_pdl_late(int(bool(on)))
+def set_occ2(mode, max_gflop=0.0):
+    """Two GEMM CTAs per SM (128 x <=128 tiles, 8 epilogue warps, <= 113 KB smem each): 0 = never, 1 = only launches that ask
+    for it (tuning table / reserved bit 5), 2 = every eligible launch of at most ``max_gflop`` GFLOP (0 = no limit)."""
+    f = L.lib().cb_debug_gemm_occ2
+    f.argtypes = [ctypes.c_int, ctypes.c_double]
+    f.restype = None
+    f(int(mode), float(max_gflop))
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout stream position on the device (fresh masks under CUDA-graph replay)
+# ------------------------------------------------------------------------------------------------
+def dropout_offset_bind(word):
+    """Launches made after this call add the uint64 device word ``word`` (a 1-element int64 tensor; None unbinds), read when
+    they RUN, into their dropout seed - see cb_dropout_offset_bind."""
+    f = L.lib().cb_dropout_offset_bind
+    f.argtypes = [_vp]
+    f.restype = _c.c_int
+    f(None if word is None else word.data_ptr())
+
+
+def dropout_offset_advance(counter, snapshot=None):
+    """++counter on the device (stream-ordered, graph-capturable); snapshot <- the new value."""
+    _call("cb_dropout_offset_advance", _p(counter), _p(snapshot), _s())
 
 
 def set_sm_limit(n):

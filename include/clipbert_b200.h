@@ -46,6 +46,19 @@ int64_t cb_launch_count(void);
  * ordered cuDNN/cuBLAS/ATen kernels). */
 int cb_set_pdl(int enable);
 
+/* Dropout stream position in DEVICE memory. The reference draws a fresh mask at every nn.Dropout call
+ * (src/modeling/transformers.py:170,222,295,375; modeling.py:57,552). Here a mask is a pure function of
+ * (seed, element index) and every mask-drawing entry point takes the seed BY VALUE, so a captured CUDA graph would
+ * replay the same masks. cb_dropout_offset_bind(word) makes every launch issued AFTERWARDS (process-wide, until the
+ * next bind; NULL unbinds) read the 64-bit `word` on the device when it RUNS and use  seed + word * odd_constant
+ * instead of seed: the forward and the backward of one step bind the same word and regenerate the same masks, the
+ * next replay sees an advanced word and draws new ones. cb_dropout_offset_advance enqueues a one-thread kernel:
+ * ++*counter; if (snapshot) *snapshot = *counter - a step advances the model's counter once and binds the per-step
+ * snapshot, so a later step (or a second forward before this one's backward) cannot change the masks of this one.
+ * Keep decision of element e: 16-bit lane (e & 3) of splitmix64(seed, e >> 2) >= round(p * 65536). */
+int cb_dropout_offset_bind(const uint64_t* device_word);
+int cb_dropout_offset_advance(uint64_t* counter, uint64_t* snapshot, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Tensor-core contraction (tcgen05.mma, TMA operand staging, TMEM accumulators).
  *

@@ -56,7 +56,7 @@ def _ctx(*a, **k):
 
 @pytest.mark.parametrize("flags", [["--graph", "1", "--size", "128"],
                                    ["--graph", "0", "--prefetch", "0", "--fused_loss", "1", "--recast_in_step", "1", "--clip_batching", "0",
-                                    "--stem", "im2col", "--overlap_shortcut", "1", "--mn3d", "1", "--pdl_late", "1"]])
+                                    "--stem", "im2col", "--mn3d", "1", "--occ2", "2"]])
 def test_bench_control_flow_on_cpu(monkeypatch, capsys, flags):
     import bench
     from ops_emulator import emulated_ops

@@ -50,15 +50,17 @@ def test_gemm_nn_dgrad(cuda, shape, knob):
     assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
 
 
-@pytest.fixture(params=["tma_store", "tma_store_8warps"])
+@pytest.fixture(params=["tma_store", "tma_store_8warps", "two_ctas_per_sm"])
 def epilogue_variant(request):
-    """The GEMM's TMA-prefetch epilogue with 16 epilogue warps (default) and with 8 (the round-1a kernel). The
-    experimental direct register->global store path (ops.set_direct_store) is off by default and not covered here."""
+    """The GEMM's TMA-prefetch epilogue with 16 epilogue warps (default), with 8 (the round-1a kernel), and the
+    two-CTAs-per-SM instantiations (ops.set_occ2(2): 128 x <=128 tiles, 8 epilogue warps taking their 32 columns in two
+    passes, a single output chunk buffer when the shared-memory half is tight)."""
     ops = _ops()
-    ops.set_direct_store(0)
     ops.set_epi_warps(8 if request.param.endswith("8warps") else 16)
+    ops.set_occ2(2 if request.param == "two_ctas_per_sm" else 0)
     yield request.param
     ops.set_epi_warps(16)
+    ops.set_occ2(1)
 
 
 @pytest.mark.parametrize("staged", [0, STAGED, PAIR, PAIR | STAGED])
@@ -209,6 +211,69 @@ def test_gemm_dropout_is_a_pure_function_of_seed_and_index(cuda):
     y = torch.empty_like(x)
     ops.dropout(x, y, 0.1, 99)
     assert torch.equal(y != 0, keep)
+
+
+def test_dropout_stream_advances_on_the_device_under_graph_replay(cuda):
+    """The reference draws fresh masks at every call (transformers.py:170,222,295,375). Seeds are by-value kernel arguments,
+    so a captured graph would replay the same masks; the stream position therefore lives in a device word that the graph
+    advances (cb_dropout_offset_advance) and every mask consumer reads at run time (cb_dropout_offset_bind). Two replays must
+    differ, and within one replay the 'backward' consumers (LayerNorm backward, a second launch) must regenerate the masks of
+    the 'forward' consumers (GEMM epilogue, cb_dropout) - same word, same seed."""
+    ops = _ops()
+    M, N, K = 256, 768, 64
+    g = torch.Generator().manual_seed(8)
+    A, B = _rnd(g, M, K), _rnd(g, N, K, scale=0.1)
+    ones = torch.ones(M, N, device=cuda, dtype=torch.bfloat16)
+    gam = torch.ones(N, device=cuda)
+    stats = torch.zeros(M, 2, device=cuda)
+    stats[:, 1] = 1.0
+    counter = torch.zeros(1, dtype=torch.int64, device=cuda)
+    word = torch.zeros(1, dtype=torch.int64, device=cuda)
+    C = torch.zeros(M, N, device=cuda)
+    m_fwd, m_bwd, dx, dxd = (torch.empty_like(ones) for _ in range(4))
+
+    def step():
+        ops.dropout_offset_advance(counter, word)
+        ops.dropout_offset_bind(word)
+        ops.gemm(mode=ops.CB_GEMM_TN, m=M, n=N, k=K, a=A, a_rows=M, a_ld=K, b=B, b_rows=N, b_ld=K, out=C, out_ld=N, out_fp32=1,
+                 dropout_p=0.1, dropout_seed=99)
+        ops.dropout(ones, m_fwd, 0.1, 99)
+        ops.dropout(ones, m_bwd, 0.1, 99)                                       # a later launch of the same step: same mask
+        ops.layernorm_bwd(ones, ones, stats, gam, dx, dxd, None, None, None, 0.1, 99)
+        ops.dropout_offset_bind(None)
+
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            step()
+        masks = []
+        for _ in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+            keep = m_fwd != 0
+            assert torch.equal(keep, m_bwd != 0)                 # regenerated identically within the step
+            assert torch.equal(keep, C != 0)                     # GEMM epilogue: same (seed, word, index) -> same decision
+            assert torch.equal(dxd != 0, (dx != 0) & keep)       # LayerNorm backward's dropped copy
+            assert abs(float(keep.float().mean()) - 0.9) < 0.01
+            masks.append(keep.clone())
+        assert int(counter.item()) == 4                          # one eager warm-up step + three replays (capturing runs nothing)
+    finally:
+        ops.dropout_offset_bind(None)
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    # two different positions are independent draws: they agree on ~0.9^2 + 0.1^2 of the elements
+    agree = float((masks[0] == masks[1]).float().mean())
+    assert abs(agree - 0.82) < 0.02
+    # unbound launches are what they always were: a pure function of (seed, index)
+    y0, y1 = torch.empty_like(ones), torch.empty_like(ones)
+    ops.dropout(ones, y0, 0.1, 99)
+    ops.dropout(ones, y1, 0.1, 99)
+    assert torch.equal(y0, y1) and not torch.equal(y0 != 0, masks[0])
 
 
 def test_gemm_rejects_bad_arguments(cuda):

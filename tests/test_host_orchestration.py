@@ -143,7 +143,6 @@ def test_cnn_engine_forward_backward_on_emulated_ops(weights, stem):
     model = _clipbert(weights).train()
     cnn = model.cnn
     cnn.stem_mode = stem
-    cnn.overlap_shortcut = stem == "im2col"      # cover the side-queue variant of the projection shortcuts on one of the two runs
     x = synth.synth_images(1, 2, size=64, seed=6)
     sd = {k: (v.clone().requires_grad_(True) if (k.endswith(".weight") and "norm" not in k and k.startswith("cnn.")) else v)
           for k, v in weights.items()}

@@ -12,10 +12,7 @@ from util import TOL_GRAD, TOL_LOGITS, cosine, make_cfg, relerr
 
 pytestmark = pytest.mark.gpu
 
-# Kernels that are compiled in but OFF by default and have never run on hardware (fused loss, long-sequence tensor-core
-# attention, 3-D TMA operand boxes) are checked only when asked for: CB_EXPERIMENTAL=1 (tools/round2_first_call.sh sets it).
 # Everything else in this file exercises the default kernels through host logic that was validated on CPU.
-experimental = pytest.mark.skipif(not os.environ.get("CB_EXPERIMENTAL"), reason="off-by-default kernel, not yet run on a B200: set CB_EXPERIMENTAL=1")
 
 
 @pytest.fixture(scope="module")
@@ -145,7 +142,6 @@ def test_config3_four_clips_two_frames_clip_batched(cuda, weights):
     assert abs(float(loss) - float(loss_ref)) < 3e-3
 
 
-@experimental
 def test_fused_clip_lse_loss_kernel(cuda):
     """cb_clip_lse_loss (forward + backward of the "lse" clip aggregation, run_video_retrieval.py:404-422) against the oracle:
     fp32 in / fp32 out, so the tolerance is accumulation-order noise (fast-math exp / log: 1e-5 relative)."""
@@ -167,12 +163,11 @@ def test_fused_clip_lse_loss_kernel(cuda):
             assert abs(float(cb.clip_lse_loss(z.to(cuda), y.to(cuda))) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
 
 
-@experimental
 @pytest.mark.parametrize("dims", [(2, 69, 20), (2, 150, 100), (1, 521, 512), (3, 128, 64), (1, 65, 0)])
 def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
     """The mma.sync online-softmax forward for L > 64 (attn_tc_fwd_flash_kernel; 448 px frames L = 69, paragraph retrieval
     L = 521) against fp32 torch attention and against the CUDA-core kernel it replaces: context, saved log-sum-exp (the general
-    backward consumes it), and the same dropout stream. Off by default (ops.set_attention_flash) until this has passed."""
+    backward consumes it), and the same dropout stream. Default for L > 64 since it passed on a B200 (profiles/r02_ab_runs.txt)."""
     from clipbert_b200 import ops
     from util import TOL_BF16_OP
     nseq, L, lt = dims
@@ -194,7 +189,7 @@ def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
                 ops.attention_fwd(qkv, mask, ctx, lse, nseq, L, lt, heads, p, seed)
                 outs[(flash, p)] = (ctx, lse)
     finally:
-        ops.set_attention_flash(0)
+        ops.set_attention_flash(1)
     x = qkv.float().view(nseq, L, 3, heads, 64)
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     full = torch.cat([ref_mask, torch.ones(nseq, L - lt, dtype=torch.int64, device=cuda)], 1)
@@ -233,7 +228,6 @@ def test_forward_error_sits_at_the_bf16_noise_floor_of_the_reference_ops(cuda, w
 
 # Last on purpose: if the driver accepts the 3-D tensor map but the hardware disagrees with the layout, a TMA fault would poison
 # the CUDA context for every test after it.
-@experimental
 def test_gemm_mn_major_operands_through_3d_tma_boxes(cuda):
     """ops.set_mn3d(1): the MN-major operands of the dgrad (NN) and wgrad GEMMs arrive as one 3-D TMA box per k-chunk instead of
     BN/64 2-D boxes. Same bytes in the same shared-memory layout, so NN results must be bit-identical to the 2-D path and the
@@ -254,7 +248,7 @@ def test_gemm_mn_major_operands_through_3d_tma_boxes(cuda):
                 ops.set_mn3d(on)
                 outs.append(fn())
         finally:
-            ops.set_mn3d(0)
+            ops.set_mn3d(1)
         return outs
 
     # ---- NN (dgrad of Linear / 1x1 conv): out [M, N] = A [M, K] @ B [K, N] ----
