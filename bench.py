@@ -223,8 +223,6 @@ def run_b200(args):
 
     opt = None
     ops.set_pdl(args.pdl)
-    ops.set_epi_warps(args.epi_warps)
-    ops.set_cbuf(args.cbuf)
     if args.sm_limit:
         ops.set_sm_limit(args.sm_limit)
     ops.set_mn3d(args.mn3d)
@@ -525,7 +523,7 @@ def run_b200(args):
                                "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem, epi_warps=args.epi_warps,
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
                                fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
@@ -639,8 +637,6 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
-    ap.add_argument("--cbuf", type=int, default=0, choices=[0, 2, 4], help="TMA-store chunk buffers of the GEMM epilogue (0 = library default)")
-    ap.add_argument("--epi_warps", type=int, default=16, choices=[8, 16], help="epilogue warps of the GEMM's TMA epilogue")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
     ap.add_argument("--prefetch", type=int, default=1, help="e2e: upload batch i+1 on a copy stream while batch i computes (0: copy on the compute stream)")

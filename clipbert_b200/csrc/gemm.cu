@@ -52,49 +52,136 @@ struct GemmEpi {
   float drop_inv_keep;
   uint64_t seed;
   const uint64_t* seed_off;   // device word folded into the seed at run time (cb_dropout_offset_bind), or nullptr
+  int shift_smem;   // TMA epilogue: the 64 shift values of every output chunk travel through shared memory (1-D bulk copy by the
+                    // loader warp, 256 B per residual-ring slot) instead of four __ldg per 16 columns: those loads sat on the
+                    // critical path of every chunk at full L2 latency (~700 cycles, profiles/r02e_gemm_cta_timeline_lean_epilogue.txt)
   int mn3d;         // MN-major operands (B of NN mode, A and B of WGRAD mode) arrive as ONE 3-D TMA box per k-chunk instead of
                     // BN/64 (BM/64) 2-D boxes: tmA / tmB are then the {64, rows, cols/64} maps of get_tmap_3d_mn (CG = 1 only)
-  long long* dbg;   // optional in-kernel clock64 timeline of CTA 0 (bring-up / tuning only; NULL in production)
+  long long* dbg;   // optional in-kernel clock64 timeline, 16 slots per CTA (bring-up / tuning only; NULL in production)
 };
 
+// bring-up / tuning only: clock64 stamps of EVERY CTA (32 slots per CTA; slots 12 / 13 = %globaltimer at entry / exit so that
+// the per-SM cycle counters can be laid on one time axis)
 __device__ __forceinline__ void dbg_stamp(const GemmEpi& epi, int slot) {
-  if (epi.dbg && blockIdx.x == 0) epi.dbg[slot] = clock64();
+  if (epi.dbg) {
+    epi.dbg[blockIdx.x * 32 + slot] = clock64();
+    if (slot == 0 || slot == 11) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      epi.dbg[blockIdx.x * 32 + (slot == 0 ? 12 : 13)] = static_cast<long long>(ns);
+    }
+  }
 }
 
-template <int BN, int CG>
+template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // a CTA pair (CG = 2) splits the B tile: each CTA stages N/2 rows
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages
 };
 
-// fused elementwise epilogue on 32 consecutive columns [nb, nb+32) of one output row
+// ---- epilogue arithmetic on NC consecutive columns [nb, nb+NC) of one output row ------------------------------------------------
+// shv[] holds the NC shift values (bias / FrozenBN shift) of these columns when has_shift. One function per epilogue KIND of the
+// step: the kind is fixed per launch and selected by ONE uniform branch per 16 columns - a single generic body with run-time
+// tests of every optional stage was if-converted by the compiler into straight-line code that evaluated gelu / gelu' / tanh
+// under predicates for every element whatever the launch asked for (~2.4 k cycles per 16 columns for a bare multiply).
+enum { EK_GENERIC = 0, EK_SHIFT_ACT = 1, EK_RELU_MASK = 2, EK_DROP_RES = 3, EK_GELU_STASH = 4, EK_AUX_MUL = 5 };
+
 template <int NC>
-__device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi, uint64_t dseed, int nb, int N, int64_t orow,
-                                              const uint32_t* res16, const uint32_t* aux16, uint32_t* o2_16) {
-  if (nb >= N) return;
+__device__ __forceinline__ void add_shift(float (&f)[NC], const float (&shv)[NC]) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) f[j] += shv[j];
+}
+template <int NC>
+__device__ __forceinline__ void add_residual(float (&f)[NC], const uint32_t (&res16)[NC / 2]) {
+#pragma unroll
+  for (int j = 0; j < NC / 2; ++j) {
+    const float2 r2 = unpack_bf16x2(res16[j]);
+    f[2 * j] += r2.x;
+    f[2 * j + 1] += r2.y;
+  }
+}
+//   EK_SHIFT_ACT : v = v (+ shift) (+ residual) -> ReLU / none      conv + FrozenBN shift (+ shortcut), Linear + bias, plain dgrad (+ residual)
+template <int NC>
+__device__ __forceinline__ void epilogue_shift_act(float (&f)[NC], const float (&shv)[NC], bool has_shift, const uint32_t (&res16)[NC / 2], bool has_res,
+                                                   bool relu) {
+  if (has_shift) add_shift<NC>(f, shv);
+  if (has_res) add_residual<NC>(f, res16);
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+}
+//   EK_RELU_MASK : v = (v (+ residual)) * (aux > 0)                dgrad through a ReLU (CB_AUX_RELU_MASK)
+template <int NC>
+__device__ __forceinline__ void epilogue_relu_mask(float (&f)[NC], const uint32_t (&res16)[NC / 2], bool has_res, const uint32_t (&aux16)[NC / 2]) {
+  if (has_res) add_residual<NC>(f, res16);
+#pragma unroll
+  for (int j = 0; j < NC / 2; ++j) {     // bf16 > 0  <=>  sign bit clear and magnitude non-zero, tested on the packed halves
+    const uint32_t a = aux16[j];
+    f[2 * j] = ((a & 0x8000u) == 0u && (a & 0x7fffu) != 0u) ? f[2 * j] : 0.0f;
+    f[2 * j + 1] = ((a & 0x80000000u) == 0u && (a & 0x7fff0000u) != 0u) ? f[2 * j + 1] : 0.0f;
+  }
+}
+//   EK_DROP_RES  : v = dropout(v + shift) + residual               BertSelfOutput / BertOutput dense (transformers.py:297-301,377-381)
+template <int NC>
+__device__ __forceinline__ void epilogue_drop_res(float (&f)[NC], const float (&shv)[NC], bool has_shift, const uint32_t (&res16)[NC / 2], bool has_res,
+                                                  uint64_t dseed, uint64_t didx, uint32_t thresh, float inv_keep) {
+  if (has_shift) add_shift<NC>(f, shv);
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {       // didx is a multiple of 4 (N % 8 == 0, 16-column runs): one hash per four columns
+    float m[4];
+    dropout_mult4(dseed, didx + j, thresh, inv_keep, m);
+    f[j] *= m[0]; f[j + 1] *= m[1]; f[j + 2] *= m[2]; f[j + 3] *= m[3];
+  }
+  if (has_res) add_residual<NC>(f, res16);
+}
+//   EK_GELU_STASH: out = gelu(v + shift), out2 = gelu'(v + shift)  BertIntermediate (transformers.py:363-366) with the derivative stashed
+template <int NC>
+__device__ __forceinline__ void epilogue_gelu_stash(float (&f)[NC], const float (&shv)[NC], bool has_shift, uint32_t (&o2_16)[NC / 2]) {
+  if (has_shift) add_shift<NC>(f, shv);
+#pragma unroll
+  for (int j = 0; j < NC / 2; ++j) {
+    float y0, g0, y1, g1;
+    gelu_erf_and_grad(f[2 * j], y0, g0);
+    gelu_erf_and_grad(f[2 * j + 1], y1, g1);
+    f[2 * j] = y0;
+    f[2 * j + 1] = y1;
+    o2_16[j] = pack_bf16x2(g0, g1);
+  }
+}
+//   EK_AUX_MUL   : v = (v (+ residual)) * aux                      dgrad through the stashed gelu'
+template <int NC>
+__device__ __forceinline__ void epilogue_aux_mul(float (&f)[NC], const uint32_t (&res16)[NC / 2], bool has_res, const uint32_t (&aux16)[NC / 2]) {
+  if (has_res) add_residual<NC>(f, res16);
+#pragma unroll
+  for (int j = 0; j < NC / 2; ++j) {
+    const float2 a2 = unpack_bf16x2(aux16[j]);
+    f[2 * j] *= a2.x;
+    f[2 * j + 1] *= a2.y;
+  }
+}
+//   EK_GENERIC   : every optional stage under run-time tests (heads, pooler tanh, ragged N): rare and tiny launches. GUARD: N is
+//   not a multiple of 64, the per-column scale vector is read under per-float4 column checks (out-of-range outputs are dropped
+//   by the caller). The activation / aux alternatives sit in separate switch arms so that only the requested one executes.
+template <int NC, bool GUARD>
+__device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi, const float (&shv)[NC], bool has_shift, uint64_t dseed, int nb, int N,
+                                              int64_t orow, const uint32_t (&res16)[NC / 2], bool has_res, const uint32_t (&aux16)[NC / 2], bool has_aux,
+                                              uint32_t (&o2_16)[NC / 2], bool has_out2) {
+  if (GUARD && nb >= N) return;
   if (epi.scale) {
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
-      if (nb + j + 4 <= N) {
+      if (!GUARD || nb + j + 4 <= N) {
         const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.scale + nb + j));
         f[j] *= s4.x; f[j + 1] *= s4.y; f[j + 2] *= s4.z; f[j + 3] *= s4.w;
       }
     }
   }
-  if (epi.shift) {
-#pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-      if (nb + j + 4 <= N) {
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
-        f[j] += s4.x; f[j + 1] += s4.y; f[j + 2] += s4.z; f[j + 3] += s4.w;
-      }
-    }
-  }
+  if (has_shift) add_shift<NC>(f, shv);
   if (epi.drop_thresh) {
-    // N % 8 == 0 and nb % 16 == 0: the run starts on a 4-element group boundary -> one hash per four columns
     const uint64_t base = static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb;
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
@@ -103,14 +190,7 @@ __device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi
       f[j] *= m[0]; f[j + 1] *= m[1]; f[j + 2] *= m[2]; f[j + 3] *= m[3];
     }
   }
-  if (res16) {
-#pragma unroll
-    for (int j = 0; j < NC / 2; ++j) {
-      const float2 r2 = unpack_bf16x2(res16[j]);
-      f[2 * j] += r2.x;
-      f[2 * j + 1] += r2.y;
-    }
-  }
+  if (has_res) add_residual<NC>(f, res16);
   if (epi.act == CB_ACT_GELU_STASH_GRAD) {      // out = gelu(v), out2 = gelu'(v): one erf for both
 #pragma unroll
     for (int j = 0; j < NC / 2; ++j) {
@@ -119,83 +199,63 @@ __device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi
       gelu_erf_and_grad(f[2 * j + 1], y1, g1);
       f[2 * j] = y0;
       f[2 * j + 1] = y1;
-      if (o2_16) o2_16[j] = pack_bf16x2(g0, g1);
+      if (has_out2) o2_16[j] = pack_bf16x2(g0, g1);
     }
-  } else if (o2_16) {
+  } else if (has_out2) {
 #pragma unroll
     for (int j = 0; j < NC / 2; ++j) o2_16[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
   }
-  if (epi.act == CB_ACT_RELU) {
+  switch (epi.act) {
+    case CB_ACT_RELU:
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
-  } else if (epi.act == CB_ACT_GELU) {
+      for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
+      break;
+    case CB_ACT_GELU:
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = gelu_erf(f[j]);
-  } else if (epi.act == CB_ACT_TANH) {
+      for (int j = 0; j < NC; ++j) f[j] = gelu_erf(f[j]);
+      break;
+    case CB_ACT_TANH:
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = tanhf(f[j]);
+      for (int j = 0; j < NC; ++j) f[j] = tanhf(f[j]);
+      break;
+    default: break;
   }
-  if (aux16) {
+  if (has_aux) {
+    switch (epi.aux_mode) {
+      case CB_AUX_RELU_MASK:
 #pragma unroll
-    for (int j = 0; j < NC / 2; ++j) {
-      const float2 a2 = unpack_bf16x2(aux16[j]);
-      if (epi.aux_mode == CB_AUX_RELU_MASK) {
-        f[2 * j] = a2.x > 0.0f ? f[2 * j] : 0.0f;
-        f[2 * j + 1] = a2.y > 0.0f ? f[2 * j + 1] : 0.0f;
-      } else if (epi.aux_mode == CB_AUX_GELU_GRAD) {
-        f[2 * j] *= gelu_erf_grad(a2.x);
-        f[2 * j + 1] *= gelu_erf_grad(a2.y);
-      } else if (epi.aux_mode == CB_AUX_TANH_GRAD) {
-        f[2 * j] *= (1.0f - a2.x * a2.x);
-        f[2 * j + 1] *= (1.0f - a2.y * a2.y);
-      } else if (epi.aux_mode == CB_AUX_MUL) {
-        f[2 * j] *= a2.x;
-        f[2 * j + 1] *= a2.y;
-      }
+        for (int j = 0; j < NC / 2; ++j) {
+          const float2 a2 = unpack_bf16x2(aux16[j]);
+          f[2 * j] = a2.x > 0.0f ? f[2 * j] : 0.0f;
+          f[2 * j + 1] = a2.y > 0.0f ? f[2 * j + 1] : 0.0f;
+        }
+        break;
+      case CB_AUX_GELU_GRAD:
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) {
+          const float2 a2 = unpack_bf16x2(aux16[j]);
+          f[2 * j] *= gelu_erf_grad(a2.x);
+          f[2 * j + 1] *= gelu_erf_grad(a2.y);
+        }
+        break;
+      case CB_AUX_TANH_GRAD:
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) {
+          const float2 a2 = unpack_bf16x2(aux16[j]);
+          f[2 * j] *= (1.0f - a2.x * a2.x);
+          f[2 * j + 1] *= (1.0f - a2.y * a2.y);
+        }
+        break;
+      case CB_AUX_MUL:
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) {
+          const float2 a2 = unpack_bf16x2(aux16[j]);
+          f[2 * j] *= a2.x;
+          f[2 * j + 1] *= a2.y;
+        }
+        break;
+      default: break;
     }
-  }
-}
-
-// Specialised epilogues for the two shapes that carry most of the CNN traffic. The generic epilogue_math costs ~230
-// instructions per 16 columns (runtime tests of every optional stage, per-float4 column guards, constant-bank reloads); the
-// HBM-bound 1x1 convs were issue-bound on exactly that (ncu: 49 % issue utilisation, ALU pipe 42 %, profiles/r01c).
-//   A: v = v + shift[n] (+ residual) -> ReLU / none          conv + FrozenBN shift (+ shortcut) of the forward pass, Linear + bias
-//   B: v = (v (+ residual)) * (aux > 0)                      dgrad through a ReLU (CB_AUX_RELU_MASK)
-template <int NC>
-__device__ __forceinline__ void epilogue_shift_act(float (&f)[NC], const float* __restrict__ shift, const uint32_t* res16, bool relu) {
-#pragma unroll
-  for (int j = 0; j < NC; j += 4) {
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(shift + j));
-    f[j] += s4.x; f[j + 1] += s4.y; f[j + 2] += s4.z; f[j + 3] += s4.w;
-  }
-  if (res16) {
-#pragma unroll
-    for (int j = 0; j < NC / 2; ++j) {
-      const float2 r2 = unpack_bf16x2(res16[j]);
-      f[2 * j] += r2.x;
-      f[2 * j + 1] += r2.y;
-    }
-  }
-  if (relu) {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
-  }
-}
-template <int NC>
-__device__ __forceinline__ void epilogue_relu_mask(float (&f)[NC], const uint32_t* res16, const uint32_t* aux16) {
-  if (res16) {
-#pragma unroll
-    for (int j = 0; j < NC / 2; ++j) {
-      const float2 r2 = unpack_bf16x2(res16[j]);
-      f[2 * j] += r2.x;
-      f[2 * j + 1] += r2.y;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NC / 2; ++j) {     // bf16 > 0  <=>  sign bit clear and magnitude non-zero, tested on the packed halves
-    const uint32_t a = aux16[j];
-    f[2 * j] = ((a & 0x8000u) == 0u && (a & 0x7fffu) != 0u) ? f[2 * j] : 0.0f;
-    f[2 * j + 1] = ((a & 0x80000000u) == 0u && (a & 0x7fff0000u) != 0u) ? f[2 * j + 1] : 0.0f;
   }
 }
 
@@ -210,17 +270,16 @@ struct TileInfo {
 };
 
 // tile index -> coordinates; n-tiles are fastest so that concurrently running CTAs share the A rows.
-// With CG = 2 a "tile" is the 256 x BN tile of a CTA pair: m0 is THIS CTA's 128-row half, nb0 its half of the B rows.
-template <int BN, int MODE, int CG>
-__device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles_n, int K, int ntaps, int iters_per_split, int rank) {
+template <int BN, int MODE>
+__device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles_n, int K, int ntaps, int iters_per_split) {
   TileInfo t;
   const int nt = tile % tiles_n;
   int r = tile / tiles_n;
   const int mt = r % tiles_m;
   r /= tiles_m;
-  t.m0 = mt * (BM * CG) + rank * BM;
+  t.m0 = mt * BM;
   t.n0 = nt * BN;
-  t.nb0 = t.n0 + rank * (BN / CG);
+  t.nb0 = t.n0;
   const int kc = (K + BK - 1) / BK;
   if (MODE == 1) {
     t.tap = r % ntaps;
@@ -235,19 +294,19 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles
   return t;
 }
 
-template <int BN, int MODE, int EPI, int CG, int EW, int OCC>
+template <int BN, int MODE, int EPI, int EW, int OCC>
 __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
                 int tap_w, int tap_sign,
                 int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, int n_rbuf, GemmEpi epi) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN>;
   constexpr int EPI_WARPS = EW;
   constexpr int EPI_THREADS = EW * 32;
   constexpr int NGRP = EW / 4;                  // warps sharing one TMEM lane quarter
-  static_assert(EW == 8 || (EW == 16 && EPI == 1), "16 epilogue warps only with the TMA epilogue");
-  static_assert(OCC == 1 || (OCC == 2 && CG == 1 && EW == 8 && BN <= 128), "two CTAs per SM: single-CTA tiles, 8 epilogue warps, 2 x BN <= 256 TMEM columns");
+  static_assert(EPI == 0 ? EW == 8 : (OCC == 1 ? EW == 16 : EW == 8), "TMA epilogue: 16 epilogue warps (8 with two CTAs per SM); staged epilogue: 8");
+  static_assert(OCC == 1 || (OCC == 2 && BN <= 128), "two CTAs per SM: 2 x BN <= 256 TMEM columns each");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = KCH * Cfg::STAGE_BYTES;           // a stage holds KCH consecutive 64-deep k-chunks (one barrier round trip)
@@ -262,9 +321,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader of the CTA pair
-  const int unit = blockIdx.x / CG;                                     // persistent work unit (CTA or CTA pair)
-  const int n_units = gridDim.x / CG;
+  const int unit = blockIdx.x;                                          // persistent work unit
+  const int n_units = gridDim.x;
   if (threadIdx.x == 0) dbg_stamp(epi, 0);   // (debug-only buffer, not produced by any kernel: safe before pdl_wait)
   pdl_trigger();   // PDL: let the next kernel's CTAs take this SM as soon as this CTA leaves it
   if (threadIdx.x == 0) {
@@ -277,12 +335,12 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
       if (epi.aux) tma_prefetch_desc(&tmX);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CG);            // one arrive.expect_tx per CTA of the pair (only the leader's copy is used)
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS * CG);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&rfull_bar[s], 1);
@@ -291,12 +349,10 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
-    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
-  if (CG == 2) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kc_per_tap = (K + BK - 1) / BK;
@@ -312,21 +368,16 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     // operands, so divergent per-lane operands are serialised through a per-lane uniform-register loop.)
     if (lane == 0) {
       constexpr int A_BOXES = (MODE == 1) ? BM / 64 : 1;
-      constexpr int B_BOXES = (MODE == 0) ? 1 : BN / CG / 64;
+      constexpr int B_BOXES = (MODE == 0) ? 1 : BN / 64;
       int s = 0;        // smem ring position / phase, carried across tiles
       uint32_t ph = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         for (int i = 0; i < t.n_iters; i += KCH) {
           const int nch = min(KCH, t.n_iters - i);
-          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[s]), 0) : 0u;   // pair: bytes are credited to the LEADER
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (CG == 2) mbar_expect_tx_cluster(fb, nch * Cfg::STAGE_BYTES);
-          else mbar_expect_tx(&full_bar[s], nch * Cfg::STAGE_BYTES);
-          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
-            if (CG == 2) tma_load_2d_2sm(dst, map, fb, c0, c1);
-            else tma_load_2d(dst, map, &full_bar[s], c0, c1);
-          };
+          mbar_expect_tx(&full_bar[s], nch * Cfg::STAGE_BYTES);
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) { tma_load_2d(dst, map, &full_bar[s], c0, c1); };
           // the producer thread is issue-bound: per-chunk index math is done once, box loops are fully unrolled
           int kit = t.it_begin + i;
           int tp = 0, kc = kit;
@@ -338,7 +389,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
               int shift = 0;
               if (ntaps == 9) shift = tap_sign * ((t.tap / 3 - 1) * tap_w + (t.tap % 3 - 1));
               const int p = kit * BK;
-              if (CG == 1 && epi.mn3d) {
+              if (epi.mn3d) {
                 tma_load_3d(sa, &tmA, &full_bar[s], 0, p, t.m0 >> 6);
                 tma_load_3d(sb, &tmB, &full_bar[s], 0, p + shift, t.nb0 >> 6);
               } else {
@@ -354,7 +405,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
               load(sa, &tmA, kc * BK, t.m0 + shift);
               if (MODE == 0) {
                 load(sb, &tmB, tp * K + kc * BK, t.nb0);
-              } else if (CG == 1 && epi.mn3d) {
+              } else if (epi.mn3d) {
                 tma_load_3d(sb, &tmB, &full_bar[s], 0, kc * BK, (tp * N + t.nb0) >> 6);
               } else {
 #pragma unroll
@@ -371,13 +422,13 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {              // only the leader CTA of a pair issues MMAs
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, MODE == 1, MODE != 0);
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MODE == 1, MODE != 0);
       int s = 0;
       uint32_t ph = 0;
       int local = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
@@ -399,17 +450,13 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
               if (MODE == 0) bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
               else bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
               const uint32_t accum = (i > 0 || ch > 0 || k > 0) ? 1u : 0u;
-              if (CG == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
-              else umma_bf16(d_tmem, ad, bd, idesc, accum);
+              umma_bf16(d_tmem, ad, bd, idesc, accum);
             }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
-          if (CG == 2) umma_commit_2sm(&empty_bar[s], 3);
-          else umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[s]);           // frees this smem stage once the MMAs have read it
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (CG == 2) umma_commit_2sm(&tfull_bar[acc], 3);   // accumulator complete (both halves)
-        else umma_commit(&tfull_bar[acc]);
+        umma_commit(&tfull_bar[acc]);         // accumulator complete
         if (local == 0) dbg_stamp(epi, 5);
       }
       dbg_stamp(epi, 6);
@@ -420,31 +467,32 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     // swizzled smem buffers, running ahead of the epilogue warps (rempty / rfull mbarriers). It used to be the elected
     // epilogue thread's job after every chunk barrier: ~200 serial single-thread instructions (tile decode, two TMA
     // issues) on the critical path of all sixteen epilogue warps, and a fixed look-ahead of two chunks.
-    if (EPI == 1 && lane == 0 && (epi.residual != nullptr || epi.aux != nullptr)) {
+    if (EPI == 1 && lane == 0 && (epi.residual != nullptr || epi.aux != nullptr || epi.shift_smem)) {
       constexpr int CPT = BN / 64;
-      const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr, has_out2 = epi.out2 != nullptr;
+      const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr, has_out2 = epi.out2 != nullptr, has_sh = epi.shift_smem != 0;
       uint8_t* rbuf = stg_base + n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1);
       uint8_t* xbuf = rbuf + (has_res ? n_rbuf * CHUNK_BYTES : 0);
+      const uint32_t sbuf32 = smem_u32(xbuf + (has_aux ? n_rbuf * CHUNK_BYTES : 0));   // [n_rbuf][64 floats] shift values of the chunk
       const uint32_t bytes = CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
       int g = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units) {
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         for (int c = 0; c < CPT; ++c, ++g) {
           const int b = g & (n_rbuf - 1);
           const uint32_t ph = (g / n_rbuf) & 1;
+          const int ncols = min(64, N - (t.n0 + c * 64));                  // N % 8 == 0: a multiple of 8 floats = 32 bytes
+          const uint32_t sbytes = (has_sh && ncols > 0) ? static_cast<uint32_t>(ncols) * 4u : 0u;
           mbar_wait(&rempty_bar[b], ph ^ 1);
-          mbar_expect_tx(&rfull_bar[b], bytes);
+          mbar_expect_tx(&rfull_bar[b], bytes + sbytes);
           if (has_res) tma_load_2d(rbuf + b * CHUNK_BYTES, &tmR, &rfull_bar[b], t.n0 + c * 64, t.m0);
           if (has_aux) tma_load_2d(xbuf + b * CHUNK_BYTES, &tmX, &rfull_bar[b], t.n0 + c * 64, t.m0);
+          if (sbytes) bulk_load_1d(sbuf32 + b * 256, epi.shift + t.n0 + c * 64, sbytes, &rfull_bar[b]);
         }
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    auto release_acc = [&](uint64_t* bar) {   // hand the accumulator stage back to the (leader's) MMA warp
-      if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
-      else mbar_arrive(bar);
-    };
+    auto release_acc = [&](uint64_t* bar) { mbar_arrive(bar); };   // hand the accumulator stage back to the MMA warp
     const uint64_t dseed = epi.drop_thresh ? drop_seed(epi.seed, epi.seed_off) : 0ull;   // after pdl_wait: the word is device data
     const int ew = warp - 3;          // 0 .. EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
@@ -452,65 +500,81 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
     int local = 0;
 
     if (EPI == 1) {
-      // ---------- TMA epilogue: rowmap NONE, bf16 output ----------
+      // ---------- TMA epilogue: bf16 output ----------
+      // The four warp groups of a TMEM lane quarter (32 output rows) form an independent unit: they own rows q*32 .. q*32+31
+      // of every 128 x 64 output chunk, synchronise among themselves (named barrier 1+q, 128 threads - not the whole CTA) and
+      // their first lane issues the TMA store of that 32-row slab. All shared-memory traffic goes through explicit 32-bit
+      // shared addresses (ld/st.shared.v4) whose per-thread swizzled offsets are computed ONCE: the first version indexed the
+      // buffers through generic pointers and spent ~250 instructions per 16 columns, most of them 64-bit address arithmetic -
+      // every GEMM of the step was bound by the ISSUE rate of its epilogue (profiles/r02c_gemm_cta_timeline.txt: 7.3 k cycles
+      // for a bias-only 128 x 256 tile against 6.1 k cycles of MMA).
       constexpr int CPT = BN / 64;                      // 64-column chunks per tile
-      uint8_t* cbuf = stg_base;                         // [n_cbuf][128 x 128 B] output chunks (n_cbuf = 2 or 4)
+      constexpr int NCW = 64 / NGRP;                    // columns of a chunk owned by this warp: 16 (16 warps) or 32 (8 warps)
+      constexpr int NC = 16;                            // ... worked off 16 at a time (one tcgen05.ld.x16)
+      constexpr int NSUB = NCW / NC;
+      constexpr int NUW = NCW / 8;                      // 16-byte units of a chunk row owned by this warp
+      constexpr int QT = NGRP * 32;                     // threads of one lane-quarter unit
       const bool has_out2 = epi.out2 != nullptr;        // pre-activation stash: a second set of output chunks
-      uint8_t* c2buf = cbuf + n_cbuf * CHUNK_BYTES;
-      uint8_t* rbuf = c2buf + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [n_rbuf] residual chunks (if any), filled by the loader warp
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
-      uint8_t* xbuf = rbuf + (has_res ? n_rbuf * CHUNK_BYTES : 0);     // [n_rbuf] aux chunks
-      const bool has_in = has_res || has_aux;
+      const bool has_shift = epi.shift != nullptr, sh_smem = epi.shift_smem != 0;
+      const bool has_in = has_res || has_aux || sh_smem;            // the loader warp fills a ring slot for every chunk
       const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: cooperative coalesced stores instead of TMA
-      const int etid = threadIdx.x - 96;                // index among the epilogue threads
-      const bool elected = (ew == 0 && lane == 0);
+      const uint32_t cbuf32 = smem_u32(stg_base);       // [n_cbuf][128 x 128 B] output chunks
+      const uint32_t c2buf32 = cbuf32 + n_cbuf * CHUNK_BYTES;
+      const uint32_t rbuf32 = c2buf32 + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [n_rbuf] residual chunks, filled by the loader warp
+      const uint32_t xbuf32 = rbuf32 + (has_res ? n_rbuf * CHUNK_BYTES : 0);     // [n_rbuf] aux chunks
+      const uint32_t sbuf32 = xbuf32 + (has_aux ? n_rbuf * CHUNK_BYTES : 0) + grp * (NCW * 4);   // [n_rbuf][64] shift values: this warp's columns
       const int row = q * 32 + lane;                    // row inside the 128-row tile
-      const int swz = row & 7;                          // 128B-swizzle XOR of this row
-      // epilogue kind, fixed for the launch (see epilogue_shift_act / epilogue_relu_mask)
-      const bool plain = epi.scale == nullptr && epi.drop_thresh == 0 && !has_out2 && (N & 63) == 0;
-      const int kind = !plain ? 0
-                     : (epi.shift != nullptr && !has_aux && (epi.act == CB_ACT_NONE || epi.act == CB_ACT_RELU)) ? 1
-                     : (epi.shift == nullptr && has_aux && epi.aux_mode == CB_AUX_RELU_MASK && epi.act == CB_ACT_NONE) ? 2 : 0;
+      const int qtid = grp * 32 + lane;                 // index inside the lane-quarter unit
+      const bool qlead = qtid == 0;
+      uint32_t off[NUW];                                // this thread's 16-byte units of a chunk row (128-byte swizzle applied)
+#pragma unroll
+      for (int j = 0; j < NUW; ++j) off[j] = row * 128 + (((grp * NUW + j) ^ (row & 7)) << 4);
+      // epilogue kind, fixed for the launch (see the EK_* functions)
+      const bool full = (N & 63) == 0 && epi.scale == nullptr;
+      const bool drop = epi.drop_thresh != 0;
+      int kind = EK_GENERIC;
+      if (full) {
+        if (!drop && !has_out2 && !has_aux && (epi.act == CB_ACT_NONE || epi.act == CB_ACT_RELU)) kind = EK_SHIFT_ACT;
+        else if (!drop && !has_out2 && !has_shift && has_aux && epi.aux_mode == CB_AUX_RELU_MASK && epi.act == CB_ACT_NONE) kind = EK_RELU_MASK;
+        else if (drop && !has_out2 && !has_aux && epi.act == CB_ACT_NONE) kind = EK_DROP_RES;
+        else if (!drop && has_out2 && !has_aux && !has_res && epi.act == CB_ACT_GELU_STASH_GRAD) kind = EK_GELU_STASH;
+        else if (!drop && !has_out2 && !has_shift && has_aux && epi.aux_mode == CB_AUX_MUL && epi.act == CB_ACT_NONE) kind = EK_AUX_MUL;
+      }
       const bool kind_relu = epi.act == CB_ACT_RELU;
+      const bool guard = (N & 63) != 0;                 // ragged last chunk: per-float4 column checks in the generic epilogue
       int g = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         const int64_t orow = t.m0 + row;
+        const int ncol0 = t.n0 + grp * NCW;             // this thread's first column of chunk 0
         mbar_wait(&tfull_bar[acc], acc_ph);
         tc_fence_after();
-        if (elected && local == 0) dbg_stamp(epi, 7);
-        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if (qlead && q == 3 && local == 0) dbg_stamp(epi, 7);      // (warp 3 = first epilogue warp)
+        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + grp * NCW;
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++g) {
-          // columns of a 64-column chunk owned by this thread: NCW = 32 (8 warps) or 16 (16 warps), worked off NC at a time:
-          // the two-CTAs-per-SM variant (OCC = 2: 88 registers per thread) takes its 32 columns in two passes of 16
-          constexpr int NCW = 64 / NGRP;
-          constexpr int NC = (OCC == 2 && NCW == 32) ? 16 : NCW;
-          constexpr int NSUB = NCW / NC;
-          constexpr int NU = NC / 8;                    // columns of one pass in 16-byte units
           const int b = g & (n_rbuf - 1);
           const uint32_t bph = (g / n_rbuf) & 1;
-          const int cb = g & (n_cbuf - 1);
-          uint8_t* cr = cbuf + cb * CHUNK_BYTES + row * 128;
-          uint8_t* c2r = c2buf + cb * CHUNK_BYTES + row * 128;
+          const uint32_t cboff = (g & (n_cbuf - 1)) * CHUNK_BYTES;
+          const bool stamp = epi.dbg != nullptr && qlead && q == 3 && local == 0;
+          if (stamp && c < 4) dbg_stamp(epi, 24 + c);            // chunk c of the first tile starts
           if (has_in) mbar_wait(&rfull_bar[b], bph);
-          if (n_cbuf == 1) {      // single output buffer: the previous chunk's TMA store (or cooperative copy) must be done with it
-            if (elected && !remap) tma_store_wait_read<0>();
+          if (n_cbuf == 1) {      // single output buffer: this unit's previous TMA store (or cooperative copy) must be done with it
+            if (qlead && !remap) tma_store_wait_read<0>();
             __syncwarp();
-            named_bar_sync(2, EPI_THREADS);
+            named_bar_sync(5 + q, QT);
           }
-#pragma unroll 1
+#pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
-            const int col0 = grp * NCW + sub * NC;      // first column of this pass inside the chunk
-            const int u0 = col0 >> 3;                   // ... as a 16-byte unit index of the 128-byte row
-            const int nb = t.n0 + c * 64 + col0;
+            const int nb = ncol0 + c * 64 + sub * NC;   // global column of f[0]
             uint32_t v[NC];
             __syncwarp();
-            if constexpr (NC == 32) tmem_ld32(trow + c * 64 + col0, reinterpret_cast<uint32_t(&)[32]>(v));
-            else tmem_ld16(trow + c * 64 + col0, reinterpret_cast<uint32_t(&)[16]>(v));
+            tmem_ld16(trow + c * 64 + sub * NC, v);
             tmem_ld_wait();
+            if (stamp && c == 0 && sub == 0) dbg_stamp(epi, 16);   // accumulator columns in registers
             if (c == CPT - 1 && sub == NSUB - 1) {      // last TMEM read of this tile
               tc_fence_before();
               __syncwarp();
@@ -518,22 +582,36 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
             }
             uint32_t res16[NC / 2], aux16[NC / 2];
             if (has_res) {
-              const uint8_t* rr = rbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
-              for (int j = 0; j < NU; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rr + (((u0 + j) ^ swz) << 4));
+              for (int j = 0; j < 2; ++j) {
+                const uint4 u = lds128(rbuf32 + b * CHUNK_BYTES + off[sub * 2 + j]);
                 res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
               }
             }
             if (has_aux) {
-              const uint8_t* xr = xbuf + b * CHUNK_BYTES + row * 128;
 #pragma unroll
-              for (int j = 0; j < NU; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(xr + (((u0 + j) ^ swz) << 4));
+              for (int j = 0; j < 2; ++j) {
+                const uint4 u = lds128(xbuf32 + b * CHUNK_BYTES + off[sub * 2 + j]);
                 aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
               }
             }
-            if (has_in && sub == NSUB - 1) {            // this warp has its residual / aux values in registers: hand the buffer back
+            float shv[NC];                              // shift (bias / FrozenBN shift) of these columns
+            if (sh_smem) {
+#pragma unroll
+              for (int j = 0; j < NC / 4; ++j) {        // every lane reads the same 16 bytes: a shared-memory broadcast
+                const uint4 u = lds128(sbuf32 + b * 256 + sub * (NC * 4) + j * 16);
+                shv[4 * j] = __uint_as_float(u.x); shv[4 * j + 1] = __uint_as_float(u.y);
+                shv[4 * j + 2] = __uint_as_float(u.z); shv[4 * j + 3] = __uint_as_float(u.w);
+              }
+            } else if (has_shift) {
+#pragma unroll
+              for (int j = 0; j < NC; j += 4) {
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!guard || nb + j + 4 <= N) s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
+                shv[j] = s4.x; shv[j + 1] = s4.y; shv[j + 2] = s4.z; shv[j + 3] = s4.w;
+              }
+            }
+            if (has_in && sub == NSUB - 1) {            // this warp has its residual / aux / shift values in registers: hand the slot back
               __syncwarp();
               if (lane == 0) mbar_arrive(&rempty_bar[b]);
             }
@@ -541,45 +619,56 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
 #pragma unroll
             for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
             uint32_t o2_16[NC / 2];
-            if (kind == 1) epilogue_shift_act<NC>(f, epi.shift + nb, has_res ? res16 : nullptr, kind_relu);
-            else if (kind == 2) epilogue_relu_mask<NC>(f, has_res ? res16 : nullptr, aux16);
-            else epilogue_math<NC>(f, epi, dseed, nb, N, orow, has_res ? res16 : nullptr, has_aux ? aux16 : nullptr, has_out2 ? o2_16 : nullptr);
+            switch (kind) {
+              case EK_SHIFT_ACT: epilogue_shift_act<NC>(f, shv, has_shift, res16, has_res, kind_relu); break;
+              case EK_RELU_MASK: epilogue_relu_mask<NC>(f, res16, has_res, aux16); break;
+              case EK_DROP_RES:
+                epilogue_drop_res<NC>(f, shv, has_shift, res16, has_res, dseed, static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb, epi.drop_thresh,
+                                      epi.drop_inv_keep);
+                break;
+              case EK_GELU_STASH: epilogue_gelu_stash<NC>(f, shv, has_shift, o2_16); break;
+              case EK_AUX_MUL: epilogue_aux_mul<NC>(f, res16, has_res, aux16); break;
+              default:
+                if (guard) epilogue_math<NC, true>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
+                else epilogue_math<NC, false>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
+            }
+            if (stamp && c == 0 && sub == 0) dbg_stamp(epi, 17);   // residual / aux read, epilogue math done
             if (has_out2) {
 #pragma unroll
-              for (int j = 0; j < NU; ++j)
-                *reinterpret_cast<uint4*>(c2r + (((u0 + j) ^ swz) << 4)) = make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]);
+              for (int j = 0; j < 2; ++j)
+                sts128(c2buf32 + cboff + off[sub * 2 + j], make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]));
             }
 #pragma unroll
-            for (int j = 0; j < NU; ++j)
-              *reinterpret_cast<uint4*>(cr + (((u0 + j) ^ swz) << 4)) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            for (int j = 0; j < 2; ++j)
+              sts128(cbuf32 + cboff + off[sub * 2 + j],
+                     make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
           }
+          if (stamp && c == 0) dbg_stamp(epi, 18);               // chunk written to shared memory
           if (!remap) {
             fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the TMA store
-            if (elected && n_cbuf > 1) {                // the buffer the NEXT chunk writes must be free again
-              if (n_cbuf == 4) tma_store_wait_read<2>();
-              else tma_store_wait_read<0>();
-            }
+            if (stamp && c == 0) dbg_stamp(epi, 19);
+            if (qlead && n_cbuf > 1) tma_store_wait_read<0>();   // the buffer the NEXT chunk writes must be free again
           }
+          if (stamp && c == 0) dbg_stamp(epi, 20);
           __syncwarp();
-          named_bar_sync(1, EPI_THREADS);
-          if (elected) {
-            if (!remap) {
-              tma_store_2d(&tmC, cbuf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
-              if (has_out2) tma_store_2d(&tmC2, c2buf + cb * CHUNK_BYTES, t.n0 + c * 64, t.m0);
+          named_bar_sync(1 + q, QT);
+          if (stamp && c == 0) dbg_stamp(epi, 21);
+          if (!remap) {
+            if (qlead) {                                // this unit's 32 rows x 64 columns
+              tma_store_2d_s32(&tmC, cbuf32 + cboff + q * 4096, t.n0 + c * 64, t.m0 + q * 32);
+              if (has_out2) tma_store_2d_s32(&tmC2, c2buf32 + cboff + q * 4096, t.n0 + c * 64, t.m0 + q * 32);
               tma_store_commit();
             }
-          }
-          if (remap) {
-            // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment,
-            // EPI_THREADS / 8 rows per pass; the buffer is rewritten two chunks later, after the next named barrier
-            const int seg = etid & 7;
+          } else {
+            // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment, QT / 8 rows
+            // per pass; with two buffers a buffer is rewritten two chunks later, after this unit's next named barrier
+            const int seg = qtid & 7;
             const int n = t.n0 + c * 64 + seg * 8;
-            constexpr int ROWS_PER_PASS = EPI_THREADS / 8;
+            constexpr int ROWS_PER_PASS = QT / 8;
 #pragma unroll
-            for (int pass = 0; pass < 128 / ROWS_PER_PASS; ++pass) {
-              const int r = (etid >> 3) + pass * ROWS_PER_PASS;
+            for (int pass = 0; pass < 32 / ROWS_PER_PASS; ++pass) {
+              const int r = q * 32 + (qtid >> 3) + pass * ROWS_PER_PASS;
               const int mm = t.m0 + r;
               bool ok = mm < M && n + 8 <= N;
               int64_t orr = mm;
@@ -599,14 +688,15 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
               }
               if (ok)
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orr * epi.out_ld + n) =
-                    *reinterpret_cast<const uint4*>(cbuf + cb * CHUNK_BYTES + r * 128 + ((seg ^ (r & 7)) << 4));
+                    lds128(cbuf32 + cboff + r * 128 + ((seg ^ (r & 7)) << 4));
             }
           }
         }
+        if (qlead && q == 3 && local == 0) dbg_stamp(epi, 14);
       }
-      if (elected) dbg_stamp(epi, 8);
-      if (elected) tma_store_wait_all<0>();
-      if (elected) dbg_stamp(epi, 9);
+      if (qlead && q == 3) dbg_stamp(epi, 8);
+      if (qlead) tma_store_wait_all<0>();               // every unit drains its own bulk groups before the CTA may exit
+      if (qlead && q == 3) dbg_stamp(epi, 9);
     } else {
       // ---------- staged epilogue: row re-map, fp32 output, pre-activation stash, wgrad accumulation ----------
       uint8_t* stg = stg_base + ew * STG_BYTES;
@@ -614,7 +704,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
       const int srow = lane >> 3;                   // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
       const int sseg = lane & 7;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
-        const TileInfo t = decode_tile<BN, MODE, CG>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split, rank);
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         const int m = t.m0 + q * 32 + lane;
@@ -734,8 +824,19 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
               const int nb = ncol + h * 32;
-              epilogue_math<32>(f, epi, dseed, nb, N, orow, epi.residual ? res + h * 16 : nullptr, epi.aux ? axv + h * 16 : nullptr,
-                            epi.out2 ? o2 + h * 16 : nullptr);
+              float shv[32];
+              const bool has_shift = epi.shift != nullptr;
+              if (has_shift) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (nb + j + 4 <= N) s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
+                  shv[j] = s4.x; shv[j + 1] = s4.y; shv[j + 2] = s4.z; shv[j + 3] = s4.w;
+                }
+              }
+              epilogue_math<32, true>(f, epi, shv, has_shift, dseed, nb, N, orow, reinterpret_cast<const uint32_t(&)[16]>(res[h * 16]), epi.residual != nullptr,
+                                      reinterpret_cast<const uint32_t(&)[16]>(axv[h * 16]), epi.aux != nullptr, reinterpret_cast<uint32_t(&)[16]>(o2[h * 16]),
+                                      epi.out2 != nullptr);
               if (epi.out_fp32) {
                 // fp32 output: stage 32 columns (128 B per row) and store coalesced right away
                 __syncwarp();
@@ -802,12 +903,10 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
   }
   tc_fence_before();
   __syncthreads();
-  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until here
   if (threadIdx.x == 0) dbg_stamp(epi, 10);
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
-    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (threadIdx.x == 32) dbg_stamp(epi, 11);
 }
@@ -829,9 +928,7 @@ static int sm_count() {
 
 static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
-static int g_force_cbuf = 0;  // tuning hook: output chunk buffers of the TMA epilogue (0 = automatic, else 2 or 4)
 static int g_mn3d = 1;        // 1 (default) = MN-major operands through one 3-D TMA box per k-chunk (GemmEpi::mn3d); cb_debug_gemm_mn3d
-static int g_epi_warps = 16;  // epilogue warps of the TMA epilogue: 16 (default) or 8 (cb_debug_gemm_epi_warps, env CB_EPI_WARPS)
 
 // Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
 // stage. Measured (profiles/r01_gemm_kch_probe.txt, r01_gemm_staged_probe.txt): every stage costs a ~450-cycle barrier
@@ -841,14 +938,16 @@ struct SmemPlan {
   int epi_bytes, n_cbuf, n_rbuf, kch, stages, chunk_bytes;
 };
 constexpr int SMEM_LIMIT_OCC2 = 113 * 1024;   // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
-static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0, int occ = 1) {
+static SmemPlan plan_smem(int bn, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0, int occ = 1, bool sh_smem = false) {
   SmemPlan p;
   const int limit = occ == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
-  p.chunk_bytes = BM * BK * 2 + (bn / cg) * BK * 2;
-  p.n_cbuf = g_force_cbuf ? g_force_cbuf : 2;
+  p.chunk_bytes = BM * BK * 2 + bn * BK * 2;
+  p.n_cbuf = 2;
   p.n_rbuf = 2;
   const int n_in = (has_res ? 1 : 0) + (has_aux ? 1 : 0);
-  auto epi_bytes_for = [&](int n_cbuf, int n_rbuf) { return n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in; };
+  auto epi_bytes_for = [&](int n_cbuf, int n_rbuf) {
+    return n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in + (sh_smem ? 1024 : 0);   // + [<= 4][64 floats] shift slots
+  };
   auto fit = [&](int n_cbuf, int n_rbuf) { return (limit - 1024 - 256 - epi_bytes_for(n_cbuf, n_rbuf)) / p.chunk_bytes; };
   if (tma_epi) {
     if (occ == 2) {
@@ -884,14 +983,14 @@ static SmemPlan plan_smem(int bn, int cg, bool tma_epi, bool has_res, bool has_a
   return p;
 }
 
-template <int BN, int MODE, int EPI, int CG, int EW = 8, int OCC = 1>
+template <int BN, int MODE, int EPI, int EW = 8, int OCC = 1>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_t stream) {
   GemmEpi epi = epi_in;
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN>;
   constexpr int GEMM_THREADS = gemm_threads(EW);
   constexpr int LIMIT = OCC == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE, EPI, CG, EW, OCC>;
+  auto kern = gemm_kernel<BN, MODE, EPI, EW, OCC>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LIMIT);
     if (e == cudaSuccess && OCC == 2)   // both CTAs of an SM need their 113 KB: ask for the full shared-memory carve-out
@@ -906,23 +1005,23 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
   alignas(64) CUtensorMap ta, tb, tc, tr, tx, tc2;
   bool mn3d = false;
   int iters_per_split = 0;
-  const int tiles_m = ceil_div(d.m, BM * CG), tiles_n = ceil_div(d.n, BN);
+  const int tiles_m = ceil_div(d.m, BM), tiles_n = ceil_div(d.n, BN);
   int total = tiles_m * tiles_n;
   int kiters;
   bool ok;
   if (MODE == 0) {
     ok = get_tmap_2d(&ta, d.a, d.k, d.a_rows, d.a_ld, BK, BM) &&
-         get_tmap_2d(&tb, d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN / CG);
+         get_tmap_2d(&tb, d.b, static_cast<uint64_t>(d.k) * d.ntaps, d.b_rows, d.b_ld, BK, BN);
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else if (MODE == 2) {
     ok = get_tmap_2d(&ta, d.a, d.k, d.a_rows, d.a_ld, BK, BM);
-    mn3d = g_mn3d && CG == 1 && d.n % 64 == 0 &&
+    mn3d = g_mn3d && d.n % 64 == 0 &&
            get_tmap_3d_mn(&tb, d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, BK, BN / 64);
     // not asked for, or the driver refused the 3-D view: the 2-D boxes always work
     if (!mn3d) ok = ok && get_tmap_2d(&tb, d.b, static_cast<uint64_t>(d.n) * d.ntaps, d.b_rows, d.b_ld, 64, BK);
     kiters = ceil_div(d.k, BK) * d.ntaps;
   } else {
-    mn3d = g_mn3d && CG == 1 && d.m % 64 == 0 && d.n % 64 == 0 && get_tmap_3d_mn(&ta, d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) &&
+    mn3d = g_mn3d && d.m % 64 == 0 && d.n % 64 == 0 && get_tmap_3d_mn(&ta, d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) &&
            get_tmap_3d_mn(&tb, d.b, d.n, d.b_rows, d.b_ld, BK, BN / 64);
     ok = mn3d || (get_tmap_2d(&ta, d.a, d.m, d.a_rows, d.a_ld, 64, BK) && get_tmap_2d(&tb, d.b, d.n, d.b_rows, d.b_ld, 64, BK));
     const int kc = ceil_div(d.k, BK);
@@ -936,120 +1035,99 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
   if (!ok) return CB_ERR_CUDA;
   tc = tr = tx = tc2 = ta;   // placeholders for the maps this launch does not use (a __grid_constant__ parameter must be a valid object)
   if (EPI == 1) {
-    if (d.rowmap == CB_ROWMAP_NONE && !get_tmap_2d(&tc, d.out, d.n, d.m, d.out_ld, 64, BM)) return CB_ERR_CUDA;
+    // output maps: one box = the 32 rows x 64 columns a lane-quarter unit of the epilogue stores
+    if (d.rowmap == CB_ROWMAP_NONE && !get_tmap_2d(&tc, d.out, d.n, d.m, d.out_ld, 64, 32)) return CB_ERR_CUDA;
     if (d.residual && !get_tmap_2d(&tr, d.residual, d.n, d.m, d.res_ld, 64, BM)) return CB_ERR_CUDA;
     if (d.aux && !get_tmap_2d(&tx, d.aux, d.n, d.m, d.aux_ld, 64, BM)) return CB_ERR_CUDA;
-    if (d.out2 && !get_tmap_2d(&tc2, d.out2, d.n, d.m, d.out2_ld, 64, BM)) return CB_ERR_CUDA;
+    if (d.out2 && !get_tmap_2d(&tc2, d.out2, d.n, d.m, d.out2_ld, 64, 32)) return CB_ERR_CUDA;
   }
   epi.mn3d = mn3d ? 1 : 0;
-  const SmemPlan sp = plan_smem(BN, CG, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15, OCC);
+  const bool sh_smem = EPI == 1 && d.shift != nullptr && (reinterpret_cast<uintptr_t>(d.shift) & 15) == 0;
+  epi.shift_smem = sh_smem ? 1 : 0;
+  const SmemPlan sp = plan_smem(BN, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15, OCC, sh_smem);
   const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, n_rbuf = sp.n_rbuf, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
     set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B, %d CTA(s) per SM)", BN, epi_bytes, OCC);
     return CB_ERR_INVALID;
   }
   const int smem_bytes = stages * kch * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
-  const int units = sm_count() * OCC / CG;
-  const int grid = (total < units ? total : units) * CG;
-  if (CG == 1) {
-    launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-             iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign, iters_per_split,
-                                       tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
-    if (e != cudaSuccess) {
-      set_error("cb_gemm: cluster launch failed: %s", cudaGetErrorString(e));
-      return CB_ERR_CUDA;
-    }
-  }
+  const int units = sm_count() * OCC;
+  const int grid = total < units ? total : units;
+  launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+           iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
   return check_launch("cb_gemm");
 }
 
 // ------------------------------------------------------------------------------------------------
-// Launch configuration. Measured on B200 (tools/probe_gemm_timeline.py, profiles/r01_gemm_timeline.txt): a
+// Launch configuration. Measured on B200 (tools/probe_gemm_cta_timeline.py, profiles/r02c_gemm_cta_timeline.txt): a
 // persistent CTA sustains ~60-70 B/clk of TMA ingest, so its main loop costs about (k-iterations x stage bytes)
 // / 60 cycles and the launch is done when the busiest SM is. The model picks the tile width (and the wgrad
-// K-split) minimising that plus a per-tile epilogue term. 128 x 256 single-CTA tiles reach 1.27 PFLOP/s on
-// 8192^2 x 2048 (87 % of the measured sustained cuBLAS figure). The cta_group::2 CTA-pair path is functionally
-// complete and unit-tested but measured ~2x SLOWER than single CTAs in round 1 (cause not yet found), so it is
-// only used when a caller forces it (cb_gemm_desc.reserved bit 2).
+// K-split) minimising that plus a per-tile epilogue term. 128 x 256 tiles reach 1.27 PFLOP/s on 8192^2 x 2048
+// (87 % of the measured sustained cuBLAS figure).
+// (A cta_group::2 CTA-pair variant existed in round 1; it measured 15-60 % SLOWER than single CTAs on every shape of
+// the step, compute-bound 3x3 convs included - profiles/r02c_gemm_cta_timeline.txt, "pair" rows - and was removed.)
 // ------------------------------------------------------------------------------------------------
 struct LaunchCfg {
-  int bn, cg, splits;
+  int bn, splits;
 };
 
 // Two CTAs per SM (the OCC = 2 instantiations: 128 x <=128 tiles, 8 epilogue warps, <= 113 KB of shared memory, 2 x BN <= 256
-// TMEM columns each). One CTA's prologue / epilogue / barrier round trips run under the other's main loop, a launch of the
-// dgrad chain and a wgrad launch of the side stream can share an SM, and an HBM-bound 1x1 conv keeps two operand + residual
-// rings in flight per SM. The price is operand traffic: a 128 x 128 tile needs 128 B/clk of L2 -> SM ingest for a full-rate
-// tensor pipe against ~70 B/clk measured, so the compute-bound convs stay on 128 x 256 tiles with one CTA per SM.
-//   g_occ2_mode: 0 = never, 1 = only launches that ask for it (cb_gemm_desc.reserved bit 5), 2 = every eligible launch whose
-//   work is at most g_occ2_max_gflop (0 = no limit).
+// TMEM columns each). One CTA's prologue / epilogue / barrier round trips run under the other's main loop, and an HBM-bound
+// 1x1 conv keeps two operand + residual rings in flight per SM. The price is operand traffic: a 128 x 128 tile needs 128 B/clk
+// of L2 -> SM ingest for a full-rate tensor pipe against ~70 B/clk measured, so everything compute-bound stays on 128 x 256
+// tiles with one CTA per SM (measured, profiles/r02_ab_runs.txt: turning it on for all BERT GEMMs costs 4 % of the step).
+//   g_occ2_mode: 0 = never, 1 = only launches that ask for it (cb_gemm_desc.reserved bit 5: the tuning table), 2 = every
+//   eligible launch whose work is at most g_occ2_max_gflop (0 = no limit).
 static int g_occ2_mode = 1;
 static double g_occ2_max_gflop = 0.0;
 
-static LaunchCfg choose_config(const cb_gemm_desc& d, int force_cg, bool tma_epi, int occ = 1) {
-  const int sms = sm_count() * occ;
+static LaunchCfg choose_config(const cb_gemm_desc& d, bool tma_epi, int occ = 1) {
+  const int units = sm_count() * occ;
   const int kc = ceil_div(d.k, BK);
   const bool wgrad = d.mode == CB_GEMM_WGRAD;
-  static const int cand[5][2] = {{64, 1}, {128, 1}, {256, 1}, {128, 2}, {256, 2}};
-  LaunchCfg best = {0, 1, 1};      // bn = 0: no candidate fits (only possible with occ = 2)
+  static const int cand[3] = {64, 128, 256};
+  LaunchCfg best = {0, 1};      // bn = 0: no candidate fits (only possible with occ = 2)
   double best_cost = 1e30;
-  for (int c = 0; c < 5; ++c) {
-    const int bn = cand[c][0], cg = cand[c][1];
-    if (cg != (force_cg ? force_cg : 1)) continue;
-    if (occ == 2 && (cg != 1 || bn > 128)) continue;
+  for (int c = 0; c < 3; ++c) {
+    const int bn = cand[c];
+    if (occ == 2 && bn > 128) continue;
     if (d.block_n && bn != d.block_n) continue;
     if (bn > 64 && d.n <= bn / 2) continue;               // mostly padding
-    if (cg == 2 && d.m <= BM) continue;
-    const int units = sms / cg;
-    const int64_t base = static_cast<int64_t>(ceil_div(d.m, BM * cg)) * ceil_div(d.n, bn) * (wgrad ? d.ntaps : 1);
+    const int64_t base = static_cast<int64_t>(ceil_div(d.m, BM)) * ceil_div(d.n, bn) * (wgrad ? d.ntaps : 1);
     const int max_split = wgrad ? (d.split_k > 0 ? d.split_k : (kc < 32 ? kc : 32)) : 1;
     for (int sp = (wgrad && d.split_k > 0) ? d.split_k : 1; sp <= max_split; ++sp) {
       const int ips = ceil_div(wgrad ? kc : kc * d.ntaps, sp);
       const int real_sp = wgrad ? ceil_div(kc, ips) : 1;
       const int64_t tiles = base * real_sp;
       const double rounds = static_cast<double>((tiles + units - 1) / units);
-      const SmemPlan pl = plan_smem(bn, cg, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15, occ);
+      const SmemPlan pl = plan_smem(bn, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15, occ,
+                                    tma_epi && !wgrad && d.shift != nullptr && (reinterpret_cast<uintptr_t>(d.shift) & 15) == 0);
       if (pl.stages < 2) continue;
       // per stage: ~450-cycle barrier round trip + bytes at ~60 B/clk (shared by the CTAs of an SM); per tile: epilogue (fp32 red.add / staged bf16 / TMA bf16)
       const double stage_cost = 450.0 + pl.kch * pl.chunk_bytes / (60.0 / occ);
       const double epi = wgrad ? bn * 24.0 : (tma_epi ? bn * 12.0 : bn * 30.0);
-      const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost + epi) + 2500.0 + (cg == 2 ? 600.0 : 0.0);
+      const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost + epi) + 2500.0;
       if (cost < best_cost) {
         best_cost = cost;
-        best = {bn, cg, real_sp};
+        best = {bn, real_sp};
       }
     }
   }
+  if (best.bn == 0 && occ == 1) best = {64, 1};
   return best;
 }
 
 }  // namespace cb
 
-/* bring-up / tuning hook (not part of the public header): device buffer of >= 16 int64 receiving clock64() stamps of CTA 0 */
+/* bring-up / tuning hook (not part of the public header): device buffer of >= 16 x grid int64 receiving clock64() stamps of every CTA */
 extern "C" void cb_debug_gemm_timeline(void* device_buf) { cb::g_gemm_timeline = static_cast<long long*>(device_buf); }
 extern "C" void cb_debug_gemm_kch(int kch) { cb::g_force_kch = kch; }
-extern "C" void cb_debug_gemm_cbuf(int n) { cb::g_force_cbuf = n; }
-extern "C" void cb_debug_gemm_epi_warps(int n) { cb::g_epi_warps = (n == 8) ? 8 : 16; }
 extern "C" void cb_debug_gemm_mn3d(int on) { cb::g_mn3d = on ? 1 : 0; }
 extern "C" void cb_debug_gemm_occ2(int mode, double max_gflop) {
   cb::g_occ2_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   cb::g_occ2_max_gflop = max_gflop;
 }
-extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? (n < 2 ? 2 : n & ~1) : 0; }   // even: CTA pairs
+extern "C" void cb_debug_gemm_sm_limit(int n) { cb::g_sm_limit = n > 0 ? n : 0; }
 
 extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   using namespace cb;
@@ -1083,6 +1161,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
   epi.seed = d.dropout_seed;
   epi.dbg = g_gemm_timeline;
   epi.mn3d = 0;
+  epi.shift_smem = 0;
   {
     const DropCfg dc = make_drop(d.dropout_p, d.dropout_seed);
     epi.drop_thresh = dc.thresh;
@@ -1101,7 +1180,6 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(!(d.out2 && d.out_fp32), "cb_gemm(TN): out2 requires a bf16 primary output");
     CB_REQUIRE(d.rowmap == CB_ROWMAP_NONE || (d.map_h > 0 && d.map_w > 0), "cb_gemm: rowmap needs map_h/map_w");
     CB_REQUIRE(d.ntaps == 1 || d.tap_w > 2, "cb_gemm: tap modes need tap_w (padded row pitch in pixels)");
-    const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
     // TMA-prefetch epilogue whenever the output is bf16 (residual / aux tiles arrive by TMA; the output leaves by TMA store
     // or, when rows are re-mapped, by cooperative coalesced stores)
     const bool tma_epi = !d.out_fp32 && (d.reserved & 1) == 0 && !(d.rowmap != CB_ROWMAP_NONE && (d.out2 || d.dropout_p > 0.0f)) &&
@@ -1110,35 +1188,21 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
                          (!d.aux || (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0);
     // two CTAs per SM (see g_occ2_mode): TMA epilogue only (the staged bf16 epilogue needs 168 registers)
     const double gflop = 2.0e-9 * d.m * d.n * d.k * d.ntaps;
-    const bool want_occ2 = tma_epi && force_cg != 2 && (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
+    const bool want_occ2 = tma_epi && (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
                            ((d.reserved & 32) ? g_occ2_mode >= 1 : (g_occ2_mode == 2 && (g_occ2_max_gflop <= 0.0 || gflop <= g_occ2_max_gflop)));
     if (want_occ2) {
-      const LaunchCfg l2 = choose_config(d, 1, tma_epi, 2);
-      if (l2.bn == 64) return nn ? launch_gemm<64, 2, 1, 1, 8, 2>(d, epi, stream) : launch_gemm<64, 0, 1, 1, 8, 2>(d, epi, stream);
-      if (l2.bn == 128) return nn ? launch_gemm<128, 2, 1, 1, 8, 2>(d, epi, stream) : launch_gemm<128, 0, 1, 1, 8, 2>(d, epi, stream);
+      const LaunchCfg l2 = choose_config(d, tma_epi, 2);
+      if (l2.bn == 64) return nn ? launch_gemm<64, 2, 1, 8, 2>(d, epi, stream) : launch_gemm<64, 0, 1, 8, 2>(d, epi, stream);
+      if (l2.bn == 128) return nn ? launch_gemm<128, 2, 1, 8, 2>(d, epi, stream) : launch_gemm<128, 0, 1, 8, 2>(d, epi, stream);
     }
-    const LaunchCfg lc = choose_config(d, force_cg, tma_epi);
-#define CB_DISPATCH(BN_, CG_, EW_)                                                                                                  \
-  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, CG_, EW_>(d, epi, stream) : launch_gemm<BN_, 2, 0, CG_>(d, epi, stream))            \
-            : (tma_epi ? launch_gemm<BN_, 0, 1, CG_, EW_>(d, epi, stream) : launch_gemm<BN_, 0, 0, CG_>(d, epi, stream))
-    if (lc.cg == 2) {
-      if (lc.bn == 128) { CB_DISPATCH(128, 2, 8); }
-      CB_DISPATCH(256, 2, 8);
-    }
-    // TMA epilogue: 16 epilogue warps (4 per scheduler) unless the caller pins the 8-warp variant (reserved bit 4: A/B runs)
-    const bool ew16 = g_epi_warps == 16 && (d.reserved & 16) == 0;
-    if (ew16) {
-      switch (lc.bn) {
-        case 64: CB_DISPATCH(64, 1, 16);
-        case 128: CB_DISPATCH(128, 1, 16);
-        case 256: CB_DISPATCH(256, 1, 16);
-        default: break;
-      }
-    }
+    const LaunchCfg lc = choose_config(d, tma_epi);
+#define CB_DISPATCH(BN_)                                                                                                     \
+  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, 16>(d, epi, stream) : launch_gemm<BN_, 2, 0, 8>(d, epi, stream))            \
+            : (tma_epi ? launch_gemm<BN_, 0, 1, 16>(d, epi, stream) : launch_gemm<BN_, 0, 0, 8>(d, epi, stream))
     switch (lc.bn) {
-      case 64: CB_DISPATCH(64, 1, 8);
-      case 128: CB_DISPATCH(128, 1, 8);
-      case 256: CB_DISPATCH(256, 1, 8);
+      case 64: CB_DISPATCH(64);
+      case 128: CB_DISPATCH(128);
+      case 256: CB_DISPATCH(256);
       default: CB_REQUIRE(false, "cb_gemm: block_n must be 0, 64, 128 or 256 (got %d)", lc.bn);
     }
 #undef CB_DISPATCH
@@ -1147,29 +1211,24 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     CB_REQUIRE(d.m % 8 == 0 && d.n % 8 == 0, "cb_gemm(WGRAD): m, n must be multiples of 8 (got %d, %d)", d.m, d.n);
     CB_REQUIRE(d.out_ld % 4 == 0, "cb_gemm(WGRAD): out_ld must be a multiple of 4");
     CB_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "cb_gemm(WGRAD): out must be 16-byte aligned");
-    const int force_cg = (d.reserved & 2) ? 1 : ((d.reserved & 4) ? 2 : 0);
     const double gflop = 2.0e-9 * d.m * d.n * d.k * d.ntaps;
-    const bool want_occ2 = force_cg != 2 && (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
+    const bool want_occ2 = (d.reserved & 64) == 0 && (!d.block_n || d.block_n <= 128) &&
                            ((d.reserved & 32) ? g_occ2_mode >= 1 : (g_occ2_mode == 2 && (g_occ2_max_gflop <= 0.0 || gflop <= g_occ2_max_gflop)));
     if (want_occ2) {
-      const LaunchCfg l2 = choose_config(d, 1, false, 2);
+      const LaunchCfg l2 = choose_config(d, false, 2);
       cb_gemm_desc d2 = d;
       d2.split_k = l2.splits;
-      if (l2.bn == 64) return launch_gemm<64, 1, 0, 1, 8, 2>(d2, epi, stream);
-      if (l2.bn == 128) return launch_gemm<128, 1, 0, 1, 8, 2>(d2, epi, stream);
+      if (l2.bn == 64) return launch_gemm<64, 1, 0, 8, 2>(d2, epi, stream);
+      if (l2.bn == 128) return launch_gemm<128, 1, 0, 8, 2>(d2, epi, stream);
     }
-    const LaunchCfg lc = choose_config(d, force_cg, false);
+    const LaunchCfg lc = choose_config(d, false);
     cb_gemm_desc d2 = d;
     d2.split_k = lc.splits;
-    if (lc.cg == 2) {
-      if (lc.bn == 128) return launch_gemm<128, 1, 0, 2>(d2, epi, stream);
-      return launch_gemm<256, 1, 0, 2>(d2, epi, stream);
-    }
     switch (lc.bn) {
-      case 64: return launch_gemm<64, 1, 0, 1>(d2, epi, stream);
-      case 128: return launch_gemm<128, 1, 0, 1>(d2, epi, stream);
-      case 256: return launch_gemm<256, 1, 0, 1>(d2, epi, stream);
-      default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64, 128 (or 256 paired) (got %d)", lc.bn);
+      case 64: return launch_gemm<64, 1, 0, 8>(d2, epi, stream);
+      case 128: return launch_gemm<128, 1, 0, 8>(d2, epi, stream);
+      case 256: return launch_gemm<256, 1, 0, 8>(d2, epi, stream);
+      default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64, 128 or 256 (got %d)", lc.bn);
     }
   }
   return CB_ERR_INVALID;

@@ -90,11 +90,6 @@ def launch_count():
     return int(L.lib().cb_launch_count())
 
 
-def set_epi_warps(n):
-    """Tuning hook: epilogue warps of the GEMM's TMA epilogue, 16 (default) or 8."""
-    L.lib().cb_debug_gemm_epi_warps(int(n))
-
-
 def set_attention_flash(on):
     """Forward attention of sequences longer than 64 tokens: 1 (default) = tensor-core online-softmax kernel (2.1x on config 5,
     profiles/r02_ab_runs.txt), 0 = the CUDA-core kernel."""
@@ -137,11 +132,6 @@ def set_sm_limit(n):
     """Tuning hook: cap the persistent GEMM grid at ``n`` CTAs (0 = every SM): leaves SMs to a co-resident NCCL kernel so
     that the static tile schedule does not spill into a second wave while a gradient all-reduce overlaps the backward."""
     L.lib().cb_debug_gemm_sm_limit(int(n))
-
-
-def set_cbuf(n):
-    """Tuning hook: output chunk buffers of the GEMM's TMA-store epilogue (0 = automatic, 2 or 4)."""
-    L.lib().cb_debug_gemm_cbuf(int(n))
 
 
 def set_pdl(enable):

@@ -137,8 +137,9 @@ typedef struct cb_gemm_desc {
   float dropout_p;
   uint64_t dropout_seed;
   int32_t block_n;  /* 0 = let the library choose (64 / 128 / 256) */
-  int32_t reserved; /* tuning / test knobs: bit0 force the staged (non-TMA) epilogue, bit1 force single-CTA tiles,
-                       bit2 force CTA pairs, bits 8-11 k-chunks per pipeline stage (0 = automatic) */
+  int32_t reserved; /* tuning / test knobs: bit0 force the staged (non-TMA) epilogue, bit5 ask for / bit6 forbid the
+                       two-CTAs-per-SM instantiation (128 x <=128 tiles), bits 8-11 k-chunks per pipeline stage
+                       (0 = automatic); other bits ignored */
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

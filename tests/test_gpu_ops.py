@@ -20,13 +20,13 @@ def _rnd(g, *shape, scale=1.0, dev="cuda"):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
-PAIR, SINGLE, STAGED = 4, 2, 1      # cb_gemm_desc.reserved test knobs
+SINGLE, STAGED, OCC2 = 2, 1, 32      # cb_gemm_desc.reserved test knobs (OCC2: the two-CTAs-per-SM instantiations)
 
 
-@pytest.mark.parametrize("cfg", [(64, SINGLE), (128, SINGLE), (256, SINGLE), (128, PAIR), (256, PAIR)])
+@pytest.mark.parametrize("cfg", [(64, SINGLE), (128, SINGLE), (256, SINGLE)])
 @pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (1312, 768, 768), (77, 264, 1096), (40000, 256, 64)])
 def test_gemm_tn_fp32_out(cuda, cfg, shape):
-    """Every tile width, single CTAs and CTA pairs (cta_group::2), ragged M / N / K, several tiles per persistent CTA."""
+    """Every tile width, ragged M / N / K, several tiles per persistent CTA."""
     ops = _ops()
     M, N, K = shape
     bn, knob = cfg
@@ -38,7 +38,7 @@ def test_gemm_tn_fp32_out(cuda, cfg, shape):
     assert relerr(C, A.float() @ B.float().t()) < TOL_FP32_OP
 
 
-@pytest.mark.parametrize("knob", [SINGLE, PAIR])
+@pytest.mark.parametrize("knob", [SINGLE])
 @pytest.mark.parametrize("shape", [(500, 384, 256), (1312, 2304, 768), (64, 768, 3072)])
 def test_gemm_nn_dgrad(cuda, shape, knob):
     ops = _ops()
@@ -50,20 +50,18 @@ def test_gemm_nn_dgrad(cuda, shape, knob):
     assert relerr(C, A.float() @ B.float()) < TOL_FP32_OP
 
 
-@pytest.fixture(params=["tma_store", "tma_store_8warps", "two_ctas_per_sm"])
+@pytest.fixture(params=["tma_store", "two_ctas_per_sm"])
 def epilogue_variant(request):
-    """The GEMM's TMA-prefetch epilogue with 16 epilogue warps (default), with 8 (the round-1a kernel), and the
-    two-CTAs-per-SM instantiations (ops.set_occ2(2): 128 x <=128 tiles, 8 epilogue warps taking their 32 columns in two
-    passes, a single output chunk buffer when the shared-memory half is tight)."""
+    """The GEMM's TMA epilogue in its two instantiations: 16 epilogue warps / one CTA per SM (default), and two CTAs per SM
+    (ops.set_occ2(2): 128 x <=128 tiles, 8 epilogue warps taking their 32 columns in two passes, a single output chunk
+    buffer when the shared-memory half is tight)."""
     ops = _ops()
-    ops.set_epi_warps(8 if request.param.endswith("8warps") else 16)
     ops.set_occ2(2 if request.param == "two_ctas_per_sm" else 0)
     yield request.param
-    ops.set_epi_warps(16)
     ops.set_occ2(1)
 
 
-@pytest.mark.parametrize("staged", [0, STAGED, PAIR, PAIR | STAGED])
+@pytest.mark.parametrize("staged", [0, STAGED])
 @pytest.mark.parametrize("shape", [(500, 384, 256), (20000, 512, 128), (3000, 64, 64)])
 def test_gemm_epilogues(cuda, staged, shape, epilogue_variant):
     """Both epilogue I/O paths (TMA-prefetched / TMA-stored vs. per-warp staged), several tiles per persistent CTA."""
@@ -108,7 +106,7 @@ def test_gemm_epilogues(cuda, staged, shape, epilogue_variant):
     assert relerr(C, (acc + shift) * msk.float() + R.float()) < TOL_BF16_OP
 
 
-@pytest.mark.parametrize("knob", [SINGLE, PAIR, SINGLE | STAGED])
+@pytest.mark.parametrize("knob", [SINGLE, SINGLE | STAGED])
 @pytest.mark.parametrize("dims", [(2, 7, 7, 64, 64), (3, 14, 14, 128, 128), (2, 28, 28, 64, 192), (1, 3, 5, 512, 64), (64, 14, 14, 256, 256)])
 def test_conv3x3_fwd_and_dgrad(cuda, dims, knob, epilogue_variant):
     ops = _ops()
@@ -154,7 +152,7 @@ def test_rowmap_pad_keeps_border_zero(cuda, dims, knob, epilogue_variant):
 
 @pytest.mark.parametrize("case", [(64, 128, 64, 64, 1, SINGLE), (1312, 768, 768, 128, 1, SINGLE), (1000, 256, 192, 64, 1, SINGLE),
                                   (333, 136, 72, 64, 1, SINGLE), (5000, 256, 256, 128, 7, SINGLE), (640, 128, 128, 64, 100, SINGLE),
-                                  (32, 8, 1536, 128, 1, SINGLE), (1312, 768, 3072, 256, 0, PAIR), (5000, 512, 256, 128, 3, PAIR),
+                                  (32, 8, 1536, 128, 1, SINGLE), (1312, 768, 3072, 256, 0, SINGLE), (5000, 512, 256, 128, 3, OCC2),
                                   (1312, 2304, 768, 0, 0, 0), (50176, 512, 128, 0, 0, 0)])
 def test_wgrad(cuda, case):
     ops = _ops()
@@ -172,7 +170,7 @@ def test_wgrad(cuda, case):
     assert relerr(dW, 2 * (dY.float().t() @ X.float()) * rs[:, None]) < TOL_FP32_OP
 
 
-@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 128, 1, SINGLE), (4, 14, 14, 128, 128, 3, SINGLE), (4, 14, 14, 256, 256, 0, PAIR)])
+@pytest.mark.parametrize("dims", [(2, 7, 7, 64, 128, 1, SINGLE), (4, 14, 14, 128, 128, 3, SINGLE), (4, 14, 14, 256, 256, 0, OCC2)])
 def test_wgrad_conv3x3(cuda, dims):
     ops = _ops()
     NB, H, W, Cin, Cout, sk, knob = dims
