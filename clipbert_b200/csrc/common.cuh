@@ -93,6 +93,14 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_s32(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
@@ -231,11 +239,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 1 / x as ONE MUFU.RCP (<= 1 ulp). __frcp_rn compiles to MUFU.RCP + a Newton step + a conditional CALL to an IEEE slow path per
+// element, which serialised the GELU epilogue (16 calls per 16 columns, profiles/r02g: 2.5 k cycles per pass).
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution): 1 rcp, 1 ex2, 6 fma.
 // Replaces erff (~30 instructions) in the GELU epilogues, which are ALU-bound at ClipBERT's GEMM sizes.
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -250,7 +266,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // the derivative, so stashing gelu'(u) in the forward costs 3 extra flops and turns the backward epilogue into one multiply.
 __device__ __forceinline__ void gelu_erf_and_grad(float x, float& y, float& g) {
   const float az = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, az, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

@@ -6,15 +6,18 @@
 //   MODE 1 (WGRAD) : dW = dY^T X with both operands read MN-major from the activation layout,
 //                    split over the pixel/token dimension, fp32 red.global accumulation.
 //
-// Structure (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+// Structure (persistent CTAs, grid = min(#tiles, #SMs x CTAs per SM), static round-robin tile schedule):
 //   warp 0      TMA producer   : smem ring of STAGES x (A 128x64 | B BNx64) bf16 tiles, 128B swizzle
 //   warp 1      MMA issuer     : tcgen05.mma into one of TWO TMEM accumulator stages (2 x BN columns)
-//   warps 2..9  epilogue       : TMEM -> registers -> fused epilogue, overlapping the next tile's TMA + MMA
-//                                through the tmem_full / tmem_empty barrier pair. Two I/O paths:
-//       EPI 1 (bf16 out, no row re-map): residual / aux tiles are TMA-PREFETCHED two 64-column chunks
-//             ahead into swizzled smem, the output chunk is written to swizzled smem and leaves with a
-//             TMA store (bulk async group), so the memory-bound 1x1 convs keep >= 64 KB in flight per SM;
-//       EPI 0 (row re-map / fp32 / wgrad red.add): per-warp smem staging -> coalesced 128-byte accesses.
+//   warps 2..   epilogue       : TMEM -> registers -> fused epilogue, overlapping the next tile's TMA + MMA through the
+//                                tmem_full / tmem_empty barrier pair. Two I/O paths:
+//       EPI 1 (bf16 out): BN/16 WARP-PRIVATE pipelines. Warp (q, c) owns the 32-row x 64-column slab (TMEM lane quarter q,
+//             64-column chunk c) of every tile: its lane 0 TMA-loads the slab of the residual / aux tensor and the chunk's 64
+//             shift values into the warp's own shared-memory slab one main loop ahead, the warp converts its accumulator
+//             columns in four passes of 16, writes the result IN PLACE and lane 0 TMA-stores the slab. No barrier between
+//             warps, no loader warp: one tile costs a warp ~250 instructions (the chunk-cooperative version with named
+//             barriers cost ~1000 and was bound by their issue rate, profiles/r02e_gemm_cta_timeline_lean_epilogue.txt).
+//       EPI 0 (row re-map with stash / fp32 / wgrad red.add): per-warp smem staging -> coalesced 128-byte accesses, 8 warps.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -22,13 +25,10 @@ namespace cb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-// Epilogue warps: 8 (two per TMEM lane quarter, 32 columns each per 64-column chunk) or, for the TMA epilogue, 16 (four per
-// quarter, 16 columns each). ncu on the 8-warp HBM-bound 1x1 convs (profiles/r01b_gemm_full_stalls.txt): two warps per
-// scheduler issue only 38 % of the cycles of a chunk - the rest is fixed-latency / scoreboard / barrier wait nothing else
-// can fill; four warps per scheduler with half the registers each hide it.
-constexpr int gemm_threads(int ew) { return 96 + ew * 32; }   // TMA producer, MMA issuer, epilogue loader, EW epilogue warps
+__host__ __device__ constexpr int gemm_threads(int ew) { return 64 + ew * 32; }   // TMA producer, MMA issuer, EW epilogue warps
+__host__ __device__ constexpr int epi_warps(int bn, int epi) { return epi == 1 ? bn / 16 : 8; }   // TMA epilogue: one warp per 32 x 64 output slab of a tile
 constexpr int MAX_STAGES = 8;
-constexpr int CHUNK_BYTES = BM * 128;           // one 128-row x 64-column bf16 chunk (TMA epilogue path)
+constexpr int SLAB_BYTES = 32 * 128;            // one 32-row x 64-column bf16 slab (TMA epilogue: one warp's share of a tile)
 constexpr int SMEM_LIMIT = 232448;              // 227 KB opt-in limit per CTA
 constexpr int STG_ROW = 144;                    // staging row pitch in bytes (128 + 16: conflict-free 16 B accesses)
 constexpr int STG_BYTES = 32 * STG_ROW;         // per epilogue warp
@@ -78,7 +78,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages
 };
 
@@ -294,18 +294,16 @@ __device__ __forceinline__ TileInfo decode_tile(int tile, int tiles_m, int tiles
   return t;
 }
 
-template <int BN, int MODE, int EPI, int EW, int OCC>
-__global__ void __launch_bounds__(gemm_threads(EW), OCC)
+template <int BN, int MODE, int EPI, int OCC>
+__global__ void __launch_bounds__(gemm_threads(epi_warps(BN, EPI)), OCC)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC2, int M, int N, int K, int ntaps,
                 int tap_w, int tap_sign,
-                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, int n_cbuf, int n_rbuf, GemmEpi epi) {
+                int iters_per_split, int tiles_m, int tiles_n, int total_tiles, int STAGES, int KCH, int epi_bytes, GemmEpi epi) {
   using Cfg = GemmCfg<BN>;
+  constexpr int EW = epi_warps(BN, EPI);
   constexpr int EPI_WARPS = EW;
-  constexpr int EPI_THREADS = EW * 32;
-  constexpr int NGRP = EW / 4;                  // warps sharing one TMEM lane quarter
-  static_assert(EPI == 0 ? EW == 8 : (OCC == 1 ? EW == 16 : EW == 8), "TMA epilogue: 16 epilogue warps (8 with two CTAs per SM); staged epilogue: 8");
   static_assert(OCC == 1 || (OCC == 2 && BN <= 128), "two CTAs per SM: 2 x BN <= 256 TMEM columns each");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -315,9 +313,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator stage drained by the epilogue
-  uint64_t* rfull_bar = tempty_bar + 2;          // [4] residual / aux chunk landed (EPI 1)
-  uint64_t* rempty_bar = rfull_bar + 4;          // [4] ... and consumed by every epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 4);
+  uint64_t* win_bar = tempty_bar + 2;            // [16][2] per epilogue warp: inputs (residual / aux slab, shift values) of a tile landed (EPI 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(win_bar + 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -342,10 +339,7 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], EPI_WARPS);
     }
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(&rfull_bar[s], 1);
-      mbar_init(&rempty_bar[s], EPI_WARPS);
-    }
+    for (int s = 0; s < 32; ++s) mbar_init(&win_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -461,75 +455,38 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
       }
       dbg_stamp(epi, 6);
     }
-  } else if (warp == 2) {
-    // ===================== epilogue loader =====================
-    // One thread streams the residual / aux tiles of every 64-column output chunk of this CTA into a ring of n_rbuf
-    // swizzled smem buffers, running ahead of the epilogue warps (rempty / rfull mbarriers). It used to be the elected
-    // epilogue thread's job after every chunk barrier: ~200 serial single-thread instructions (tile decode, two TMA
-    // issues) on the critical path of all sixteen epilogue warps, and a fixed look-ahead of two chunks.
-    if (EPI == 1 && lane == 0 && (epi.residual != nullptr || epi.aux != nullptr || epi.shift_smem)) {
-      constexpr int CPT = BN / 64;
-      const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr, has_out2 = epi.out2 != nullptr, has_sh = epi.shift_smem != 0;
-      uint8_t* rbuf = stg_base + n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1);
-      uint8_t* xbuf = rbuf + (has_res ? n_rbuf * CHUNK_BYTES : 0);
-      const uint32_t sbuf32 = smem_u32(xbuf + (has_aux ? n_rbuf * CHUNK_BYTES : 0));   // [n_rbuf][64 floats] shift values of the chunk
-      const uint32_t bytes = CHUNK_BYTES * ((has_res ? 1 : 0) + (has_aux ? 1 : 0));
-      int g = 0;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
-        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
-        for (int c = 0; c < CPT; ++c, ++g) {
-          const int b = g & (n_rbuf - 1);
-          const uint32_t ph = (g / n_rbuf) & 1;
-          const int ncols = min(64, N - (t.n0 + c * 64));                  // N % 8 == 0: a multiple of 8 floats = 32 bytes
-          const uint32_t sbytes = (has_sh && ncols > 0) ? static_cast<uint32_t>(ncols) * 4u : 0u;
-          mbar_wait(&rempty_bar[b], ph ^ 1);
-          mbar_expect_tx(&rfull_bar[b], bytes + sbytes);
-          if (has_res) tma_load_2d(rbuf + b * CHUNK_BYTES, &tmR, &rfull_bar[b], t.n0 + c * 64, t.m0);
-          if (has_aux) tma_load_2d(xbuf + b * CHUNK_BYTES, &tmX, &rfull_bar[b], t.n0 + c * 64, t.m0);
-          if (sbytes) bulk_load_1d(sbuf32 + b * 256, epi.shift + t.n0 + c * 64, sbytes, &rfull_bar[b]);
-        }
-      }
-    }
   } else {
     // ===================== epilogue warps =====================
     auto release_acc = [&](uint64_t* bar) { mbar_arrive(bar); };   // hand the accumulator stage back to the MMA warp
     const uint64_t dseed = epi.drop_thresh ? drop_seed(epi.seed, epi.seed_off) : 0ull;   // after pdl_wait: the word is device data
-    const int ew = warp - 3;          // 0 .. EW-1
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int grp = ew >> 2;          // two warps share each lane quarter and split the columns
+    const int ew = warp - 2;          // 0 .. EW-1
+    const int q = warp & 3;           // TMEM lane quarter this warp may access (any four consecutive warps cover all four)
+    const int grp = ew >> 2;          // EPI 1: the 64-column chunk of the tile this warp owns; EPI 0: which half of the chunks
     int local = 0;
 
     if (EPI == 1) {
-      // ---------- TMA epilogue: bf16 output ----------
-      // The four warp groups of a TMEM lane quarter (32 output rows) form an independent unit: they own rows q*32 .. q*32+31
-      // of every 128 x 64 output chunk, synchronise among themselves (named barrier 1+q, 128 threads - not the whole CTA) and
-      // their first lane issues the TMA store of that 32-row slab. All shared-memory traffic goes through explicit 32-bit
-      // shared addresses (ld/st.shared.v4) whose per-thread swizzled offsets are computed ONCE: the first version indexed the
-      // buffers through generic pointers and spent ~250 instructions per 16 columns, most of them 64-bit address arithmetic -
-      // every GEMM of the step was bound by the ISSUE rate of its epilogue (profiles/r02c_gemm_cta_timeline.txt: 7.3 k cycles
-      // for a bias-only 128 x 256 tile against 6.1 k cycles of MMA).
-      constexpr int CPT = BN / 64;                      // 64-column chunks per tile
-      constexpr int NCW = 64 / NGRP;                    // columns of a chunk owned by this warp: 16 (16 warps) or 32 (8 warps)
-      constexpr int NC = 16;                            // ... worked off 16 at a time (one tcgen05.ld.x16)
-      constexpr int NSUB = NCW / NC;
-      constexpr int NUW = NCW / 8;                      // 16-byte units of a chunk row owned by this warp
-      constexpr int QT = NGRP * 32;                     // threads of one lane-quarter unit
-      const bool has_out2 = epi.out2 != nullptr;        // pre-activation stash: a second set of output chunks
+      // ---------- TMA epilogue: bf16 output, warp-private pipelines ----------
+      // This warp owns rows q*32 .. q*32+31, columns grp*64 .. grp*64+63 of every tile. Shared memory of the warp:
+      //   S0  [32 x 128 B, 128B-swizzled]  residual slab in (TMA load), output slab out (written in place, TMA store)
+      //   S1  [32 x 128 B]                 aux slab in, or second output (pre-activation stash / gelu') out
+      //   SH  [2][64 floats]               shift values of the chunk, double-buffered
+      // Lane 0 requests the inputs of the warp's NEXT tile right after the store of the current one has read the slab, i.e.
+      // one main loop before they are needed. All shared-memory traffic uses explicit 32-bit shared addresses whose per-thread
+      // swizzled offsets are computed once.
+      constexpr int NC = 16;                            // columns per pass (one tcgen05.ld.x16)
+      constexpr int NPASS = 64 / NC;
+      const bool has_out2 = epi.out2 != nullptr;        // pre-activation stash: a second output slab
       const bool has_res = epi.residual != nullptr, has_aux = epi.aux != nullptr;
       const bool has_shift = epi.shift != nullptr, sh_smem = epi.shift_smem != 0;
-      const bool has_in = has_res || has_aux || sh_smem;            // the loader warp fills a ring slot for every chunk
-      const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: cooperative coalesced stores instead of TMA
-      const uint32_t cbuf32 = smem_u32(stg_base);       // [n_cbuf][128 x 128 B] output chunks
-      const uint32_t c2buf32 = cbuf32 + n_cbuf * CHUNK_BYTES;
-      const uint32_t rbuf32 = c2buf32 + (has_out2 ? n_cbuf * CHUNK_BYTES : 0);   // [n_rbuf] residual chunks, filled by the loader warp
-      const uint32_t xbuf32 = rbuf32 + (has_res ? n_rbuf * CHUNK_BYTES : 0);     // [n_rbuf] aux chunks
-      const uint32_t sbuf32 = xbuf32 + (has_aux ? n_rbuf * CHUNK_BYTES : 0) + grp * (NCW * 4);   // [n_rbuf][64] shift values: this warp's columns
-      const int row = q * 32 + lane;                    // row inside the 128-row tile
-      const int qtid = grp * 32 + lane;                 // index inside the lane-quarter unit
-      const bool qlead = qtid == 0;
-      uint32_t off[NUW];                                // this thread's 16-byte units of a chunk row (128-byte swizzle applied)
-#pragma unroll
-      for (int j = 0; j < NUW; ++j) off[j] = row * 128 + (((grp * NUW + j) ^ (row & 7)) << 4);
+      const bool has_in = has_res || has_aux || sh_smem;
+      const bool second = (has_res && has_aux) || has_out2;     // aux alone lives in S0 (read, then overwritten in place by the output)
+      const bool remap = epi.rowmap != CB_ROWMAP_NONE;  // output rows are re-mapped: coalesced stores by the warp instead of TMA
+      const uint32_t s0 = smem_u32(stg_base) + ew * SLAB_BYTES;
+      const uint32_t s1 = second ? smem_u32(stg_base) + (EW + ew) * SLAB_BYTES : s0;
+      const uint32_t sh = smem_u32(stg_base) + EW * SLAB_BYTES * (second ? 2 : 1) + ew * 512;
+      uint64_t* my_bar = win_bar + ew * 2;              // [2]: inputs of this warp's even / odd tiles
+      const int swz = lane & 7;                         // 128B-swizzle XOR of this thread's slab row (row = lane)
+      const uint32_t rowb = lane * 128;                 // this thread's 128-byte slab row; its 16-byte unit u sits at rowb + ((u ^ swz) << 4)
       // epilogue kind, fixed for the launch (see the EK_* functions)
       const bool full = (N & 63) == 0 && epi.scale == nullptr;
       const bool drop = epi.drop_thresh != 0;
@@ -543,160 +500,168 @@ __global__ void __launch_bounds__(gemm_threads(EW), OCC)
       }
       const bool kind_relu = epi.act == CB_ACT_RELU;
       const bool guard = (N & 63) != 0;                 // ragged last chunk: per-float4 column checks in the generic epilogue
-      int g = 0;
+
+      // lane 0: request the inputs of this warp's i-th tile (slab rows / columns outside the tensor are zero-filled by TMA)
+      auto request_inputs = [&](int i, int tile) {
+        const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
+        const int col = t.n0 + grp * 64, rw = t.m0 + q * 32;
+        const int ncols = min(64, N - col);                                // N % 8 == 0: a multiple of 8 floats = 32 bytes
+        const uint32_t sbytes = (sh_smem && ncols > 0) ? static_cast<uint32_t>(ncols) * 4u : 0u;
+        const uint32_t bytes = (has_res ? SLAB_BYTES : 0) + (has_aux ? SLAB_BYTES : 0) + sbytes;
+        uint64_t* bar = my_bar + (i & 1);
+        if (bytes) mbar_expect_tx(bar, bytes);
+        else mbar_arrive(bar);
+        if (has_res) tma_load_2d_s32(s0, &tmR, bar, col, rw);
+        if (has_aux) tma_load_2d_s32(s1, &tmX, bar, col, rw);     // s1 == s0 when there is no residual
+        if (sbytes) bulk_load_1d(sh + (i & 1) * 256, epi.shift + col, sbytes, bar);
+      };
+      if (has_in && lane == 0 && unit < total_tiles) request_inputs(0, unit);
       for (int tile = unit; tile < total_tiles; tile += n_units, ++local) {
         const TileInfo t = decode_tile<BN, MODE>(tile, tiles_m, tiles_n, K, ntaps, iters_per_split);
         const int acc = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
-        const int64_t orow = t.m0 + row;
-        const int ncol0 = t.n0 + grp * NCW;             // this thread's first column of chunk 0
+        const int col0 = t.n0 + grp * 64;               // first column of this warp's slab
+        const int row0 = t.m0 + q * 32;                 // first row of this warp's slab
+        const int64_t orow = row0 + lane;
         mbar_wait(&tfull_bar[acc], acc_ph);
         tc_fence_after();
-        if (qlead && q == 3 && local == 0) dbg_stamp(epi, 7);      // (warp 3 = first epilogue warp)
-        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + grp * NCW;
-#pragma unroll 1
-        for (int c = 0; c < CPT; ++c, ++g) {
-          const int b = g & (n_rbuf - 1);
-          const uint32_t bph = (g / n_rbuf) & 1;
-          const uint32_t cboff = (g & (n_cbuf - 1)) * CHUNK_BYTES;
-          const bool stamp = epi.dbg != nullptr && qlead && q == 3 && local == 0;
-          if (stamp && c < 4) dbg_stamp(epi, 24 + c);            // chunk c of the first tile starts
-          if (has_in) mbar_wait(&rfull_bar[b], bph);
-          if (n_cbuf == 1) {      // single output buffer: this unit's previous TMA store (or cooperative copy) must be done with it
-            if (qlead && !remap) tma_store_wait_read<0>();
+        const bool stamp = epi.dbg != nullptr && ew == 0 && lane == 0 && local == 0;
+        if (stamp) dbg_stamp(epi, 7);
+        if (has_in) mbar_wait(my_bar + (local & 1), (local >> 1) & 1);
+        if (!has_res && !has_aux) {      // nothing was loaded into the slabs: the previous tile's store may still be reading them
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + grp * 64;
+        const uint32_t shb = sh + (local & 1) * 256;
+        // 128 x 256 tiles (576 threads, 96 registers): not unrolled, the four passes share one copy of every epilogue kind in the
+        // i-cache. Narrower tiles have 8 / 4 epilogue warps and registers to spare: two passes in flight per warp give the
+        // schedulers the independent instructions that two warps per scheduler cannot (GELU / dropout passes are latency-bound).
+#pragma unroll(BN <= 128 ? 2 : 1)
+        for (int ps = 0; ps < NPASS; ++ps) {
+          const int nb = col0 + ps * NC;                // global column of f[0]
+          const uint32_t off0 = rowb + (((2 * ps) ^ swz) << 4), off1 = rowb + (((2 * ps + 1) ^ swz) << 4);
+          uint32_t v[NC];
+          __syncwarp();
+          tmem_ld16(trow + ps * NC, v);
+          tmem_ld_wait();
+          if (stamp && ps == 0) dbg_stamp(epi, 16);
+          if (ps == NPASS - 1) {                        // last TMEM read of this tile
+            tc_fence_before();
             __syncwarp();
-            named_bar_sync(5 + q, QT);
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+          uint32_t res16[NC / 2], aux16[NC / 2];
+          if (has_res) {
 #pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            const int nb = ncol0 + c * 64 + sub * NC;   // global column of f[0]
-            uint32_t v[NC];
-            __syncwarp();
-            tmem_ld16(trow + c * 64 + sub * NC, v);
-            tmem_ld_wait();
-            if (stamp && c == 0 && sub == 0) dbg_stamp(epi, 16);   // accumulator columns in registers
-            if (c == CPT - 1 && sub == NSUB - 1) {      // last TMEM read of this tile
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) release_acc(&tempty_bar[acc]);
+            for (int j = 0; j < 2; ++j) {
+              const uint4 u = lds128(s0 + (j ? off1 : off0));
+              res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
             }
-            uint32_t res16[NC / 2], aux16[NC / 2];
-            if (has_res) {
+          }
+          if (has_aux) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint4 u = lds128(rbuf32 + b * CHUNK_BYTES + off[sub * 2 + j]);
-                res16[4 * j] = u.x; res16[4 * j + 1] = u.y; res16[4 * j + 2] = u.z; res16[4 * j + 3] = u.w;
-              }
+            for (int j = 0; j < 2; ++j) {
+              const uint4 u = lds128(s1 + (j ? off1 : off0));
+              aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
             }
-            if (has_aux) {
+          }
+          float shv[NC];                                // shift (bias / FrozenBN shift) of these columns
+          if (sh_smem) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint4 u = lds128(xbuf32 + b * CHUNK_BYTES + off[sub * 2 + j]);
-                aux16[4 * j] = u.x; aux16[4 * j + 1] = u.y; aux16[4 * j + 2] = u.z; aux16[4 * j + 3] = u.w;
-              }
+            for (int j = 0; j < NC / 4; ++j) {          // every lane reads the same 16 bytes: a shared-memory broadcast
+              const uint4 u = lds128(shb + ps * (NC * 4) + j * 16);
+              shv[4 * j] = __uint_as_float(u.x); shv[4 * j + 1] = __uint_as_float(u.y);
+              shv[4 * j + 2] = __uint_as_float(u.z); shv[4 * j + 3] = __uint_as_float(u.w);
             }
-            float shv[NC];                              // shift (bias / FrozenBN shift) of these columns
-            if (sh_smem) {
+          } else if (has_shift) {
 #pragma unroll
-              for (int j = 0; j < NC / 4; ++j) {        // every lane reads the same 16 bytes: a shared-memory broadcast
-                const uint4 u = lds128(sbuf32 + b * 256 + sub * (NC * 4) + j * 16);
-                shv[4 * j] = __uint_as_float(u.x); shv[4 * j + 1] = __uint_as_float(u.y);
-                shv[4 * j + 2] = __uint_as_float(u.z); shv[4 * j + 3] = __uint_as_float(u.w);
-              }
-            } else if (has_shift) {
+            for (int j = 0; j < NC; j += 4) {
+              float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!guard || nb + j + 4 <= N) s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
+              shv[j] = s4.x; shv[j + 1] = s4.y; shv[j + 2] = s4.z; shv[j + 3] = s4.w;
+            }
+          }
+          float f[NC];
 #pragma unroll
-              for (int j = 0; j < NC; j += 4) {
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!guard || nb + j + 4 <= N) s4 = __ldg(reinterpret_cast<const float4*>(epi.shift + nb + j));
-                shv[j] = s4.x; shv[j + 1] = s4.y; shv[j + 2] = s4.z; shv[j + 3] = s4.w;
-              }
-            }
-            if (has_in && sub == NSUB - 1) {            // this warp has its residual / aux / shift values in registers: hand the slot back
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&rempty_bar[b]);
-            }
-            float f[NC];
-#pragma unroll
-            for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
-            uint32_t o2_16[NC / 2];
-            switch (kind) {
-              case EK_SHIFT_ACT: epilogue_shift_act<NC>(f, shv, has_shift, res16, has_res, kind_relu); break;
-              case EK_RELU_MASK: epilogue_relu_mask<NC>(f, res16, has_res, aux16); break;
-              case EK_DROP_RES:
-                epilogue_drop_res<NC>(f, shv, has_shift, res16, has_res, dseed, static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb, epi.drop_thresh,
-                                      epi.drop_inv_keep);
-                break;
-              case EK_GELU_STASH: epilogue_gelu_stash<NC>(f, shv, has_shift, o2_16); break;
-              case EK_AUX_MUL: epilogue_aux_mul<NC>(f, res16, has_res, aux16); break;
-              default:
-                if (guard) epilogue_math<NC, true>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
-                else epilogue_math<NC, false>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
-            }
-            if (stamp && c == 0 && sub == 0) dbg_stamp(epi, 17);   // residual / aux read, epilogue math done
-            if (has_out2) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-                sts128(c2buf32 + cboff + off[sub * 2 + j], make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]));
-            }
+          for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]);
+          uint32_t o2_16[NC / 2];
+          switch (kind) {
+            case EK_SHIFT_ACT: epilogue_shift_act<NC>(f, shv, has_shift, res16, has_res, kind_relu); break;
+            case EK_RELU_MASK: epilogue_relu_mask<NC>(f, res16, has_res, aux16); break;
+            case EK_DROP_RES:
+              epilogue_drop_res<NC>(f, shv, has_shift, res16, has_res, dseed, static_cast<uint64_t>(orow) * static_cast<uint64_t>(N) + nb, epi.drop_thresh,
+                                    epi.drop_inv_keep);
+              break;
+            case EK_GELU_STASH: epilogue_gelu_stash<NC>(f, shv, has_shift, o2_16); break;
+            case EK_AUX_MUL: epilogue_aux_mul<NC>(f, res16, has_res, aux16); break;
+            default:
+              if (guard) epilogue_math<NC, true>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
+              else epilogue_math<NC, false>(f, epi, shv, has_shift, dseed, nb, N, orow, res16, has_res, aux16, has_aux, o2_16, has_out2);
+          }
+          if (stamp && ps == 0) dbg_stamp(epi, 17);
+          if (has_out2) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              sts128(cbuf32 + cboff + off[sub * 2 + j],
-                     make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
+              sts128(s1 + (j ? off1 : off0), make_uint4(o2_16[4 * j], o2_16[4 * j + 1], o2_16[4 * j + 2], o2_16[4 * j + 3]));
           }
-          if (stamp && c == 0) dbg_stamp(epi, 18);               // chunk written to shared memory
-          if (!remap) {
-            fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the TMA store
-            if (stamp && c == 0) dbg_stamp(epi, 19);
-            if (qlead && n_cbuf > 1) tma_store_wait_read<0>();   // the buffer the NEXT chunk writes must be free again
-          }
-          if (stamp && c == 0) dbg_stamp(epi, 20);
-          __syncwarp();
-          named_bar_sync(1 + q, QT);
-          if (stamp && c == 0) dbg_stamp(epi, 21);
-          if (!remap) {
-            if (qlead) {                                // this unit's 32 rows x 64 columns
-              tma_store_2d_s32(&tmC, cbuf32 + cboff + q * 4096, t.n0 + c * 64, t.m0 + q * 32);
-              if (has_out2) tma_store_2d_s32(&tmC2, c2buf32 + cboff + q * 4096, t.n0 + c * 64, t.m0 + q * 32);
-              tma_store_commit();
-            }
-          } else {
-            // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 threads move one 128-byte row segment, QT / 8 rows
-            // per pass; with two buffers a buffer is rewritten two chunks later, after this unit's next named barrier
-            const int seg = qtid & 7;
-            const int n = t.n0 + c * 64 + seg * 8;
-            constexpr int ROWS_PER_PASS = QT / 8;
 #pragma unroll
-            for (int pass = 0; pass < 32 / ROWS_PER_PASS; ++pass) {
-              const int r = q * 32 + (qtid >> 3) + pass * ROWS_PER_PASS;
-              const int mm = t.m0 + r;
-              bool ok = mm < M && n + 8 <= N;
-              int64_t orr = mm;
-              if (epi.rowmap == CB_ROWMAP_PAD) {
-                const int hw = epi.H * epi.W;
-                const int img = mm / hw;
-                const int rr = mm - img * hw;
-                const int y = rr / epi.W, x = rr - y * epi.W;
-                orr = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
-              } else {
-                const int wp = epi.W + 2, hp = epi.H + 2;
-                const int img = mm / (hp * wp);
-                const int rr = mm - img * (hp * wp);
-                const int y = rr / wp, x = rr - y * wp;
-                ok = ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
-                orr = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
-              }
-              if (ok)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orr * epi.out_ld + n) =
-                    lds128(cbuf32 + cboff + r * 128 + ((seg ^ (r & 7)) << 4));
-            }
-          }
+          for (int j = 0; j < 2; ++j)
+            sts128(s0 + (j ? off1 : off0), make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                    pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
         }
-        if (qlead && q == 3 && local == 0) dbg_stamp(epi, 14);
+        if (stamp) dbg_stamp(epi, 18);
+        const bool in_range = row0 < M && col0 < N;     // (a slab entirely outside the tensor is not stored)
+        if (!remap) {
+          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            if (in_range) {
+              tma_store_2d_s32(&tmC, s0, col0, row0);
+              if (has_out2) tma_store_2d_s32(&tmC2, s1, col0, row0);
+            }
+            tma_store_commit();
+          }
+        } else {
+          // row-re-mapped output (zero-bordered <-> compact pixel rows): 8 lanes move one 128-byte row segment, 4 rows per pass
+          __syncwarp();
+          const int seg = lane & 7;
+          const int n = col0 + seg * 8;
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 4 + (lane >> 3);
+            const int mm = row0 + r;
+            bool ok = mm < M && n + 8 <= N;
+            int64_t orr = mm;
+            if (epi.rowmap == CB_ROWMAP_PAD) {
+              const int hw = epi.H * epi.W;
+              const int img = mm / hw;
+              const int rr = mm - img * hw;
+              const int y = rr / epi.W, x = rr - y * epi.W;
+              orr = (static_cast<int64_t>(img) * (epi.H + 2) + y + 1) * (epi.W + 2) + x + 1;
+            } else {
+              const int wp = epi.W + 2, hp = epi.H + 2;
+              const int img = mm / (hp * wp);
+              const int rr = mm - img * (hp * wp);
+              const int y = rr / wp, x = rr - y * wp;
+              ok = ok && y >= 1 && y <= epi.H && x >= 1 && x <= epi.W;
+              orr = (static_cast<int64_t>(img) * epi.H + (y - 1)) * epi.W + (x - 1);
+            }
+            if (ok)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + orr * epi.out_ld + n) = lds128(s0 + r * 128 + ((seg ^ (r & 7)) << 4));
+          }
+          __syncwarp();                                 // every lane has read the slab before it is handed to the next loads
+        }
+        if (stamp) dbg_stamp(epi, 14);
+        // inputs of this warp's next tile: the slabs are free once this tile's store has read them
+        if (has_in && lane == 0 && tile + n_units < total_tiles) {
+          if (!remap && (has_res || has_aux)) tma_store_wait_read<0>();
+          request_inputs(local + 1, tile + n_units);
+        }
       }
-      if (qlead && q == 3) dbg_stamp(epi, 8);
-      if (qlead) tma_store_wait_all<0>();               // every unit drains its own bulk groups before the CTA may exit
-      if (qlead && q == 3) dbg_stamp(epi, 9);
+      if (ew == 0 && lane == 0) dbg_stamp(epi, 8);
+      if (lane == 0) tma_store_wait_all<0>();           // every warp drains its own bulk groups before the CTA may exit
+      if (ew == 0 && lane == 0) dbg_stamp(epi, 9);
     } else {
       // ---------- staged epilogue: row re-map, fp32 output, pre-activation stash, wgrad accumulation ----------
       uint8_t* stg = stg_base + ew * STG_BYTES;
@@ -930,45 +895,27 @@ static long long* g_gemm_timeline = nullptr;
 static int g_force_kch = 0;   // tuning hook: chunks per stage (0 = automatic)
 static int g_mn3d = 1;        // 1 (default) = MN-major operands through one 3-D TMA box per k-chunk (GemmEpi::mn3d); cb_debug_gemm_mn3d
 
-// Shared-memory plan of one launch: epilogue buffers first, then as many 64-deep operand chunks as fit, grouped KCH per
-// stage. Measured (profiles/r01_gemm_kch_probe.txt, r01_gemm_staged_probe.txt): every stage costs a ~450-cycle barrier
-// round trip whatever its size, so deep stages beat many stages (1312x768x3072: 26.5 / 18.3 / 15.8 us with 1 / 2 / 4
-// chunks per stage); two output buffers perform like four.
+// Shared-memory plan of one launch: epilogue region first (TMA epilogue: one 4 KB slab per epilogue warp, a second one when the
+// launch has an aux input or a second output, 2 x 256 B of shift values per warp), then as many 64-deep operand chunks as fit,
+// grouped KCH per stage. Measured (profiles/r01_gemm_kch_probe.txt, r01_gemm_staged_probe.txt): every stage costs a ~450-cycle
+// barrier round trip whatever its size, so deep stages beat many stages (1312x768x3072: 26.5 / 18.3 / 15.8 us with 1 / 2 / 4
+// chunks per stage).
 struct SmemPlan {
-  int epi_bytes, n_cbuf, n_rbuf, kch, stages, chunk_bytes;
+  int epi_bytes, kch, stages, chunk_bytes;
 };
 constexpr int SMEM_LIMIT_OCC2 = 113 * 1024;   // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
-static SmemPlan plan_smem(int bn, bool tma_epi, bool has_res, bool has_aux, bool has_out2, int kiters, int force_kch = 0, int occ = 1, bool sh_smem = false) {
+static SmemPlan plan_smem(int bn, bool tma_epi, bool second, bool sh_smem, int kiters, int force_kch = 0, int occ = 1) {
   SmemPlan p;
   const int limit = occ == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
   p.chunk_bytes = BM * BK * 2 + bn * BK * 2;
-  p.n_cbuf = 2;
-  p.n_rbuf = 2;
-  const int n_in = (has_res ? 1 : 0) + (has_aux ? 1 : 0);
-  auto epi_bytes_for = [&](int n_cbuf, int n_rbuf) {
-    return n_cbuf * CHUNK_BYTES * (has_out2 ? 2 : 1) + n_rbuf * CHUNK_BYTES * n_in + (sh_smem ? 1024 : 0);   // + [<= 4][64 floats] shift slots
-  };
-  auto fit = [&](int n_cbuf, int n_rbuf) { return (limit - 1024 - 256 - epi_bytes_for(n_cbuf, n_rbuf)) / p.chunk_bytes; };
   if (tma_epi) {
-    if (occ == 2) {
-      // half the shared memory: give up output / residual buffers (the co-resident CTA covers the exposed latency) until a
-      // two-chunk operand ring fits
-      static const int tries[4][2] = {{2, 2}, {1, 2}, {1, 1}, {1, 1}};
-      for (int t = 0; t < 3; ++t) {
-        p.n_cbuf = tries[t][0];
-        p.n_rbuf = tries[t][1];
-        if (fit(p.n_cbuf, p.n_rbuf) >= 2) break;
-      }
-    } else if (n_in > 0 && kiters <= 2 && fit(p.n_cbuf, 4) >= kiters + 1) {
-      // short K loops (the HBM-bound 1x1 convs) need little operand ring: spend the smem on a deeper residual / aux ring instead
-      // (4 x 16 KB per tensor in flight per SM against the ~2 us loaded HBM latency)
-      p.n_rbuf = 4;
-    }
-    p.epi_bytes = epi_bytes_for(p.n_cbuf, p.n_rbuf);
+    const int ew = epi_warps(bn, 1);
+    p.epi_bytes = ew * SLAB_BYTES * (second ? 2 : 1) + (sh_smem ? ew * 512 : 0);
+    p.epi_bytes = (p.epi_bytes + 1023) & ~1023;
   } else {
     p.epi_bytes = (8 * STG_BYTES + 1023) & ~1023;     // staged epilogue: always 8 warps
   }
-  const int chunks_fit = (limit - 1024 - 256 - p.epi_bytes) / p.chunk_bytes;
+  const int chunks_fit = (limit - 1024 - GemmCfg<64>::BAR_BYTES - p.epi_bytes) / p.chunk_bytes;
   p.kch = 1;
   if (force_kch > 0) p.kch = force_kch;
   else if (g_force_kch > 0) p.kch = g_force_kch;
@@ -983,14 +930,14 @@ static SmemPlan plan_smem(int bn, bool tma_epi, bool has_res, bool has_aux, bool
   return p;
 }
 
-template <int BN, int MODE, int EPI, int EW = 8, int OCC = 1>
+template <int BN, int MODE, int EPI, int OCC = 1>
 static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_t stream) {
   GemmEpi epi = epi_in;
   using Cfg = GemmCfg<BN>;
-  constexpr int GEMM_THREADS = gemm_threads(EW);
+  constexpr int GEMM_THREADS = gemm_threads(epi_warps(BN, EPI));
   constexpr int LIMIT = OCC == 2 ? SMEM_LIMIT_OCC2 : SMEM_LIMIT;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE, EPI, EW, OCC>;
+  auto kern = gemm_kernel<BN, MODE, EPI, OCC>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LIMIT);
     if (e == cudaSuccess && OCC == 2)   // both CTAs of an SM need their 113 KB: ask for the full shared-memory carve-out
@@ -1035,17 +982,17 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
   if (!ok) return CB_ERR_CUDA;
   tc = tr = tx = tc2 = ta;   // placeholders for the maps this launch does not use (a __grid_constant__ parameter must be a valid object)
   if (EPI == 1) {
-    // output maps: one box = the 32 rows x 64 columns a lane-quarter unit of the epilogue stores
+    // epilogue maps: one box = the 32-row x 64-column slab one epilogue warp loads / stores
     if (d.rowmap == CB_ROWMAP_NONE && !get_tmap_2d(&tc, d.out, d.n, d.m, d.out_ld, 64, 32)) return CB_ERR_CUDA;
-    if (d.residual && !get_tmap_2d(&tr, d.residual, d.n, d.m, d.res_ld, 64, BM)) return CB_ERR_CUDA;
-    if (d.aux && !get_tmap_2d(&tx, d.aux, d.n, d.m, d.aux_ld, 64, BM)) return CB_ERR_CUDA;
+    if (d.residual && !get_tmap_2d(&tr, d.residual, d.n, d.m, d.res_ld, 64, 32)) return CB_ERR_CUDA;
+    if (d.aux && !get_tmap_2d(&tx, d.aux, d.n, d.m, d.aux_ld, 64, 32)) return CB_ERR_CUDA;
     if (d.out2 && !get_tmap_2d(&tc2, d.out2, d.n, d.m, d.out2_ld, 64, 32)) return CB_ERR_CUDA;
   }
   epi.mn3d = mn3d ? 1 : 0;
   const bool sh_smem = EPI == 1 && d.shift != nullptr && (reinterpret_cast<uintptr_t>(d.shift) & 15) == 0;
   epi.shift_smem = sh_smem ? 1 : 0;
-  const SmemPlan sp = plan_smem(BN, EPI == 1, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, kiters, (d.reserved >> 8) & 15, OCC, sh_smem);
-  const int epi_bytes = sp.epi_bytes, n_cbuf = sp.n_cbuf, n_rbuf = sp.n_rbuf, kch = sp.kch, stages = sp.stages;
+  const SmemPlan sp = plan_smem(BN, EPI == 1, (d.residual && d.aux) || d.out2, sh_smem, kiters, (d.reserved >> 8) & 15, OCC);
+  const int epi_bytes = sp.epi_bytes, kch = sp.kch, stages = sp.stages;
   if (stages < 2) {
     set_error("cb_gemm: not enough shared memory for a 2-stage pipeline (BN=%d, epilogue %d B, %d CTA(s) per SM)", BN, epi_bytes, OCC);
     return CB_ERR_INVALID;
@@ -1054,7 +1001,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
   const int units = sm_count() * OCC;
   const int grid = total < units ? total : units;
   launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
-           iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, n_cbuf, n_rbuf, epi);
+           iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, epi);
   return check_launch("cb_gemm");
 }
 
@@ -1100,13 +1047,16 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, bool tma_epi, int occ = 1)
       const int real_sp = wgrad ? ceil_div(kc, ips) : 1;
       const int64_t tiles = base * real_sp;
       const double rounds = static_cast<double>((tiles + units - 1) / units);
-      const SmemPlan pl = plan_smem(bn, tma_epi && !wgrad, d.residual != nullptr, d.aux != nullptr, d.out2 != nullptr, ips, (d.reserved >> 8) & 15, occ,
-                                    tma_epi && !wgrad && d.shift != nullptr && (reinterpret_cast<uintptr_t>(d.shift) & 15) == 0);
+      const SmemPlan pl = plan_smem(bn, tma_epi && !wgrad, (d.residual && d.aux) || d.out2,
+                                    tma_epi && !wgrad && d.shift != nullptr && (reinterpret_cast<uintptr_t>(d.shift) & 15) == 0, ips, (d.reserved >> 8) & 15, occ);
       if (pl.stages < 2) continue;
+      // a ring of 2 chunks cannot cover the TMA round trip of a long K loop (measured: 128 x 256 tiles on a 2-chunk
+      // ring run their main loop 4x slower, profiles/r02g_gemm_cta_timeline_warp_private.txt, ffn1_fwd bn256)
+      const double shallow = (pl.stages * pl.kch < 3 && ips > 2) ? 3.0 : 1.0;
       // per stage: ~450-cycle barrier round trip + bytes at ~60 B/clk (shared by the CTAs of an SM); per tile: epilogue (fp32 red.add / staged bf16 / TMA bf16)
       const double stage_cost = 450.0 + pl.kch * pl.chunk_bytes / (60.0 / occ);
-      const double epi = wgrad ? bn * 24.0 : (tma_epi ? bn * 12.0 : bn * 30.0);
-      const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost + epi) + 2500.0;
+      const double epi = wgrad ? bn * 24.0 : (tma_epi ? 2000.0 : bn * 30.0);   // TMA epilogue: every warp converts ONE 32 x 64 slab per tile
+      const double cost = rounds * (ceil_div(ips, pl.kch) * stage_cost * shallow + epi) + 2500.0;
       if (cost < best_cost) {
         best_cost = cost;
         best = {bn, real_sp};
@@ -1192,13 +1142,13 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
                            ((d.reserved & 32) ? g_occ2_mode >= 1 : (g_occ2_mode == 2 && (g_occ2_max_gflop <= 0.0 || gflop <= g_occ2_max_gflop)));
     if (want_occ2) {
       const LaunchCfg l2 = choose_config(d, tma_epi, 2);
-      if (l2.bn == 64) return nn ? launch_gemm<64, 2, 1, 8, 2>(d, epi, stream) : launch_gemm<64, 0, 1, 8, 2>(d, epi, stream);
-      if (l2.bn == 128) return nn ? launch_gemm<128, 2, 1, 8, 2>(d, epi, stream) : launch_gemm<128, 0, 1, 8, 2>(d, epi, stream);
+      if (l2.bn == 64) return nn ? launch_gemm<64, 2, 1, 2>(d, epi, stream) : launch_gemm<64, 0, 1, 2>(d, epi, stream);
+      if (l2.bn == 128) return nn ? launch_gemm<128, 2, 1, 2>(d, epi, stream) : launch_gemm<128, 0, 1, 2>(d, epi, stream);
     }
     const LaunchCfg lc = choose_config(d, tma_epi);
 #define CB_DISPATCH(BN_)                                                                                                     \
-  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1, 16>(d, epi, stream) : launch_gemm<BN_, 2, 0, 8>(d, epi, stream))            \
-            : (tma_epi ? launch_gemm<BN_, 0, 1, 16>(d, epi, stream) : launch_gemm<BN_, 0, 0, 8>(d, epi, stream))
+  return nn ? (tma_epi ? launch_gemm<BN_, 2, 1>(d, epi, stream) : launch_gemm<BN_, 2, 0>(d, epi, stream))            \
+            : (tma_epi ? launch_gemm<BN_, 0, 1>(d, epi, stream) : launch_gemm<BN_, 0, 0>(d, epi, stream))
     switch (lc.bn) {
       case 64: CB_DISPATCH(64);
       case 128: CB_DISPATCH(128);
@@ -1218,16 +1168,16 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
       const LaunchCfg l2 = choose_config(d, false, 2);
       cb_gemm_desc d2 = d;
       d2.split_k = l2.splits;
-      if (l2.bn == 64) return launch_gemm<64, 1, 0, 8, 2>(d2, epi, stream);
-      if (l2.bn == 128) return launch_gemm<128, 1, 0, 8, 2>(d2, epi, stream);
+      if (l2.bn == 64) return launch_gemm<64, 1, 0, 2>(d2, epi, stream);
+      if (l2.bn == 128) return launch_gemm<128, 1, 0, 2>(d2, epi, stream);
     }
     const LaunchCfg lc = choose_config(d, false);
     cb_gemm_desc d2 = d;
     d2.split_k = lc.splits;
     switch (lc.bn) {
-      case 64: return launch_gemm<64, 1, 0, 8>(d2, epi, stream);
-      case 128: return launch_gemm<128, 1, 0, 8>(d2, epi, stream);
-      case 256: return launch_gemm<256, 1, 0, 8>(d2, epi, stream);
+      case 64: return launch_gemm<64, 1, 0>(d2, epi, stream);
+      case 128: return launch_gemm<128, 1, 0>(d2, epi, stream);
+      case 256: return launch_gemm<256, 1, 0>(d2, epi, stream);
       default: CB_REQUIRE(false, "cb_gemm(WGRAD): block_n must be 0, 64, 128 or 256 (got %d)", lc.bn);
     }
   }

@@ -177,10 +177,21 @@ class ClipBert(nn.Module):
         for n, p in self.cnn.feature.named_parameters():
             p.requires_grad = False
 
+    # keys the reference checkpoints carry for parts of detectron2 that are dead on this path: never an error
+    _DEAD_D2_KEYS = ("cnn.feature.proposal_generator.", "cnn.feature.roi_heads.", "cnn.feature.pixel_mean", "cnn.feature.pixel_std")
+
     def load_state_dict(self, state_dict, strict=True, **kw):
-        """Accepts the reference checkpoint layout; silently drops the dead d2 heads."""
+        """Accepts the reference checkpoint layout. The dead d2 heads and BatchNorm's ``num_batches_tracked`` are dropped
+        silently; with ``strict=True`` (the default, as ``model.load_state_dict(ckpt)`` in the reference's TrainingRestorer,
+        src/utils/load_save.py:283-300) any OTHER unexpected key and any missing key raises, like ``nn.Module.load_state_dict``."""
         own = self.state_dict()
+        dead = [k for k in state_dict if k.startswith(self._DEAD_D2_KEYS) or k.endswith("num_batches_tracked")]
         sd = {k: v for k, v in state_dict.items() if k in own}
+        if strict:
+            unexpected = sorted(k for k in state_dict if k not in own and k not in dead)
+            missing = sorted(k for k in own if k not in state_dict)
+            if unexpected or missing:
+                raise RuntimeError("Error(s) in loading state_dict for ClipBert: missing keys %s, unexpected keys %s" % (missing[:8], unexpected[:8]))
         out = super().load_state_dict(sd, strict=False)
         self.cnn.mark_weights_updated()
         self.transformer.mark_weights_updated()

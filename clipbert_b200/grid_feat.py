@@ -172,20 +172,24 @@ class GridFeatBackbone(nn.Module):
     def config_file(self):
         return _D2_CONFIG_TEXT % self.freeze_at
 
-    def load_state_dict(self, state_dict, strict=False, **kw):   # noqa: D401 (tolerant of the dead d2 heads)
-        if isinstance(state_dict, str):
-            state_dict = torch.load(state_dict, map_location="cpu")
-            state_dict = state_dict.get("model", state_dict)
-        own = self.state_dict()
-        filtered = {}
-        for k, v in state_dict.items():
-            k2 = k[len("feature."):] if False else k
-            if k2 in own:
-                filtered[k2] = v if torch.is_tensor(v) else torch.as_tensor(v)
-            elif "backbone." in k and ("feature." + k) in own:     # bare d2 checkpoint keys
-                filtered["feature." + k] = v if torch.is_tensor(v) else torch.as_tensor(v)
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        """``GridFeatBackbone.load_state_dict(path)`` in the reference (src/modeling/grid_feat.py:72-80) hands a checkpoint PATH to
+        d2's DetectionCheckpointer: ``.pth`` or the MSRA ``R-50.pkl`` pickles, d2 key names relative to ``feature``. A dict is
+        taken as a state dict (module keys, bare d2 keys, or ``cnn.``-prefixed). Shapes must match; keys of the dead d2 heads are
+        ignored and returned in ``.ignored``. A missing path is an error that names it."""
+        import os
+
+        from . import load_save
+        if isinstance(state_dict, (str, bytes, os.PathLike)):
+            if not os.path.exists(state_dict):
+                raise FileNotFoundError("GridFeatBackbone.load_state_dict: checkpoint %r does not exist (the reference falls back to the d2 "
+                                        "config's MODEL.WEIGHTS URL, which this offline path cannot download)" % (state_dict,))
+        loaded, ignored = load_save.load_detectron2_checkpoint(self, state_dict)
         self._dirty = True
-        return super().load_state_dict(filtered, strict=False)
+        missing = sorted(k for k in self.state_dict() if k not in loaded)
+        if strict and missing:
+            raise RuntimeError("GridFeatBackbone.load_state_dict: missing keys %s" % missing[:8])
+        return torch.nn.modules.module._IncompatibleKeys(missing, ignored)
 
     def mark_weights_updated(self):
         self._dirty = True

@@ -237,7 +237,7 @@ def gemm(**kw):
     if _tuning and "block_n" not in kw and "reserved" not in kw:
         t = _tuning.get(gemm_key(kw))
         if t is not None:
-            kw = dict(kw, block_n=t[0], split_k=t[1], reserved=t[2] << 8)
+            kw = dict(kw, block_n=t[0], split_k=t[1], reserved=(t[2] << 8) | (32 if (len(t) > 3 and t[3]) else 0))
     d = L.GemmDesc()
     d.ntaps = 1
     d.tap_sign = 1

@@ -130,9 +130,14 @@ class FusedAdamW(Optimizer):
                                exp_avg=m_buf, exp_avg_sq=v_buf, scales=mod.optimizer_scales(), params=[p for p, _ in views]))
             mod._optimizer_emits_packed = True
         ng = len(self.param_groups)
-        self._hyper_host = torch.zeros(ng, 8, dtype=torch.float32)
-        if dev.type == "cuda":
-            self._hyper_host = self._hyper_host.pin_memory()
+        # per-step hyper-parameters travel through a small RING of pinned staging buffers, each guarded by an event: the host
+        # may run several steps ahead of the device (no .item() in the loop), and rewriting ONE pinned buffer before its
+        # asynchronous copy has executed would hand step t the learning rate / bias correction of step t+1
+        self._hyper_ring = []
+        for _ in range(4):
+            h = torch.zeros(ng, 8, dtype=torch.float32)
+            self._hyper_ring.append([h.pin_memory() if dev.type == "cuda" else h, None])
+        self._hyper_slot = 0
         self._hyper_dev = torch.zeros(ng, 8, dtype=torch.float32, device=dev)
         self._gsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._plan = halves
@@ -164,6 +169,11 @@ class FusedAdamW(Optimizer):
     def step(self, closure=None, zero_grad=False):
         loss = closure() if closure is not None else None
         plan = self._ensure_plan()
+        slot = self._hyper_ring[self._hyper_slot]
+        self._hyper_slot = (self._hyper_slot + 1) % len(self._hyper_ring)
+        if slot[1] is not None:
+            slot[1].synchronize()          # the copy that last read this staging buffer has executed
+        hyper_host = slot[0]
         for gi, g in enumerate(self.param_groups):
             self._group_steps[gi] += 1
             t = self._group_steps[gi]
@@ -171,8 +181,11 @@ class FusedAdamW(Optimizer):
             step_size = g["lr"]
             if g["correct_bias"]:      # adamw.py:81-85
                 step_size = step_size * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-            self._hyper_host[gi] = torch.tensor([g["lr"], step_size, g["weight_decay"], b1, b2, g["eps"], 0.0, 0.0])
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            hyper_host[gi] = torch.tensor([g["lr"], step_size, g["weight_decay"], b1, b2, g["eps"], 0.0, 0.0])
+        self._hyper_dev.copy_(hyper_host, non_blocking=True)
+        if self._hyper_dev.is_cuda:
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
         clip = self._pending_max_norm > 0
         for h in plan:
             f = h["flat"]
@@ -184,6 +197,23 @@ class FusedAdamW(Optimizer):
             h["mod"].packed_written_by_optimizer()
         self._pending_max_norm = -1.0
         return loss
+
+    # ---- restoring / re-grouping: the plan (flat moment buffers, per-group step counts) is rebuilt from self.state -------------
+    def load_state_dict(self, state_dict):
+        """torch's Optimizer.load_state_dict replaces ``self.state[p]`` with fresh tensors. The kernels work on the flat moment
+        buffers the plan owns, so the plan is dropped here and rebuilt on the next use: ``_build_plan`` adopts the loaded
+        ``exp_avg`` / ``exp_avg_sq`` (copied into the flat buffers, state entries become views again) and the loaded step
+        counts - whether the restore happens before the first step (TrainingRestorer, src/utils/load_save.py:245-300) or later."""
+        super().load_state_dict(state_dict)
+        self._plan = None
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._plan = None
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._plan = None
 
     def zero_grad(self, set_to_none=False):
         """Zero the flat gradient buffers (one memset each); ``step(zero_grad=True)`` does it inside the update kernel."""

@@ -124,3 +124,70 @@ def test_fused_adamw_matches_reference_optimizer(cuda):
     osd = opt.state_dict()
     some = next(iter(osd["state"].values()))
     assert set(some) >= {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_fused_adamw_state_dict_round_trip_after_steps(cuda):
+    """TrainingRestorer (src/utils/load_save.py:245-300) restores the optimizer in the middle of training. torch's
+    load_state_dict replaces the state tensors, so FusedAdamW must re-adopt the restored moments / step counts into its flat
+    buffers: run 2 steps, save, run a 3rd step, restore, re-run the 3rd step with the same gradients -> identical parameters,
+    and both equal the oracle's third step from the saved state."""
+    import copy
+
+    import clipbert_b200 as cb
+    from clipbert_b200.optim import FusedAdamW
+    from oracle import adamw_ref as A, synth
+    sd = synth.full_state_dict(42)
+    cfg = make_cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml")
+    model.load_state_dict(sd)
+    model = model.to(cuda).train()
+    groups = [g for g in e2e_param_groups(model) if g["params"]]
+    opt = FusedAdamW(groups, lr=5e-5, betas=(0.9, 0.98), model=model)
+    batch = synth.synth_batch(1, 2, n_ex=1, size=96, seed=3)
+    model({k: (v.to(cuda) if torch.is_tensor(v) else list(v)) for k, v in batch.items()})["loss"].mean().backward()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    gidx = {id(p): gi for gi, g in enumerate(opt.param_groups) for p in g["params"]}
+    gen = torch.Generator(device=cuda).manual_seed(23)
+
+    def fill_grads(seed_scale):
+        for m in (model.transformer, model.cnn):
+            m._flat.attach_grads()
+            m._flat.grad.zero_()
+            for e in m._flat.entries:
+                if e["param"].requires_grad:
+                    m._flat.grad[e["offset"]: e["offset"] + e["numel"]].copy_(torch.randn(e["numel"], generator=gen, device=cuda) * seed_scale)
+
+    for _ in range(2):
+        fill_grads(1e-5)
+        opt.step(zero_grad=True)
+    saved_opt = copy.deepcopy(opt.state_dict())
+    saved_params = {n: p.detach().clone() for n, p in named}
+    sel = [i for i, (n, p) in enumerate(named) if i % 17 == 0 or n.endswith(("grid_encoder.0.weight", "word_embeddings.weight", "classifier.2.bias"))]
+    mom = {i: (opt.state[named[i][1]]["exp_avg"].detach().float().cpu().clone(), opt.state[named[i][1]]["exp_avg_sq"].detach().float().cpu().clone())
+           for i in sel}
+    fill_grads(2e-5)
+    g3 = {n: p.grad.detach().clone() for n, p in named}
+    opt.step(zero_grad=True)
+    after_a = {n: p.detach().clone() for n, p in named}
+    # ---- restore parameters + optimizer, replay step 3 ----
+    with torch.no_grad():
+        for n, p in named:
+            p.copy_(saved_params[n])
+    model.transformer.mark_weights_updated()
+    model.cnn.mark_weights_updated()
+    opt.load_state_dict(saved_opt)
+    for m in (model.transformer, model.cnn):
+        m._flat.attach_grads()
+    for n, p in named:
+        p.grad.copy_(g3[n])
+    opt.step(zero_grad=True)
+    for n, p in named:
+        assert torch.equal(p.detach(), after_a[n]), n        # the restored run is bit-identical to the uninterrupted one
+    assert all(opt.state[p]["step"] == 3 for _, p in named)
+    # ---- and it is the reference's third step from the saved state ----
+    for i in sel:
+        n_, p = named[i]
+        g = opt.param_groups[gidx[id(p)]]
+        ref, _, _ = A.adamw_step(saved_params[n_].float().cpu(), g3[n_].float().cpu(), mom[i][0], mom[i][1], 3, g["lr"], g["betas"], g["eps"],
+                                 g["weight_decay"], g["correct_bias"])
+        assert relerr(p.detach().float().cpu(), ref) < 2e-6, n_

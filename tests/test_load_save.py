@@ -106,3 +106,53 @@ def test_helpers_agree_with_the_reference_functions(tmp_path):
     ref["load_state_dict_with_mismatch"](a, sd)
     LS.load_state_dict_with_mismatch(b, sd)
     assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+
+
+def test_clipbert_load_state_dict_is_strict_except_for_the_dead_d2_heads():
+    """TrainingRestorer calls model.load_state_dict(ckpt) (src/utils/load_save.py:283-300): a wrong or partial checkpoint must
+    raise, the detectron2 RPN / ROI-head keys a reference checkpoint carries must not."""
+    model = _model()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["cnn.feature.roi_heads.box_head.fc1.weight"] = torch.zeros(4, 4)
+    sd["cnn.feature.proposal_generator.rpn_head.conv.weight"] = torch.zeros(4, 4)
+    sd["cnn.feature.pixel_mean"] = torch.zeros(3, 1, 1)
+    sd["cnn.feature.backbone.stem.conv1.norm.num_batches_tracked"] = torch.zeros(())
+    res = model.load_state_dict(sd)                       # strict by default: accepted
+    assert not res.missing_keys
+    partial = dict(sd)
+    del partial["transformer.bert.pooler.dense.weight"]
+    with pytest.raises(RuntimeError, match="missing keys"):
+        model.load_state_dict(partial)
+    model.load_state_dict(partial, strict=False)          # the tolerant form stays available
+    wrong = dict(sd)
+    wrong["transformer.bert.encoder.layer.12.output.dense.weight"] = torch.zeros(2, 2)
+    with pytest.raises(RuntimeError, match="unexpected keys"):
+        model.load_state_dict(wrong)
+
+
+def test_grid_feat_backbone_loads_d2_pickles_and_names_a_missing_path(tmp_path):
+    """GridFeatBackbone.load_state_dict(path) (src/modeling/grid_feat.py:72-80): detectron2 .pkl checkpoints with numpy arrays
+    (the MSRA R-50.pkl layout) and .pth files load through the same key map; a path that does not exist is a clear error."""
+    import pickle
+
+    from clipbert_b200 import load_save as LS
+    src, dst = _model(), _model()
+    with torch.no_grad():
+        for p in src.cnn.parameters():
+            p.add_(0.25)
+    d2 = {k[len("feature."):]: v.detach().cpu().numpy() for k, v in src.cnn.state_dict().items() if k.startswith("feature.backbone.")}
+    d2["roi_heads.box_head.fc1.weight"] = torch.zeros(2, 2).numpy()
+    pkl = tmp_path / "R-50.pkl"
+    with open(pkl, "wb") as f:
+        pickle.dump({"model": d2, "__author__": "test"}, f)
+    res = dst.cnn.load_state_dict(str(pkl))
+    assert "roi_heads.box_head.fc1.weight" in res.unexpected_keys
+    for k, v in src.cnn.state_dict().items():
+        if k.startswith("feature.backbone."):
+            assert torch.equal(dst.cnn.state_dict()[k], v), k
+    assert all(not k.startswith("feature.backbone.") for k in res.missing_keys)       # only grid_encoder is absent from a d2 checkpoint
+    with pytest.raises(FileNotFoundError, match="does not exist"):
+        dst.cnn.load_state_dict(str(tmp_path / "nope.pth"))
+    with pytest.raises(ValueError, match="shape mismatch"):
+        dst.cnn.load_state_dict({"backbone.stem.conv1.weight": torch.zeros(1, 1, 1, 1)})
+    assert LS is not None

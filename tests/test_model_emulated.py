@@ -42,3 +42,11 @@ def test_fused_adamw_gpu_test_body_on_emulated_ops():
     reference groups, clip bookkeeping, state views, operand emission flags) with cb_sumsq / cb_adamw_step restated in torch."""
     with emulated_ops():
         GO.test_fused_adamw_matches_reference_optimizer(cuda=CPU)
+
+
+def test_fused_adamw_restore_round_trip_on_emulated_ops():
+    """The optimizer restore test (save after two steps, step, load_state_dict, replay the step) on CPU: the plan is rebuilt
+    from the restored state (the moments / step counts of a mid-training restore were silently ignored)."""
+    with emulated_ops():
+        GO.test_fused_adamw_state_dict_round_trip_after_steps(cuda=CPU)
+

@@ -154,11 +154,13 @@ def main():
             for bn in bns:
                 for kch in (0, 1, 2, 4):
                     cands.append((bn, 0, kch))
+        # two CTAs per SM (reserved bit 5): 128 x <=128 tiles only
+        cands = [c + (0,) for c in cands] + [c + (1,) for c in cands if c[0] <= 128 and c[2] in (0, 1)]
         best, best_t = None, base if base is not None else 1e9
-        for (bn, sp, kch) in cands:
-            t = time_cfg(ops, dict(call, block_n=bn, split_k=sp, reserved=kch << 8))
+        for (bn, sp, kch, occ2) in cands:
+            t = time_cfg(ops, dict(call, block_n=bn, split_k=sp, reserved=(kch << 8) | (32 if occ2 else 64)))
             if t is not None and t < best_t * 0.97:
-                best, best_t = (bn, sp, kch), t
+                best, best_t = (bn, sp, kch, occ2), t
         if best is not None:
             table[key] = list(best)
             saved += (base - best_t) * counts[key] if base is not None else 0.0
@@ -172,7 +174,7 @@ def main():
         except Exception:
             old = {}
     old.update(table)
-    json.dump(dict(device=torch.cuda.get_device_name(0), note="(block_n, split_k, kch) per GEMM shape; see tools/autotune_gemm.py",
+    json.dump(dict(device=torch.cuda.get_device_name(0), note="(block_n, split_k, kch, two CTAs per SM) per GEMM shape; see tools/autotune_gemm.py",
                    configs=old), open(args.out, "w"), indent=0, sort_keys=True)
     print("tuned %d / %d shapes; predicted saving %.2f ms per step; wrote %s (%.1f s)" % (len(table), len(uniq), saved / 1e3, args.out, time.time() - t0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

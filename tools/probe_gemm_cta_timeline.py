@@ -15,9 +15,8 @@ lib = L.lib()
 dev = "cuda"
 PHASES = [("setup", 0, 1), ("to_first_tma", 1, 2), ("tma_latency", 2, 4), ("tile0_mainloop", 4, 5), ("all_mma", 4, 6), ("tile0_epilogue", 7, 14),
           ("epi_tail_after_last_mma", 6, 8), ("store_drain", 8, 9), ("teardown", 9, 11), ("whole_cta", 0, 11),
-          # inside the first chunk of the first tile (one lane-quarter unit of the TMA epilogue)
-          ("c0:acc_ready->tmem_ld", 24, 16), ("c0:math", 16, 17), ("c0:sts", 17, 18), ("c0:fence", 18, 19), ("c0:store_wait_read", 19, 20),
-          ("c0:bar", 20, 21), ("chunk0", 24, 25), ("chunk1", 25, 26), ("chunk2", 26, 27)]
+          # inside the first tile of the first epilogue warp (warp-private TMA epilogue)
+          ("e:inputs+tmem_ld", 7, 16), ("e:pass0_math", 16, 17), ("e:passes1-3", 17, 18), ("e:store_issue", 18, 14)]
 
 
 def med(v):
