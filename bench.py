@@ -11,6 +11,11 @@ on one synthetic batch per GPU: for each of n_clips clips ClipBert.forward (Grid
 and (N > 1) the data-parallel gradient all-reduce. Dropout is ON (train mode, p = 0.1) as in the
 reference. 1 clip = one (video, clip) unit = T frames through the CNN + n_ex sequences through BERT.
 
+--config selects the workload (BASELINE.json `configs`; the default, "headline", is the configuration the metric string
+names: 32 videos x 2 clips x 2 frames). c2: 1 clip x 2 frames; c3: 4 clips x 2 frames; c4: TGIF-QA multiple choice, 64 videos x
+2 clips x 1 frame x 5 options; c5: paragraph-retrieval INFERENCE, one video of 16 clips x 1 frame against 8 captions of 512
+tokens per step (CNN once per video, one BERT pass over 128 sequences of L = 521).
+
 JSON keys beyond the base contract:
   value     clips/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
   e2e       same metric through the public API (ClipBert.forward on a batch dict) with HOST (pinned)
@@ -164,13 +169,47 @@ def hbm_bound_launch(ops, rec, stream, peaks, reps=20):
 # ------------------------------------------------------------------------------------------------
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
+CONFIGS = {          # BASELINE.json `configs` -> workload parameters (explicit flags override)
+    "headline": dict(batch=32, n_clips=2, n_frm=2, txt_len=32, n_ex=1, head="retrieval", inference=False),
+    "c2": dict(batch=32, n_clips=1, n_frm=2, txt_len=32, n_ex=1, head="retrieval", inference=False),
+    "c3": dict(batch=32, n_clips=4, n_frm=2, txt_len=32, n_ex=1, head="retrieval", inference=False),
+    "c4": dict(batch=64, n_clips=2, n_frm=1, txt_len=32, n_ex=5, head="multiple_choice", inference=False),
+    "c5": dict(batch=1, n_clips=16, n_frm=1, txt_len=512, n_ex=8, head="retrieval", inference=True),
+}
+METRIC_TRAIN = "clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)"
+
+
+def apply_config(args):
+    for k, v in CONFIGS[args.config].items():
+        if getattr(args, k, None) is None:
+            setattr(args, k, v)
+    args.num_classes = 5 if args.head == "multiple_choice" else 2
+    return args
+
+
+def workload_name(args):
+    if args.inference:
+        return ("paragraph retrieval inference: %d video(s)/GPU x %d clips x %d frame(s) %dx%d against %d captions of %d tokens (CNN once per "
+                "video, one BERT pass over %d sequences)" % (args.batch, args.n_clips, args.n_frm, args.size, args.size, args.n_ex, args.txt_len,
+                                                              args.batch * args.n_clips * args.n_ex))
+    if args.head == "multiple_choice":
+        return ("TGIF-QA multiple-choice train step: %d videos/GPU x %d clips x %d frame(s) %dx%d, %d options x %d-token text, LSE clip "
+                "aggregation + CE over the options, dropout 0.1, grad allreduce when N>1" % (args.batch, args.n_clips, args.n_frm, args.size, args.size,
+                                                                                             args.n_ex, args.txt_len))
+    return ("MSRVTT retrieval train step: %d videos/GPU x %d clips x %d frames %dx%d, %d-token text, n_ex=%d, LSE clip aggregation + CE, "
+            "dropout 0.1, grad allreduce when N>1" % (args.batch, args.n_clips, args.n_frm, args.size, args.size, args.txt_len, args.n_ex))
+
+
 def make_host_batch(args, rank):
-    from oracle import synth   # shapes / value ranges of the synthetic inputs only
+    from clipbert_b200 import workload as synth   # shapes / value ranges of the synthetic inputs only
     B, frames = args.batch, args.n_clips * args.n_frm
     u8 = synth.synth_images(B, frames, size=args.size, seed=42 + rank, as_uint8=True)
     ids, mask = synth.synth_text(B * args.n_ex, args.txt_len, seed=42 + rank)
     g = torch.Generator().manual_seed(1000 + rank)
-    labels = torch.randint(0, 2, (B * args.n_ex,), generator=g)
+    if getattr(args, "head", "retrieval") == "multiple_choice":
+        labels = torch.randint(0, args.n_ex, (B,), generator=g)          # index of the right option of each video
+    else:
+        labels = torch.randint(0, 2, (B * args.n_ex,), generator=g)
     pin = _pin if torch.cuda.is_available() else (lambda t: t)
     return dict(visual_inputs=pin(u8), text_input_ids=pin(ids), text_input_mask=pin(mask), labels=pin(labels))
 
@@ -207,15 +246,20 @@ def run_b200(args):
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
     import clipbert_b200 as cb
-    from clipbert_b200 import ops
-    from util import make_cfg
+    from clipbert_b200 import ops, workload as synth
+    from clipbert_b200.workload import make_cfg
 
     torch.manual_seed(42)
-    cfg = make_cfg()                      # base_model.json + retrieval head (num_labels 2, CE)
-    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", transformer_cls=cb.ClipBertForVideoTextRetrieval)
-    from oracle import synth
+    if args.head == "multiple_choice":    # ClipBertForMultipleChoice: one logit per (video, option) row, CE over the options
+        cfg = make_cfg(num_labels=args.n_ex)
+        tcls = cb.ClipBertForMultipleChoice
+    else:                                 # base_model.json + retrieval head (num_labels 2, CE)
+        cfg = make_cfg()
+        tcls = cb.ClipBertForVideoTextRetrieval
+    model = cb.ClipBert(cfg, detectron2_model_cfg="R-50-grid.yaml", transformer_cls=tcls)
     model.load_state_dict(synth.cnn_state_dict(42), strict=False)     # randomised FrozenBN statistics (random-init weights)
-    model = model.to(dev).train()
+    model = model.to(dev)
+    model = model.eval() if args.inference else model.train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
     if world > 1:
@@ -239,16 +283,26 @@ def run_b200(args):
             dbuf[k].copy_(host[k], non_blocking=True)
 
     def fwd_bwd():
+        if args.inference:         # inference_retrieval (run_video_retrieval.py:629-734): CNN once per video, then the captions
+            with torch.no_grad():
+                grid = model.encode_clips(dbuf["visual_inputs"], n_clips)
+                mb = dict(text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"], n_examples_list=[n_ex] * B)
+                logits = model.forward_clips(mb, n_clips, grid=grid)["logits"]
+                loss_dev.copy_(logits.float().mean().reshape(1))          # the per-step result read back by the e2e leg
+            return
         if args.clip_batching:     # the n_clips passes of the reference loop as ONE pass over B*n_clips units
             mb = dict(visual_inputs=dbuf["visual_inputs"], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
-                      labels=dbuf["labels"], n_examples_list=[n_ex] * B)
+                      n_examples_list=[n_ex] * B)
+            if args.head == "retrieval":
+                mb["labels"] = dbuf["labels"]     # (the QA loop hands the model labels=None and computes the loss on the stacked clip logits,
+                                                  # run_video_qa.py:465-501)
             logits = model.forward_clips(mb, n_clips)["logits"]
         else:                      # the reference loop as written (run_video_retrieval.py:396-401)
             vis = dbuf["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
             logits = []
             for c in range(n_clips):
                 mb = dict(visual_inputs=vis[:, c], text_input_ids=dbuf["text_input_ids"], text_input_mask=dbuf["text_input_mask"],
-                          labels=dbuf["labels"], n_examples_list=[n_ex] * B)
+                          labels=dbuf["labels"] if args.head == "retrieval" else None, n_examples_list=[n_ex] * B)
                 logits.append(model(mb)["logits"])
         loss = cb.clip_lse_loss(logits, dbuf["labels"]) if args.fused_loss else lse_loss(logits, dbuf["labels"])
         loss.backward()
@@ -309,7 +363,7 @@ def run_b200(args):
     # tensor-core operands are re-emitted by the optimizer kernel after each update (the role of apex amp O2's master ->
     # model copy inside optimizer.step, :307-309), so forward + backward - the metric - does not re-cast the weights.
     # Without an optimizer attached the modules conservatively re-cast after every backward (2 extra launches per step).
-    if args.optimizer and not args.recast_in_step:
+    if args.optimizer and not args.recast_in_step and not args.inference:
         try:
             model.zero_grad()
             fwd_bwd()                      # both halves now own their flat buffers (the sequence tests/test_gpu_optim.py covers)
@@ -395,7 +449,7 @@ def run_b200(args):
 
     clips_per_step = B * n_clips * world
     L = args.txt_len + (args.size // 32 // 2) ** 2
-    fl_clip = flops_per_clip(T, L, n_ex, 2, args.size)
+    fl_clip = flops_per_clip(T, L, n_ex, 1 if args.head == "multiple_choice" else 2, args.size, backward=not args.inference)
     peaks = load_peaks()
     value = clips_per_step / (ms_dev / args.steps / 1e3)
     e2e_value = clips_per_step / (ms_e2e / args.steps / 1e3)
@@ -485,13 +539,13 @@ def run_b200(args):
             sys.stderr.flush()
             os._exit(0)
     try:          # rank 0 at N = 1 only (the contract's cpu_baseline leg); never at the cost of the bench line
-        cpu = None if (args.no_cpu or rank != 0 or world > 1) else cpu_baseline(args)
+        cpu = None if (args.no_cpu or rank != 0 or world > 1 or args.config not in ("headline", "c2", "c3")) else cpu_baseline(args)
     except Exception as e:
         print("[bench] cpu_baseline failed (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
         cpu = None
     # ---- informational: the fused optimizer step that follows fwd+bwd in training (not part of the metric) ----
     opt_info = None
-    if args.optimizer and world == 1:
+    if args.optimizer and world == 1 and not args.inference:
       try:
         named = [(n_, p_) for n_, p_ in model.named_parameters() if p_.requires_grad]
         if opt is None:
@@ -516,11 +570,12 @@ def run_b200(args):
         opt_info = None
 
     if rank == 0:
-        out = dict(metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=round(value, 2), unit="clips/s", n_gpus=world,
+        metric = METRIC_TRAIN if args.config in ("headline", "c2", "c3") else (
+            "clips/sec inference paragraph retrieval (ResNet50+BERT-base)" if args.inference else "clips/sec fwd+bwd TGIF-QA multiple choice (ResNet50+BERT-base)")
+        out = dict(metric=metric, value=round(value, 2), unit="clips/s", n_gpus=world,
                    steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 4), higher_is_better=True,
                    scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                   config=dict(workload="MSRVTT retrieval train step: %d videos/GPU x %d clips x %d frames %dx%d, %d-token text, n_ex=%d, "
-                               "LSE clip aggregation + CE, dropout 0.1, grad allreduce when N>1" % (B, n_clips, T, args.size, args.size, args.txt_len, n_ex),
+                   config=dict(workload=workload_name(args), name=args.config,
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
@@ -598,6 +653,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if args.head != "retrieval" or args.inference:
+        print(json.dumps(dict(impl="reference", unavailable="the CPU arm times the retrieval train step (configs headline / c2 / c3) only")))
+        return
     b = args.cpu_batch
     sd, batch = _cpu_setup(args, b)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -609,7 +667,7 @@ def run_reference(args):
     dt = (time.time() - t0) / steps
     val = round(b * args.n_clips / dt, 3)
     L = args.txt_len + (args.size // 32 // 2) ** 2
-    out = dict(impl="reference", metric="clips/sec fwd+bwd MSRVTT ret (ResNet50+BERT-base)", value=val, unit="clips/s", n_gpus=args.gpus,
+    out = dict(impl="reference", metric=METRIC_TRAIN, value=val, unit="clips/s", n_gpus=args.gpus,
                steps=steps, warmup=1, ms_per_step=round(dt * 1e3, 2), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                data="synthetic",
                config=dict(workload="MSRVTT retrieval train step (bounded CPU sample): %d videos x %d clips x %d frames %dx%d, %d-token text, n_ex=%d"
@@ -628,12 +686,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="videos per GPU")
-    ap.add_argument("--n_clips", type=int, default=2)
-    ap.add_argument("--n_frm", type=int, default=2)
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the configuration the metric names)")
+    ap.add_argument("--batch", type=int, default=None, help="videos per GPU (default: the config's)")
+    ap.add_argument("--n_clips", type=int, default=None)
+    ap.add_argument("--n_frm", type=int, default=None)
     ap.add_argument("--size", type=int, default=224)
-    ap.add_argument("--txt_len", type=int, default=32)
-    ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--txt_len", type=int, default=None)
+    ap.add_argument("--n_ex", type=int, default=None, help="text rows per video (captions / answer options)")
+    ap.add_argument("--head", default=None, choices=["retrieval", "multiple_choice"])
+    ap.add_argument("--inference", type=int, default=None, help="1: forward only (config c5)")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
@@ -654,7 +715,7 @@ def main():
     ap.add_argument("--optimizer", type=int, default=1, help="also time the fused AdamW step (informational key fused_optimizer)")
     ap.add_argument("--opt_steps", type=int, default=10, help="timed iterations of the informational fused-optimizer leg")
     ap.add_argument("--no_cpu", type=int, default=0, help="skip the CPU baseline leg (profiling runs)")
-    args = ap.parse_args()
+    args = apply_config(ap.parse_args())
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -145,6 +145,7 @@ class GridFeatBackbone(nn.Module):
         self._bn = None
         self._dirty = True
         self._capture = None     # tests set this to a dict to receive per-stage activations
+        self._inject = None      # tests: {"res5.2": NHWC activation} makes that block start from the given tensor
         self._pending_backward = 0
         self._bucket_hook = None   # data-parallel: called as hook(flat_grad, first_finished_element, side_stream) mid-backward
         self._segments = None
@@ -405,6 +406,9 @@ class GridFeatBackbone(nn.Module):
             stage = getattr(bb, name)
             for bi, blk in enumerate(stage):
                 last = (si == len(stage_names) - 1) and (bi == len(stage) - 1)
+                if self._inject is not None and ("%s.%d" % (name, bi)) in self._inject:
+                    # test hook: this block starts from a given NHWC activation (layer-local parity: both implementations see the same input)
+                    cur = self._inject["%s.%d" % (name, bi)].to(device=dev, dtype=bf16).reshape(n * hh * ww, -1).contiguous()
                 x_in, h_in, w_in = cur, hh, ww
                 if blk.stride == 2:
                     hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1

@@ -190,6 +190,7 @@ class _ClipBertHeadModel(nn.Module):
         self._seed_base = None
         self._drop_counter = None   # uint64 device word: the dropout stream position, advanced ON THE DEVICE once per training forward
         self._capture = None     # tests set this to a dict to receive per-layer activations
+        self._inject = None      # tests: {layer index: (B', L, 768) hidden state} makes that encoder layer start from the given tensor
         self._pending_backward = 0
         self._grad_ready_hook = None
         self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
@@ -422,6 +423,8 @@ class _ClipBertHeadModel(nn.Module):
         # ---- encoder ----
         for i in range(len(self.bert.encoder.layer)):
             ls = seed + 16 * (i + 1)
+            if self._inject is not None and i in self._inject:      # test hook: layer-local parity (same input on both sides)
+                x = self._inject[i].to(device=dev, dtype=bf16).reshape(M, H).contiguous()
             qkv_l, ao_l, in_l, out_l = (self._lin["l%d.%s" % (i, k)] for k in ("qkv", "ao", "inter", "out"))
             g1, b1, _, _ = self._ln("l%d.ln1" % i)
             g2, b2, _, _ = self._ln("l%d.ln2" % i)

@@ -99,6 +99,39 @@ def test_bench_control_flow_on_cpu(monkeypatch, capsys, flags):
         assert hb is None or "error" not in hb, hb
 
 
+@pytest.mark.parametrize("config", ["c4", "c5"])
+def test_bench_other_baseline_configs_on_cpu(monkeypatch, capsys, config):
+    """bench.py --config c4 (TGIF-QA multiple choice train step) and c5 (paragraph-retrieval inference: CNN once per video, one
+    BERT pass over clips x captions) in miniature through the emulated ABI: the workload plumbing and the JSON line."""
+    import bench
+    from ops_emulator import emulated_ops
+    cpu = torch.device("cpu")
+    for name, val in (("Stream", _Stream), ("Event", _Event), ("CUDAGraph", _Graph), ("graph", _ctx), ("stream", _ctx),
+                      ("current_stream", lambda *a: _Stream()), ("synchronize", lambda *a: None), ("set_device", lambda *a: None),
+                      ("is_available", lambda: False)):
+        monkeypatch.setattr(torch.cuda, name, val)
+    monkeypatch.setattr(bench, "_device", lambda r: cpu)
+    monkeypatch.setattr(bench, "_pin", lambda t: t)
+    small = {"c4": ["--batch", "2", "--n_ex", "3", "--txt_len", "12"], "c5": ["--n_clips", "3", "--n_ex", "2", "--txt_len", "70"]}[config]
+    argv = ["bench.py", "--config", config, "--gpus", "1", "--steps", "2", "--warmup", "1", "--size", "64", "--no_cpu", "1", "--overlap_wgrad", "0",
+            "--opt_steps", "1", "--graph", "0", "--prefetch", "0"] + small
+    monkeypatch.setattr(sys, "argv", argv)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    with emulated_ops(ignore_dropout=True) as calls:
+        bench.main()
+    out, err = capsys.readouterr()
+    d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert d["config"]["name"] == config and d["unit"] == "clips/s" and d["value"] > 0
+    assert "roofline pass failed" not in err and "error" not in d["roofline"], (err, d["roofline"])
+    if config == "c4":
+        assert "multiple choice" in d["metric"] and d["config"]["clips_per_step_per_gpu"] == 4 and d["fused_optimizer"] is not None
+        assert calls["clip_lse_loss"] > 0
+    else:
+        assert "inference" in d["metric"] and d["config"]["clips_per_step_per_gpu"] == 3 and d["config"]["seq_len"] == 71
+        assert d["fused_optimizer"] is None and calls["attention_bwd"] == 0 and calls["attention_fwd"] > 0
+
+
 def calls_per_step_expected(flags):
     # GEMM launches of one training step: CNN 53 convs forward + backward of res3-5 / grid_encoder, transformer 12 layers + heads;
     # the per-clip loop runs the whole thing once per clip

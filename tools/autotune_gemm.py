@@ -19,15 +19,22 @@ import bench  # noqa: E402
 
 
 def record_step(args):
+    """cb_gemm descriptors of ONE step of the bench workload ``args`` describes (bench.CONFIGS: train steps and config 5's inference)."""
     import clipbert_b200 as cb
-    from clipbert_b200 import ops
-    from oracle import synth
-    from util import make_cfg
+    from clipbert_b200 import ops, workload as synth
+    from clipbert_b200.workload import make_cfg
+    if not hasattr(args, "head") or args.head is None:
+        args.config = getattr(args, "config", "headline")
+        bench.apply_config(args)
     dev = torch.device("cuda:0")
     torch.manual_seed(42)
-    model = cb.ClipBert(make_cfg(), detectron2_model_cfg="x")
+    if args.head == "multiple_choice":
+        model = cb.ClipBert(make_cfg(num_labels=args.n_ex), detectron2_model_cfg="x", transformer_cls=cb.ClipBertForMultipleChoice)
+    else:
+        model = cb.ClipBert(make_cfg(), detectron2_model_cfg="x")
     model.load_state_dict(synth.cnn_state_dict(42), strict=False)
-    model = model.to(dev).train()
+    model = model.to(dev)
+    model = model.eval() if args.inference else model.train()
     model.cnn.pixel_mean = bench.IMAGE_MEAN
     host = bench.make_host_batch(args, 0)
     d = {k: v.to(dev) for k, v in host.items()}
@@ -35,18 +42,24 @@ def record_step(args):
     os.environ["CB_NO_TUNING"] = "1"
     ops._tuning = {}
     ops._gemm_record = []
-    if getattr(args, "clip_batching", 1):
-        mb = dict(visual_inputs=d["visual_inputs"], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
-                  labels=d["labels"], n_examples_list=[n_ex] * B)
-        logits = model.forward_clips(mb, n_clips)["logits"]
+    if args.inference:
+        with torch.no_grad():
+            grid = model.encode_clips(d["visual_inputs"], n_clips)
+            model.forward_clips(dict(text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"], n_examples_list=[n_ex] * B), n_clips, grid=grid)
     else:
-        vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
-        logits = []
-        for c in range(n_clips):
-            mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"], labels=d["labels"],
-                      n_examples_list=[n_ex] * B)
-            logits.append(model(mb)["logits"])
-    bench.lse_loss(logits, d["labels"]).backward()
+        if getattr(args, "clip_batching", 1):
+            mb = dict(visual_inputs=d["visual_inputs"], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"], n_examples_list=[n_ex] * B)
+            if args.head == "retrieval":
+                mb["labels"] = d["labels"]
+            logits = model.forward_clips(mb, n_clips)["logits"]
+        else:
+            vis = d["visual_inputs"].view(B, n_clips, T, 3, args.size, args.size)
+            logits = []
+            for c in range(n_clips):
+                mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
+                          labels=d["labels"] if args.head == "retrieval" else None, n_examples_list=[n_ex] * B)
+                logits.append(model(mb)["logits"])
+        bench.lse_loss(logits, d["labels"]).backward()
     torch.cuda.synchronize()
     rec, ops._gemm_record = ops._gemm_record, None
     return rec
@@ -114,16 +127,19 @@ def time_cfg(ops, call, reps=10):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--n_clips", type=int, default=2)
-    ap.add_argument("--n_frm", type=int, default=2)
+    ap.add_argument("--config", default="headline", choices=sorted(bench.CONFIGS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--n_clips", type=int, default=None)
+    ap.add_argument("--n_frm", type=int, default=None)
     ap.add_argument("--size", type=int, default=224)
-    ap.add_argument("--txt_len", type=int, default=32)
-    ap.add_argument("--n_ex", type=int, default=1)
+    ap.add_argument("--txt_len", type=int, default=None)
+    ap.add_argument("--n_ex", type=int, default=None)
+    ap.add_argument("--head", default=None)
+    ap.add_argument("--inference", type=int, default=None)
     ap.add_argument("--clip_batching", type=int, default=1)
     ap.add_argument("--out", default=os.path.join(ROOT, "clipbert_b200", "gemm_tuning.json"))
     ap.add_argument("--merge", type=int, default=1)
-    args = ap.parse_args()
+    args = bench.apply_config(ap.parse_args())
     from clipbert_b200 import ops
     dev = torch.device("cuda:0")
     t0 = time.time()
@@ -178,7 +194,7 @@ def main():
                    configs=old), open(args.out, "w"), indent=0, sort_keys=True)
     print("tuned %d / %d shapes; predicted saving %.2f ms per step; wrote %s (%.1f s)" % (len(table), len(uniq), saved / 1e3, args.out, time.time() - t0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    open(os.path.join(ROOT, "gpurun_out", "autotune_report.txt"), "w").write("\n".join(report) + "\n")
+    open(os.path.join(ROOT, "gpurun_out", "autotune_report_%s.txt" % args.config), "w").write("\n".join(report) + "\n")
 
 
 if __name__ == "__main__":

@@ -32,8 +32,8 @@ def main():
     args = ap.parse_args()
     import clipbert_b200 as cb
     from clipbert_b200 import ops
-    from oracle import synth
-    from util import make_cfg
+    from clipbert_b200 import workload as synth
+    from clipbert_b200.workload import make_cfg
     dev = torch.device("cuda", 0)
     model = cb.ClipBert(make_cfg(), detectron2_model_cfg="R-50-grid.yaml", transformer_cls=cb.ClipBertForVideoTextRetrieval)
     model.load_state_dict(synth.cnn_state_dict(42), strict=False)

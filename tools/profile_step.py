@@ -28,8 +28,8 @@ def main():
     args = ap.parse_args()
     import clipbert_b200 as cb
     from clipbert_b200 import ops
-    from oracle import synth
-    from util import make_cfg
+    from clipbert_b200 import workload as synth
+    from clipbert_b200.workload import make_cfg
     dev = torch.device("cuda:0")
     torch.manual_seed(42)
     model = cb.ClipBert(make_cfg(), detectron2_model_cfg="x")
