@@ -584,6 +584,22 @@ __global__ void cast_scale_kernel(const float* __restrict__ in, const float* __r
   }
 }
 
+// bf16 -> fp32 (gradients back from the bf16 wire format of the data-parallel exchange)
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
+  pdl_trigger();
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  if (i + 8 <= n) {
+    const uint4 u = *reinterpret_cast<const uint4*>(in + i);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    *reinterpret_cast<float4*>(out + i) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(c.x, c.y, d.x, d.y);
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = __bfloat162float(in[k]);
+  }
+}
+
 // all conv weights of the backbone in ONE launch: segment g (blockIdx.y) = one conv's KRSC block, scaled per output row
 __global__ void cast_scale_segments_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
                                            const int64_t* __restrict__ seg /*[nseg][4]: offset, numel, row_len, scale_off (-1: none)*/,
@@ -745,6 +761,13 @@ int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void*
   launch_k(cast_scale_kernel, ceil_div(ceil_div(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       in, rowscale, row_len, static_cast<__nv_bfloat16*>(out), n);
   return check_launch("cb_cast_scale");
+}
+
+int cb_cast_bf16_f32(const void* in, float* out, int64_t n, void* stream) {
+  CB_REQUIRE(in && out && n > 0, "cb_cast_bf16_f32: bad arguments");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "cb_cast_bf16_f32: misaligned");
+  launch_k(cast_bf16_f32_kernel, ceil_div(ceil_div(n, 8), 256), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(in), out, n);
+  return check_launch("cb_cast_bf16_f32");
 }
 
 }  // extern "C"

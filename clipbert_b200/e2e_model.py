@@ -36,6 +36,17 @@ def allreduce_flat(grads, group=None, average=True, async_op=False):
     return works
 
 
+class _Bf16WireWork:
+    """One slice of a gradient buffer on its way through the bf16 wire format: ``wait()`` makes the caller's stream wait for the
+    all-reduce and for the cast of the averaged values back into the fp32 buffer (both enqueued on the exchange's side stream)."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class _StreamWork:
     """``Work.wait()`` for an exchange enqueued on a side stream: the caller's stream waits for its end."""
 
@@ -242,6 +253,45 @@ class ClipBert(nn.Module):
             ev.record(comm)
         return [_StreamWork(ev)]
 
+    def _bf16_wire_exchange(self, tensors):
+        """The all-reduce in the reference's wire precision: amp O2 keeps fp16 gradients and Horovod all-reduces them as they
+        are (src/tasks/run_video_retrieval.py:299-309,432) - 2 bytes per parameter, the 297 MB of SURVEY.md §8d - whereas the flat
+        buffers here accumulate in fp32. Each slice is cast into a persistent bf16 shadow of its buffer (cb_cast_scale), averaged
+        over the ranks in bf16, and cast back (cb_cast_bf16_f32), all on one side stream so that neither cast nor collective
+        sits on the backward's critical path. Halves the NVLink payload and the time NCCL's CTAs share the SMs with the backward."""
+        from . import ops
+        dp = self._dp
+        group = dp["group"]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        ws = dist.get_world_size(group)
+        nccl = dist.get_backend(group) == "nccl"
+        comm = dp.get("wire_stream")
+        if comm is None:
+            comm = dp["wire_stream"] = torch.cuda.Stream()
+        comm.wait_stream(torch.cuda.current_stream())          # the gradients of these slices are complete in stream order
+        with torch.cuda.stream(comm):
+            for t in tensors:
+                key = t.untyped_storage().data_ptr()
+                shadow = dp["shadows"].get(key)
+                if shadow is None:
+                    owner = next(m._flat.grad for m in (self.transformer, self.cnn)
+                                 if m._flat is not None and m._flat.grad is not None and m._flat.grad.untyped_storage().data_ptr() == key)
+                    shadow = dp["shadows"][key] = torch.empty(owner.numel(), dtype=torch.bfloat16, device=owner.device)
+                lo = t.storage_offset()
+                s = shadow[lo: lo + t.numel()]
+                ops.cast_scale(t, s)
+                if dp["average"] and nccl:
+                    dist.all_reduce(s, op=dist.ReduceOp.AVG, group=group)          # (sync op: enqueued on `comm`, the host does not wait)
+                else:
+                    if dp["average"]:
+                        s.mul_(1.0 / ws)
+                    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+                ops.cast_bf16_f32(s, t)
+            ev = torch.cuda.Event()
+            ev.record(comm)
+        return [_Bf16WireWork(ev)]
+
     def _exchange(self, tensors):
         dp = self._dp
         if not tensors:
@@ -250,9 +300,11 @@ class ClipBert(nn.Module):
             if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(dp["group"]) == 1:
                 return []
             return self._nvls_exchange(tensors)
+        if dp.get("wire") == "bf16":
+            return self._bf16_wire_exchange(tensors)
         return allreduce_flat(tensors, dp["group"], dp["average"], async_op=True)
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64):
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64, wire="fp32"):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
@@ -260,10 +312,11 @@ class ClipBert(nn.Module):
 
         ``cnn_buckets``: also exchange the tail of the CNN buffer (res5 + grid_encoder, 78 % of it) as soon as the
         res5 backward has enqueued its last weight gradient, leaving only res3/res4 (33 MB) for the final exchange.
-        The collective is issued from the wgrad side stream, which is the stream those gradients are written on."""
-        assert exchange in ("nccl", "nvls")
+        The collective is issued from the wgrad side stream, which is the stream those gradients are written on.
+        ``wire="bf16"``: exchange the gradients as bf16 (see ``_bf16_wire_exchange``)."""
+        assert exchange in ("nccl", "nvls") and wire in ("fp32", "bf16")
         self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True, exchange=exchange,
-                        max_ctas=int(max_ctas), handles={})
+                        max_ctas=int(max_ctas), handles={}, wire=wire, shadows={})
         if exchange == "nvls":
             # ``exchange="nvls"``: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) instead of NCCL. The flat
             # gradient buffers must then live in symmetric memory, so call this BEFORE the first forward (buffers that already

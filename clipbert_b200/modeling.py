@@ -369,6 +369,15 @@ class _ClipBertHeadModel(nn.Module):
                  shift=li.b, out=out, out_ld=li.n, **kw)
 
     def _forward_impl(self, ids, grid, mask, repeat, need_backward):
+        """Binds the per-call dropout word for the duration of the pass and unbinds it on the way out: the binding is process-wide
+        state of the library, and a word that outlives its tensor would be a dangling device pointer for every later launch that
+        draws masks (found by the autotuner: cb_gemm launches with dropout after the recording step's tensors had been freed)."""
+        try:
+            return self._forward_body(ids, grid, mask, repeat, need_backward)
+        finally:
+            ops.dropout_offset_bind(None)
+
+    def _forward_body(self, ids, grid, mask, repeat, need_backward):
         dev = ids.device
         cfg = self.config
         H = _cfg(cfg, "hidden_size")
@@ -519,6 +528,12 @@ class _ClipBertHeadModel(nn.Module):
         return self._mlp_head_backward(st, dout, nseq, H)
 
     def _backward_impl(self, st, dout, grid_needs_grad):
+        try:
+            return self._backward_body(st, dout, grid_needs_grad)
+        finally:
+            ops.dropout_offset_bind(None)
+
+    def _backward_body(self, st, dout, grid_needs_grad):
         self._flat.attach_grads()
         dev = st["x_last"].device
         cfg = self.config

@@ -28,6 +28,7 @@ _SIGS = {
     "cb_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "cb_pad_cast": [_vp, _i64, _vp, _i, _i, _i, _vp],
     "cb_cast_scale": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "cb_cast_bf16_f32": [_vp, _vp, _i64, _vp],
     "cb_cast_scale_segments": [_vp, _vp, _vp, _i, _vp, _vp],
     "cb_nvls_allreduce_f32": [_vp, _i64, _i, _i, _f, _i, _vp],
     "cb_clip_lse_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
@@ -329,6 +330,10 @@ def pad_cast(src, dst):
 
 def cast_scale(src, dst, rowscale=None, row_len=1):
     _call("cb_cast_scale", _p(src), _p(rowscale), row_len, _p(dst), src.numel(), _s())
+
+
+def cast_bf16_f32(src, dst):
+    _call("cb_cast_bf16_f32", _p(src), _p(dst), src.numel(), _s())
 
 
 def cast_scale_segments(master, packed, segments, scales):

@@ -217,6 +217,9 @@ int cb_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, void* 
 int cb_gelu_bwd(const void* dy, const void* u, void* dx, int64_t n, void* stream);
 int cb_pad_cast(const float* in, int64_t in_ld, void* out, int rows, int c, int cpad, void* stream);
 int cb_cast_scale(const float* in, const float* rowscale, int64_t row_len, void* out, int64_t n, void* stream);
+/* bf16 -> fp32: the averaged gradients come back from the bf16 wire format of the data-parallel exchange (the reference
+ * all-reduces its gradients in fp16 under amp O2, src/tasks/run_video_retrieval.py:299-309,432); n elements, 16-byte aligned */
+int cb_cast_bf16_f32(const void* in, float* out, int64_t n, void* stream);
 /* the same for every conv of the backbone in one launch: segments is a device int64 [nseg][4] table
  * (element offset, element count, row length, offset into `scales` or -1); offsets are 64-element aligned */
 int cb_cast_scale_segments(const float* master, void* packed, const int64_t* segments, int nseg, const float* scales, void* stream);

@@ -400,6 +400,10 @@ def opt_adamw_step(master, grad, exp_avg, exp_avg_sq, packed, chunks, nchunks, h
             packed[sl] = p.to(packed.dtype)
 
 
+def cast_bf16_f32(src, dst):
+    dst.copy_(src.float())
+
+
 def dropout_offset_bind(word):
     """cb_dropout_offset_bind: process-wide device word folded into the dropout seeds (the emulator draws no masks)."""
     global BOUND_DROPOUT_WORD
@@ -418,7 +422,7 @@ BOUND_DROPOUT_WORD = None
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
-          "cast_scale_segments", "clip_lse_loss", "nvls_allreduce", "dropout_offset_bind", "dropout_offset_advance")
+          "cast_scale_segments", "clip_lse_loss", "nvls_allreduce", "dropout_offset_bind", "dropout_offset_advance", "cast_bf16_f32")
 
 
 @contextlib.contextmanager

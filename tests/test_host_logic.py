@@ -377,3 +377,75 @@ def test_nvls_exchange_plumbing_world_size_2():
         for step, (t0, t1, c) in enumerate(out):
             assert t0 == pytest.approx(1.5 * (step + 1)) and t1 == pytest.approx(1.5 * (step + 1))
             assert c == pytest.approx([1.5 * i for i in range(640)])
+
+
+def _bf16_wire_worker(rank, world, port, q):
+    """The bf16 wire format of ClipBert's exchange (persistent bf16 shadow per buffer, slice offsets, cast -> all-reduce ->
+    cast back on a side stream, joined by allreduce_grads) over gloo: cb_cast_scale / cb_cast_bf16_f32 restated in torch,
+    streams / events inert."""
+    import contextlib as cl
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import ops_emulator
+    from clipbert_b200 import ops
+    from clipbert_b200.e2e_model import ClipBert
+
+    class _S:
+        def wait_stream(self, s):
+            pass
+
+        def wait_event(self, e):
+            pass
+
+    class _E:
+        def record(self, s=None):
+            pass
+
+    for name, val in (("Stream", _S), ("Event", _E), ("current_stream", lambda *a: _S()), ("stream", lambda s: cl.nullcontext())):
+        setattr(torch.cuda, name, val)
+    ops.cast_scale, ops.cast_bf16_f32 = ops_emulator.cast_scale, ops_emulator.cast_bf16_f32
+    m = ClipBert.__new__(ClipBert)
+    tf = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.zeros(1000)), _grad_ready_hook=None, _pending_backward=0)
+    cnn = types.SimpleNamespace(_flat=types.SimpleNamespace(grad=torch.zeros(640)), _bucket_hook=None, _pending_backward=0)
+    object.__setattr__(m, "transformer", tf)
+    object.__setattr__(m, "cnn", cnn)
+    ClipBert.enable_overlapped_allreduce(m, cnn_buckets=True, wire="bf16")
+    out = []
+    for step in range(2):
+        tf._flat.grad.copy_(torch.linspace(0.1, 3.0, 1000) * (rank + 1) * (step + 1))
+        tf._grad_ready_hook(tf._flat.grad)
+        cnn._flat.grad.zero_()
+        cnn._flat.grad[256:] = torch.arange(256.0, 640.0) * (rank + 1) / 64
+        cnn._bucket_hook(cnn._flat.grad, 256, None)
+        cnn._flat.grad[:256] = torch.arange(256.0) * (rank + 1) / 64
+        ClipBert.allreduce_grads(m)
+        assert m._dp["works"] == [] and m._dp["cnn_lo"] is None
+        out.append((tf._flat.grad.clone(), cnn._flat.grad.clone()))
+    assert len(m._dp["shadows"]) == 2 and all(v.dtype == torch.bfloat16 for v in m._dp["shadows"].values())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_bf16_wire_exchange_plumbing_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 377) % 1000
+    procs = [ctx.Process(target=_bf16_wire_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        for step, (t, c) in enumerate(out):
+            # mean over ranks (1, 2) of values rounded to bf16 before the sum, the sum rounded once more: within 2^-8 of the fp32 mean
+            want_t = torch.linspace(0.1, 3.0, 1000) * 1.5 * (step + 1)
+            want_c = torch.arange(640.0) * 1.5 / 64
+            assert float(((t - want_t).abs() / want_t).max()) < 2 ** -7
+            assert float((c - want_c).abs().max()) <= float(want_c.max()) * 2 ** -7
+            assert float((t - want_t).abs().max()) > 0.0                  # it really went through bf16

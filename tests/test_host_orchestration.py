@@ -365,3 +365,43 @@ def test_inference_retrieval_grid_reuse_on_emulated_ops(weights):
     for a, b in zip(fast, loop):
         assert a.shape == b.shape and torch.equal(a, b)
     assert relerr(torch.cat(fast, dim=1), ref) < TOL_LOGITS
+
+
+def test_dropout_stream_word_is_bound_only_for_the_duration_of_a_pass(weights):
+    """The dropout stream position (cb_dropout_offset_bind) is process-wide library state: a training forward advances the model's
+    device counter into a fresh per-call word and binds it, the backward re-binds THAT word (it must regenerate the forward's
+    masks even if another forward ran in between - the reference's per-clip loop), and both unbind on the way out, so no later
+    launch can read a word whose tensor has been freed."""
+    import ops_emulator as E
+    from oracle import synth
+    g = torch.Generator().manual_seed(4)
+    grid = (torch.randn(2, 2, 3, 3, 768, generator=g).abs()).to(torch.bfloat16)
+    ids, mask = synth.synth_text(2, 10, seed=5)
+    labels = torch.tensor([1, 0])
+    model = _transformer("ClipBertForVideoTextRetrieval", weights)
+    model.config.hidden_dropout_prob = 0.1                       # (the helper builds p = 0 models; the emulator ignores the masks)
+    seen = []
+    with emulated_transformer_ops(ignore_dropout=True):
+        from clipbert_b200 import ops
+        real_bind = ops.dropout_offset_bind
+
+        def spy(word):
+            seen.append(None if word is None else int(word.item()))
+            real_bind(word)
+        ops.dropout_offset_bind = spy
+        try:
+            out1 = model(ids, grid.clone().requires_grad_(True), mask, labels=labels, sample_size=2)
+            assert E.BOUND_DROPOUT_WORD is None and seen == [1, None]
+            out2 = model(ids, grid.clone().requires_grad_(True), mask, labels=labels, sample_size=2)     # a second forward before any backward
+            assert seen == [1, None, 2, None]
+            out1["loss"].mean().backward()                       # ... and the FIRST pass' backward re-binds the first pass' word
+            assert seen[-2:] == [1, None] and E.BOUND_DROPOUT_WORD is None
+            out2["loss"].mean().backward()
+            assert seen[-2:] == [2, None]
+        finally:
+            ops.dropout_offset_bind = real_bind
+    assert int(model._drop_counter.item()) == 2
+    model.eval()
+    with emulated_transformer_ops(), torch.no_grad():
+        model(ids, grid, mask)                                   # eval: no stream position is consumed
+    assert int(model._drop_counter.item()) == 2
