@@ -262,8 +262,11 @@ def run_b200(args):
     model = model.eval() if args.inference else model.train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
+    exchange = args.exchange
     if world > 1:
-        model.enable_overlapped_allreduce(cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, max_ctas=args.nvls_ctas, wire=args.wire)
+        if exchange == "auto":       # this library's NVLS all-reduce where the box has a multicast mapping (N = 8: 0.956 of linear against
+            exchange = "nvls" if cb.ClipBert.nvls_available(device=dev) else "nccl"          # 0.920 with NCCL, profiles/r02_multi_gpu.txt)
+        model.enable_overlapped_allreduce(cnn_buckets=bool(args.cnn_buckets), exchange=exchange, max_ctas=args.nvls_ctas, wire=args.wire, tail_ctas=args.nvls_tail_ctas)
 
     opt = None
     ops.set_pdl(args.pdl)
@@ -579,7 +582,7 @@ def run_b200(args):
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
-                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=args.exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -703,10 +706,11 @@ def main():
     ap.add_argument("--prefetch", type=int, default=1, help="e2e: upload batch i+1 on a copy stream while batch i computes (0: copy on the compute stream)")
     ap.add_argument("--fused_loss", type=int, default=1, help="1 (default): clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss); 0: ~45 ATen launches")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, or this library's NVLS all-reduce (csrc/nvls.cu; experimental until run on a multi-GPU box)")
-    ap.add_argument("--nvls_ctas", type=int, default=64, help="CTAs of the NVLS all-reduce kernel")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, this library's NVLS all-reduce (csrc/nvls.cu), or auto = nvls where a multicast mapping exists")
+    ap.add_argument("--nvls_ctas", type=int, default=64, help="CTAs of the NVLS all-reduce kernel while it overlaps the backward")
+    ap.add_argument("--nvls_tail_ctas", type=int, default=0, help="CTAs of the NVLS all-reduce of the last, exposed slices (0 = --nvls_ctas)")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"], help="N>1: gradients travel as fp32 (the flat buffers as they are) or as bf16 (cast, all-reduce, cast back: half the payload, the reference's fp16 wire precision)")
-    ap.add_argument("--cnn_buckets", type=int, default=0, help="N>1: exchange res5 + grid_encoder gradients mid-backward (experimental until measured)")
+    ap.add_argument("--cnn_buckets", type=int, default=1, help="N>1: exchange res5 + grid_encoder gradients mid-backward (default; 0: one CNN exchange at the end)")
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
     ap.add_argument("--mn3d", type=int, default=1, help="dgrad / wgrad GEMMs: MN-major operands as one 3-D TMA box per k-chunk (default) or BN/64 2-D boxes")

@@ -222,7 +222,7 @@ class ClipBert(nn.Module):
                 m._flat.grad.zero_()
 
     # ---- NVLS exchange: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) -------------------------------
-    def _nvls_exchange(self, tensors):
+    def _nvls_exchange(self, tensors, ctas=None):
         """All-reduce slices of the symmetric-memory gradient buffers on the communication stream. Each slice: cross-rank
         barrier (every rank has finished writing it - stream order on each rank), cb_nvls_allreduce_f32, barrier (every
         rank's 1/world slice has been stored everywhere)."""
@@ -247,7 +247,7 @@ class ClipBert(nn.Module):
                         raise RuntimeError("NVLS exchange: this system exposes no multicast mapping (use exchange='nccl')")
                 hdl.barrier(channel=0)
                 ops.nvls_allreduce(hdl.multicast_ptr + 4 * t.storage_offset(), t.numel(), hdl.rank, world,
-                                   1.0 / world if dp["average"] else 1.0, dp["max_ctas"])
+                                   1.0 / world if dp["average"] else 1.0, dp["max_ctas"] if ctas is None else ctas)
                 hdl.barrier(channel=0)
             ev = torch.cuda.Event()
             ev.record(comm)
@@ -292,19 +292,40 @@ class ClipBert(nn.Module):
             ev.record(comm)
         return [_Bf16WireWork(ev)]
 
-    def _exchange(self, tensors):
+    def _exchange(self, tensors, exposed=False):
+        """``exposed``: nothing is left to overlap with (the final slices of a step) - the NVLS kernel then gets ``tail_ctas`` CTAs
+        instead of the few that share the SMs with the backward."""
         dp = self._dp
         if not tensors:
             return []
         if dp.get("exchange") == "nvls":
             if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(dp["group"]) == 1:
                 return []
-            return self._nvls_exchange(tensors)
+            return self._nvls_exchange(tensors, dp["tail_ctas"] if exposed else None)
         if dp.get("wire") == "bf16":
             return self._bf16_wire_exchange(tensors)
         return allreduce_flat(tensors, dp["group"], dp["average"], async_op=True)
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64, wire="fp32"):
+    @staticmethod
+    def nvls_available(group=None, device=None):
+        """Collective probe: True on every rank iff every rank can map a symmetric-memory buffer at a multicast (NVLS) address -
+        what ``exchange="nvls"`` needs. Any failure on any rank -> False everywhere (callers fall back to NCCL)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return False
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(4096, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            ok = 1 if hdl.multicast_ptr else 0
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(int(flag.item()))
+
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64, wire="fp32", tail_ctas=None):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
@@ -316,7 +337,7 @@ class ClipBert(nn.Module):
         ``wire="bf16"``: exchange the gradients as bf16 (see ``_bf16_wire_exchange``)."""
         assert exchange in ("nccl", "nvls") and wire in ("fp32", "bf16")
         self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True, exchange=exchange,
-                        max_ctas=int(max_ctas), handles={}, wire=wire, shadows={})
+                        max_ctas=int(max_ctas), tail_ctas=int(tail_ctas if tail_ctas else max_ctas), handles={}, wire=wire, shadows={})
         if exchange == "nvls":
             # ``exchange="nvls"``: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) instead of NCCL. The flat
             # gradient buffers must then live in symmetric memory, so call this BEFORE the first forward (buffers that already
@@ -382,7 +403,7 @@ class ClipBert(nn.Module):
             g = cf.grad if lo is None else cf.grad[:lo]                    # the tail [lo:) is already in flight (cnn_buckets)
             if g.numel():
                 rest.append(g)
-        works += self._exchange(rest)
+        works += self._exchange(rest, exposed=True)
         for w in works:
             w.wait()
         return []
