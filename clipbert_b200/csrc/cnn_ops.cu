@@ -119,6 +119,35 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const TIn* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Frame resize + pad of the data pipeline (src/datasets/data_utils.py:202-234 ImageResize = F.interpolate(mode="bilinear",
+// align_corners=False) to (nh, nw) with the longer side = max_size, :136-160 ImagePad = F.pad with zeros at the bottom / right
+// up to max_size x max_size; dataset_base.py:191-195). NCHW in (uint8 or fp32), fp32 NCHW out [n, c, S, S].
+// Source coordinate of output pixel o: max(0, (o + 0.5) * in / out - 0.5) (ATen area_pixel_compute_source_index).
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) resize_pad_kernel(const TIn* __restrict__ x, float* __restrict__ y, int NC, int H, int W, int nh, int nw,
+                                                         int S, float sh, float sw) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<int64_t>(NC) * S * S) return;
+  const int ox = static_cast<int>(t % S), oy = static_cast<int>((t / S) % S);
+  const int64_t plane = t / (static_cast<int64_t>(S) * S);
+  float v = 0.f;
+  if (oy < nh && ox < nw) {
+    const float fy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(fy), H - 1), x0 = min(static_cast<int>(fx), W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const TIn* p = x + plane * H * W;
+    const float a = static_cast<float>(p[static_cast<int64_t>(y0) * W + x0]), b = static_cast<float>(p[static_cast<int64_t>(y0) * W + x1]);
+    const float c = static_cast<float>(p[static_cast<int64_t>(y1) * W + x0]), d = static_cast<float>(p[static_cast<int64_t>(y1) * W + x1]);
+    v = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * c + lx * d);
+  }
+  y[t] = v;
+}
+
 // 3x3 stride-2 pad-1 max pool, NHWC
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W,
                                     int C, int Ho, int Wo, int64_t row_pitch /* pixels */, int64_t img_pitch /* pixels */) {
@@ -339,6 +368,23 @@ int cb_stem_s2d(const void* x, int in_dtype, void* out, int n, int h, int w, int
   else
     CB_REQUIRE(false, "cb_stem_s2d: in_dtype must be 0 (fp32) or 1 (uint8)");
   return check_launch("cb_stem_s2d");
+}
+
+int cb_resize_pad(const void* x, int in_dtype, float* y, int planes, int h, int w, int new_h, int new_w, int max_size, void* stream) {
+  CB_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, "cb_resize_pad: bad arguments");
+  CB_REQUIRE(new_h > 0 && new_w > 0 && new_h <= max_size && new_w <= max_size, "cb_resize_pad: resized frame %d x %d must fit %d x %d", new_h,
+             new_w, max_size, max_size);
+  const int64_t total = static_cast<int64_t>(planes) * max_size * max_size;
+  const float sh = static_cast<float>(h) / new_h, sw = static_cast<float>(w) / new_w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == 0)
+    launch_k(resize_pad_kernel<float>, ceil_div(total, 256), 256, 0, st, static_cast<const float*>(x), y, planes, h, w, new_h, new_w, max_size, sh, sw);
+  else if (in_dtype == 1)
+    launch_k(resize_pad_kernel<uint8_t>, ceil_div(total, 256), 256, 0, st, static_cast<const uint8_t*>(x), y, planes, h, w, new_h, new_w, max_size,
+             sh, sw);
+  else
+    CB_REQUIRE(false, "cb_resize_pad: in_dtype must be 0 (fp32) or 1 (uint8)");
+  return check_launch("cb_resize_pad");
 }
 
 int cb_subsample2(const void* x, void* y, int n, int h, int w, int c, void* stream) {

@@ -76,6 +76,39 @@ class _ClipLseLoss(torch.autograd.Function):
         return (dz * g).to(ctx.in_dtype), None
 
 
+class _ClipPoolCeLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, pool):
+        from . import ops
+        z = logits.detach()
+        z = (z if z.dtype == torch.float32 else z.float()).contiguous()
+        n_clips, nseq, ncls = z.shape
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        ops.clip_pool_ce_loss(z, labels.to(torch.int64).contiguous(), loss, dz, n_clips, nseq, ncls, pool, 1.0)
+        ctx.dz, ctx.in_dtype = dz, logits.dtype
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dz, ctx.dz = ctx.dz, None
+        return (dz * g).to(ctx.in_dtype), None, None
+
+
+def clip_pool_loss(logits, labels, pool_method="lse"):
+    """Clip aggregation + cross-entropy loss of the training loops for every ``score_agg_func`` of the reference
+    (src/tasks/run_video_retrieval.py:404-422, run_video_qa.py:484-501): "lse" (the shipped configs), "mean", "max" - one fused
+    forward+backward kernel each. ``logits``: ``(n_clips, B', C)`` (``torch.stack`` of the per-clip logits, what
+    ``ClipBert.forward_clips`` returns); ``labels``: ``(B',)`` int64; returns the scalar mean loss with autograd support."""
+    if isinstance(logits, (list, tuple)):
+        logits = torch.stack(list(logits))
+    if pool_method == "lse":
+        return _ClipLseLoss.apply(logits, labels)
+    if pool_method not in ("mean", "max"):
+        raise ValueError("Invalid value for pool_method, got %s, expect one of [`mean`, `max`, `lse`]" % pool_method)
+    return _ClipPoolCeLoss.apply(logits, labels, 1 if pool_method == "mean" else 2)
+
+
 def clip_lse_loss(logits, labels):
     """Clip aggregation + loss of the training loops with ``pool_method == "lse"``
     (src/tasks/run_video_retrieval.py:404-422, run_video_qa.py:484-501) as one fused forward+backward kernel.

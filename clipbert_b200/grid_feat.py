@@ -151,6 +151,8 @@ class GridFeatBackbone(nn.Module):
         self._segments = None
         self._pad_pool = {}
         self.pixel_mean = None   # set to (r,g,b) to take uint8 frames and fuse ImageNorm into the stem gather
+        self.raw_float_inputs = False   # True: fp32 frames are RAW (0..255) and get the fused ImageNorm too (input_stage.set_image_norm)
+        self.pixel_std = None    # (r,g,b) of ImageNorm's div_(std) (data_utils.py:276): folded into the stem conv weights at pack time
         self.stem_mode = "s2d"   # "s2d": space-to-depth implicit GEMM (no patch matrix); "im2col": patch gather + GEMM
         self._s2d_ld = 16        # 16: overlapping tensor-map rows; 64: explicit windows (set automatically if the driver refuses)
         self._optimizer_emits_packed = False   # FusedAdamW writes the bf16 operands itself (clipbert_b200/optim.py)
@@ -271,6 +273,14 @@ class GridFeatBackbone(nn.Module):
             m._w = flat.packed[e["offset"]: e["offset"] + n].view(m.cout, row_len)
             m._gw = flat.grad[e["offset"]: e["offset"] + n].view(m.cout, row_len)
         stem = self.feature.backbone.stem.conv1
+        if self.pixel_std is not None and any(float(v) != 1.0 for v in self.pixel_std):
+            # conv(w, (x - mean) / std) == conv(w / std[c], x - mean): ImageNorm's division lives in the (frozen) stem weights, so the
+            # gather kernel only subtracts the mean. Input channels of the stem are in BGR order (grid_feat.py:92-94).
+            e = stem._e
+            w32 = flat.master[e["offset"]: e["offset"] + e["numel"]].view(64, 49, 3) * self._bn_scale[stem._bn_off: stem._bn_off + 64].view(64, 1, 1)
+            r, g, b_ = (float(v) for v in self.pixel_std)
+            inv = torch.tensor([1.0 / b_, 1.0 / g, 1.0 / r], dtype=torch.float32, device=w32.device)
+            stem._w.copy_((w32 * inv).reshape(64, 147))
         self._stem_w[:, :147] = stem._w      # [64, (r,s,c)] -> row pitch 152
         self._pack_stem_s2d(stem._w)
         stem._w = self._stem_w
@@ -350,9 +360,12 @@ class GridFeatBackbone(nn.Module):
         assert c == 3
         n = bsz * n_frms
         x = images.reshape(n, c, h, w)
-        if x.dtype == torch.uint8:
-            assert self.pixel_mean is not None, "uint8 frames need pixel_mean (fused ImageNorm)"
+        if x.dtype == torch.uint8 or self.raw_float_inputs:
+            # raw frames (uint8, or the fp32 output of input_stage.resize_pad): ImageNorm is fused - mean in the stem gather, 1 / std in
+            # the stem weights. Float frames are otherwise taken as already normalised (what the reference's PrefetchLoader hands over).
+            assert self.pixel_mean is not None, "raw frames need pixel_mean (fused ImageNorm)"
             mean = tuple(float(v) for v in self.pixel_mean)
+            x = x if x.dtype in (torch.uint8, torch.float32) else x.float()
         else:
             x = x.float() if x.dtype != torch.float32 else x
             mean = (0.0, 0.0, 0.0)

@@ -664,7 +664,7 @@ class ClipBertForVideoTextRetrieval(_MlpHeadMixin, _ClipBertHeadModel):
             return logits, 0
         loss_type = _cfg(self.config, "loss_type")
         if loss_type == "ce":
-            loss = F.cross_entropy(logits.view(-1, _cfg(self.config, "num_labels")), labels.view(-1), reduction="none")
+            loss = cross_entropy_none(logits.view(-1, _cfg(self.config, "num_labels")), labels.view(-1))
         elif loss_type == "rank":
             scores = torch.sigmoid(logits).squeeze()
             assert sample_size > 0
@@ -673,6 +673,38 @@ class ClipBertForVideoTextRetrieval(_MlpHeadMixin, _ClipBertHeadModel):
         else:
             raise ValueError("Invalid option for config.loss_type")
         return logits, loss
+
+
+class _CrossEntropyNone(torch.autograd.Function):
+    """``F.cross_entropy(logits, labels, reduction="none")`` on cb_cross_entropy_fwd / _bwd: one pass over each row forward, one
+    backward (ATen materialises a log-softmax of the size of the logits - 30 522 columns for the masked-LM loss)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        z = logits.detach()
+        if z.dtype != torch.float32 or z.stride(-1) != 1:
+            z = z.float().contiguous()
+        y = labels.to(torch.int64).contiguous()
+        loss = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        lse = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        ops.cross_entropy_fwd(z, y, loss, lse)
+        ctx.save_for_backward(z, y, lse)
+        ctx.in_dtype = logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        z, y, lse = ctx.saved_tensors
+        dz = torch.empty_like(z)
+        ops.cross_entropy_bwd(z, y, lse, g.to(torch.float32).contiguous(), dz)
+        return dz.to(ctx.in_dtype), None
+
+
+def cross_entropy_none(logits, labels):
+    """The reference's ``F.cross_entropy(..., reduction="none")`` calls (src/modeling/modeling.py:286-299,430-436,560-566) on this
+    library's kernel for CUDA tensors; ``logits`` (rows, C), ``labels`` (rows,) with ignore_index -100."""
+    _require_cuda(logits)
+    return _CrossEntropyNone.apply(logits, labels)
 
 
 def instance_bce_with_logits(logits, labels, reduction="mean"):
@@ -709,7 +741,7 @@ class ClipBertForSequenceClassification(_MlpHeadMixin, _ClipBertHeadModel):
         elif _cfg(self.config, "loss_type") == "bce":
             loss = instance_bce_with_logits(logits, labels, reduction="none")
         elif _cfg(self.config, "loss_type") == "ce":
-            loss = F.cross_entropy(logits.view(-1, nl), labels.view(-1), reduction="none")
+            loss = cross_entropy_none(logits.view(-1, nl), labels.view(-1))
         else:
             raise ValueError("Invalid option for config.loss_type")
         return logits, loss
@@ -743,7 +775,7 @@ class ClipBertForMultipleChoice(_MlpHeadMixin, _ClipBertHeadModel):
         elif loss_type == "bce":
             loss = instance_bce_with_logits(logits, labels, reduction="none")
         elif loss_type == "ce":
-            loss = F.cross_entropy(logits, labels.view(-1), reduction="none")
+            loss = cross_entropy_none(logits, labels.view(-1))
         else:
             raise ValueError("Invalid option for config.loss_type")
         return logits, loss
@@ -911,8 +943,8 @@ class ClipBertForPreTraining(_ClipBertHeadModel):
     def forward(self, text_input_ids, visual_inputs, text_input_mask, mlm_labels=None, itm_labels=None, _repeat_counts=None, **_unused):
         itm_scores, mlm_scores = self._run(text_input_ids, visual_inputs, text_input_mask, _repeat_counts)
         v = _cfg(self.config, "vocab_size")
-        mlm_loss = F.cross_entropy(mlm_scores.reshape(-1, v), mlm_labels.view(-1), reduction="none") if mlm_labels is not None else 0
-        itm_loss = F.cross_entropy(itm_scores.view(-1, 2), itm_labels.view(-1), reduction="none") if itm_labels is not None else 0
+        mlm_loss = cross_entropy_none(mlm_scores.reshape(-1, v), mlm_labels.view(-1)) if mlm_labels is not None else 0
+        itm_loss = cross_entropy_none(itm_scores.view(-1, 2), itm_labels.view(-1)) if itm_labels is not None else 0
         return dict(mlm_scores=mlm_scores, mlm_loss=mlm_loss, mlm_labels=mlm_labels, itm_scores=itm_scores, itm_loss=itm_loss,
                     itm_labels=itm_labels)
 

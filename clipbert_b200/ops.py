@@ -32,12 +32,16 @@ _SIGS = {
     "cb_cast_scale_segments": [_vp, _vp, _vp, _i, _vp, _vp],
     "cb_nvls_allreduce_f32": [_vp, _i64, _i, _i, _f, _i, _vp],
     "cb_clip_lse_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    "cb_clip_pool_ce_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "cb_cross_entropy_fwd": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i64, _vp],
+    "cb_cross_entropy_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64, _vp],
     "cb_attention_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_attention_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _u64, _vp],
     "cb_stem_im2col": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
     "cb_maxpool3x3s2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "cb_maxpool3x3s2_strided": [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp],
     "cb_stem_s2d": [_vp, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
+    "cb_resize_pad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "cb_subsample2": [_vp, _vp, _i, _i, _i, _i, _vp],
     "cb_unsubsample2_mask": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cb_maxpool2x2_relu_fwd": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -312,6 +316,20 @@ def clip_lse_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, grad_scale
     _call("cb_clip_lse_loss", _p(logits), _p(labels), _p(loss), _p(dlogits), n_clips, nseq, ncls, grad_scale, _s())
 
 
+def clip_pool_ce_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, pool, grad_scale=1.0):
+    """pool: 1 = mean, 2 = max over the clips, then cross entropy (cb_clip_pool_ce_loss)."""
+    _call("cb_clip_pool_ce_loss", _p(logits), _p(labels), _p(loss), _p(dlogits), n_clips, nseq, ncls, pool, grad_scale, _s())
+
+
+def cross_entropy_fwd(logits, labels, loss, lse, ignore_index=-100):
+    _call("cb_cross_entropy_fwd", _p(logits), logits.stride(0), _p(labels), _p(loss), _p(lse), logits.shape[0], logits.shape[1], ignore_index, _s())
+
+
+def cross_entropy_bwd(logits, labels, lse, grad_loss, dlogits, ignore_index=-100):
+    _call("cb_cross_entropy_bwd", _p(logits), logits.stride(0), _p(labels), _p(lse), _p(grad_loss), _p(dlogits), dlogits.stride(0), logits.shape[0],
+          logits.shape[1], ignore_index, _s())
+
+
 def colsum(x, out, m, n, ld=None):
     _call("cb_colsum", _p(x), n if ld is None else ld, _p(out), m, n, _s())
 
@@ -361,6 +379,12 @@ def stem_im2col(x, out, n, h, w, kp, mean=(0.0, 0.0, 0.0)):
 def stem_s2d(x, out, n, h, w, ld, mean=(0.0, 0.0, 0.0)):
     dt = 0 if x.dtype == torch.float32 else 1
     _call("cb_stem_s2d", _p(x), dt, _p(out), n, h, w, ld, mean[0], mean[1], mean[2], _s())
+
+
+def resize_pad(x, y, new_h, new_w):
+    """x: (..., h, w) uint8 / fp32 planes; y: (..., S, S) fp32 - bilinear (align_corners=False) resize to new_h x new_w, zero pad to S."""
+    dt = 0 if x.dtype == torch.float32 else 1
+    _call("cb_resize_pad", _p(x), dt, _p(y), x.numel() // (x.shape[-1] * x.shape[-2]), x.shape[-2], x.shape[-1], new_h, new_w, y.shape[-1], _s())
 
 
 def maxpool3x3s2(x, y, n, h, w, c, row_pitch=None, img_pitch=None):

@@ -246,6 +246,11 @@ int cb_cast_scale_segments(const float* master, void* packed, const int64_t* seg
  *   cb_maxpool2x2_relu_bwd  its backward, written into the zero-bordered layout read by the 3x3 dgrad/wgrad
  *   cb_relu_mask            dx = dy * (act > 0)
  * ------------------------------------------------------------------------------------------ */
+/* Frame resize + pad of the data pipeline (src/datasets/data_utils.py:202-234 ImageResize: F.interpolate(bilinear,
+ * align_corners=False) to new_h x new_w, longer side = max_size; :136-160 ImagePad: zeros at the bottom / right up to
+ * max_size x max_size; src/datasets/dataset_base.py:191-195). x: `planes` = n * c planes of h x w (in_dtype 0 fp32, 1 uint8),
+ * y: fp32 [planes, max_size, max_size]. */
+int cb_resize_pad(const void* x, int in_dtype, float* y, int planes, int h, int w, int new_h, int new_w, int max_size, void* stream);
 int cb_stem_im2col(const void* x, int in_dtype, void* out, int n, int h, int w, int kp, float mean_r, float mean_g,
                    float mean_b, void* stream);
 int cb_stem_s2d(const void* x, int in_dtype, void* out, int n, int h, int w, int ld, float mean_r, float mean_g, float mean_b,
@@ -267,6 +272,18 @@ int cb_relu_mask(const void* dy, const void* act, void* dx, int64_t n, void* str
  * ------------------------------------------------------------------------------------------ */
 int cb_clip_lse_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int n_clips, int nseq, int ncls,
                      float grad_scale, void* stream);
+/* pool_method "mean" (pool = 1) / "max" (pool = 2) of the same loops (run_video_retrieval.py:405-408, run_video_qa.py:485-488):
+ * logits.mean(0) / logits.max(0)[0] followed by F.cross_entropy(reduction="none").mean(); same tensors as cb_clip_lse_loss */
+int cb_clip_pool_ce_loss(const float* logits, const int64_t* labels, float* loss, float* dlogits, int n_clips, int nseq, int ncls, int pool,
+                         float grad_scale, void* stream);
+/* F.cross_entropy(logits, labels, reduction="none") over `rows` rows of `ncls` fp32 logits (row pitch ld), labels int64 with
+ * ignore_index (-100: loss 0, no gradient): the masked-LM loss over the vocabulary (src/modeling/modeling.py:286-299), the
+ * ITM / multiple-choice / retrieval CE (:560-580, :430-436). fwd: loss[rows], lse[rows] (stash). bwd: dlogits[r, c] =
+ * grad_loss[r] * (softmax(z)[c] - [c == y]) with row pitch dld. One block per row, one pass over the row each. */
+int cb_cross_entropy_fwd(const float* logits, int64_t ld, const int64_t* labels, float* loss, float* lse, int64_t rows, int ncls,
+                         int64_t ignore_index, void* stream);
+int cb_cross_entropy_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* grad_loss, float* dlogits,
+                         int64_t dld, int64_t rows, int ncls, int64_t ignore_index, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange through the NVSwitch, replacing hvd.DistributedOptimizer.synchronize()

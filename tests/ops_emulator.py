@@ -294,6 +294,14 @@ def stem_s2d(x, out, n, h, w, ld, mean=(0.0, 0.0, 0.0)):
     out.view(-1)[n * hs * ws * 16:].zero_()             # the slack the last windows run into (the kernel leaves it unwritten)
 
 
+def resize_pad(x, y, new_h, new_w):
+    lead = x.shape[:-2]
+    r = F.interpolate(x.reshape(-1, 1, x.shape[-2], x.shape[-1]).float(), size=(new_h, new_w), mode="bilinear", align_corners=False)
+    y.zero_()
+    y.view(-1, y.shape[-2], y.shape[-1])[:, :new_h, :new_w] = r[:, 0]
+    assert tuple(y.shape[:-2]) == tuple(lead)
+
+
 def maxpool3x3s2(x, y, n, h, w, c, row_pitch=None, img_pitch=None):
     row_pitch = w if row_pitch is None else row_pitch
     img_pitch = h * w if img_pitch is None else img_pitch
@@ -400,6 +408,31 @@ def opt_adamw_step(master, grad, exp_avg, exp_avg_sq, packed, chunks, nchunks, h
             packed[sl] = p.to(packed.dtype)
 
 
+def clip_pool_ce_loss(logits, labels, loss, dlogits, n_clips, nseq, ncls, pool, grad_scale=1.0):
+    z = logits.detach().double().requires_grad_(True)
+    pooled = z.mean(0) if pool == 1 else z.max(0)[0]
+    v = torch.nn.functional.cross_entropy(pooled, labels, reduction="none").mean()
+    v.backward()
+    loss.copy_(v.detach().float().reshape(1))
+    if dlogits is not None:
+        dlogits.copy_((z.grad * grad_scale).float())
+
+
+def cross_entropy_fwd(logits, labels, loss, lse, ignore_index=-100):
+    z = logits.double()
+    lse.copy_(torch.logsumexp(z, -1).float())
+    loss.copy_(torch.nn.functional.cross_entropy(z, labels, reduction="none", ignore_index=ignore_index).float())
+
+
+def cross_entropy_bwd(logits, labels, lse, grad_loss, dlogits, ignore_index=-100):
+    z = logits.double()
+    p = torch.exp(z - lse.double()[:, None])
+    ok = (labels != ignore_index) & (labels >= 0) & (labels < z.shape[1])
+    onehot = torch.zeros_like(p)
+    onehot[ok, labels[ok]] = 1.0
+    dlogits.copy_(((p - onehot) * (grad_loss.double() * ok.double())[:, None]).float())
+
+
 def cast_bf16_f32(src, dst):
     dst.copy_(src.float())
 
@@ -422,7 +455,8 @@ BOUND_DROPOUT_WORD = None
 _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "embed_visual_fwd", "embed_visual_bwd",
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
-          "cast_scale_segments", "clip_lse_loss", "nvls_allreduce", "dropout_offset_bind", "dropout_offset_advance", "cast_bf16_f32")
+          "cast_scale_segments", "clip_lse_loss", "nvls_allreduce", "dropout_offset_bind", "dropout_offset_advance", "cast_bf16_f32",
+          "clip_pool_ce_loss", "cross_entropy_fwd", "cross_entropy_bwd", "resize_pad")
 
 
 @contextlib.contextmanager

@@ -449,3 +449,23 @@ def test_bf16_wire_exchange_plumbing_world_size_2():
             assert float(((t - want_t).abs() / want_t).max()) < 2 ** -7
             assert float((c - want_c).abs().max()) <= float(want_c.max()) * 2 ** -7
             assert float((t - want_t).abs().max()) > 0.0                  # it really went through bf16
+
+
+def test_input_stage_resize_size_matches_the_reference_function():
+    """get_resize_size for tensors (src/datasets/data_utils.py:166-198), executed from the reference source where it exists."""
+    from clipbert_b200 import input_stage as IS
+    cases = [(360, 640, 448), (640, 360, 448), (224, 224, 224), (37, 53, 96), (1080, 1920, 768), (500, 499, 1000)]
+    ref_path = os.path.join(os.environ.get("CLIPBERT_REFERENCE_ROOT", "/root/reference"), "src", "datasets", "data_utils.py")
+    ref_fn = None
+    if os.path.exists(ref_path):
+        import ast
+        tree = ast.parse(open(ref_path).read())
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_resize_size"]
+        ns = {"torch": torch}
+        exec(compile(ast.Module(body=fn, type_ignores=[]), ref_path, "exec"), ns)
+        ref_fn = ns["get_resize_size"]
+    for h, w, s in cases:
+        nh, nw = IS.get_resize_size(h, w, s)
+        assert max(nh, nw) == s and min(nh, nw) == int(s * min(h, w) / max(h, w))
+        if ref_fn is not None:
+            assert (nh, nw) == tuple(ref_fn(torch.zeros(3, h, w), s))

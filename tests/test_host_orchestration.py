@@ -405,3 +405,32 @@ def test_dropout_stream_word_is_bound_only_for_the_duration_of_a_pass(weights):
     with emulated_transformer_ops(), torch.no_grad():
         model(ids, grid, mask)                                   # eval: no stream position is consumed
     assert int(model._drop_counter.item()) == 2
+
+
+def test_input_stage_on_emulated_ops(weights):
+    """clipbert_b200.input_stage: resize_pad (ImageResize + ImagePad) through the emulated cb_resize_pad, and ImageNorm's mean /
+    std fused into the stem (mean in the gather, 1 / std folded into the stem weights at pack time) against the oracle fed with
+    the explicitly normalised frames."""
+    import torch.nn.functional as F
+    from clipbert_b200 import input_stage as IS
+    from oracle import clipbert_ref as R
+    g = torch.Generator().manual_seed(9)
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    raw = torch.randint(0, 256, (1, 2, 3, 40, 72), generator=g, dtype=torch.uint8)
+    model = _clipbert(weights).eval()
+    IS.set_image_norm(model, mean, std)
+    with emulated_transformer_ops():
+        frames = torch.empty(1, 2, 3, 64, 64)          # (input_stage.resize_pad itself asserts CUDA tensors: call the op it wraps)
+        from clipbert_b200 import ops
+        nh, nw = IS.get_resize_size(40, 72, 64)
+        ops.resize_pad(raw, frames, nh, nw)
+        ref = F.pad(F.interpolate(raw.view(-1, 3, 40, 72).float(), size=(nh, nw), mode="bilinear", align_corners=False), (0, 64 - nw, 0, 64 - nh))
+        assert torch.equal(frames.view(-1, 3, 64, 64), ref) and (nh, nw) == (35, 64)
+        model.cnn._capture = {}
+        with torch.no_grad():
+            model.cnn(frames)
+        cap, model.cnn._capture = model.cnn._capture, None
+    xn = (frames - torch.tensor(mean).view(1, 1, 3, 1, 1)) / torch.tensor(std).view(1, 1, 3, 1, 1)
+    with torch.no_grad():
+        _, st = R.grid_feat_backbone(xn, weights, return_stages=True, rnd=R.Rounding.bf16())
+    assert relerr(cap["stem"].float().permute(0, 3, 1, 2), st["stem"]) < 1e-2

@@ -267,3 +267,123 @@ def test_training_step_replayed_from_a_cuda_graph_draws_fresh_dropout_masks(cuda
     assert relerr(probe(), grads[0]) < 1e-5                                # (fp32 red.add accumulation order is the only freedom left)
     _record("dropout under graph replay: losses of three replays %s, rewound replay reproduces #0 to %.1e"
             % (" ".join("%.6f" % v for v in losses), abs(float(loss_dev) - losses[0])))
+
+
+# ------------------------------------------------------------------------------------------------ loss / input-stage kernels
+def test_cross_entropy_and_clip_pooling_kernels(cuda):
+    """cb_cross_entropy_fwd / _bwd (F.cross_entropy(reduction="none"): the masked-LM loss over 30 522 classes with ignore_index,
+    the 2- / 5-way heads, src/modeling/modeling.py:286-299,430-436,560-566) and cb_clip_pool_ce_loss (pool_method "mean" / "max",
+    run_video_retrieval.py:405-408) against torch on fp32: 1e-5 relative (fast-math exp / log)."""
+    import clipbert_b200 as cb
+    from clipbert_b200.modeling import cross_entropy_none
+    g = torch.Generator().manual_seed(5)
+    for rows, ncls in ((64, 30522), (7, 2), (33, 5), (1, 3129)):
+        z = (torch.randn(rows, ncls, generator=g) * 3).to(cuda)
+        y = torch.randint(0, ncls, (rows,), generator=g).to(cuda)
+        if rows > 4:
+            y[1] = -100                                     # ignore_index rows: loss 0, no gradient
+            y[rows - 1] = -100
+        w = torch.rand(rows, generator=g).to(cuda)          # upstream gradient of the per-row losses
+        zr = z.clone().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(zr, y, reduction="none")
+        (ref * w).sum().backward()
+        zt = z.clone().requires_grad_(True)
+        got = cross_entropy_none(zt, y)
+        (got * w).sum().backward()
+        assert relerr(got, ref) < 1e-5 and relerr(zt.grad, zr.grad) < 1e-5, (rows, ncls, relerr(got, ref), relerr(zt.grad, zr.grad))
+        assert float(got[y == -100].abs().sum()) == 0.0 and float(zt.grad[y == -100].abs().sum()) == 0.0
+    for n_clips, nseq, ncls, scale in ((2, 32, 2, 1.0), (4, 320, 5, 3.0), (16, 8, 2, 0.2), (1, 1, 2, 1.0)):
+        z = (torch.randn(n_clips, nseq, ncls, generator=g) * scale).to(cuda)
+        y = torch.randint(0, ncls, (nseq,), generator=g).to(cuda)
+        for pool in ("mean", "max"):
+            zr = z.clone().requires_grad_(True)
+            pooled = zr.mean(0) if pool == "mean" else zr.max(0)[0]
+            ref = torch.nn.functional.cross_entropy(pooled, y, reduction="none").mean()
+            (2.0 * ref).backward()
+            zt = z.clone().requires_grad_(True)
+            loss = cb.clip_pool_loss(zt, y, pool)
+            (2.0 * loss).backward()
+            assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref))), (pool, n_clips, nseq, ncls)
+            assert relerr(zt.grad, zr.grad) < 2e-5, (pool, n_clips, nseq, ncls, relerr(zt.grad, zr.grad))
+    with pytest.raises(ValueError, match="pool_method"):
+        cb.clip_pool_loss(z, y, "median")
+
+
+def test_input_stage_resize_pad_and_image_norm_std(cuda, weights):
+    """SURVEY §8 f3 on the GPU: cb_resize_pad against the reference's own tensor path (ImageResize = F.interpolate(bilinear,
+    align_corners=False), ImagePad = F.pad zeros bottom / right, src/datasets/data_utils.py:136-160,202-234) for landscape,
+    portrait, up- and down-scaling, uint8 and fp32 frames; and ImageNorm's div_(std) (data_utils.py:276) folded into the stem
+    weights: stem output of raw uint8 frames == stem output of the oracle on (x - mean) / std."""
+    import torch.nn.functional as F
+    from clipbert_b200 import input_stage as IS
+    from oracle import clipbert_ref as R
+    g = torch.Generator().manual_seed(9)
+    for (h, w, S, dt) in ((360, 640, 448, torch.uint8), (640, 360, 224, torch.uint8), (100, 150, 224, torch.float32), (224, 224, 224, torch.uint8),
+                          (37, 53, 96, torch.float32)):
+        x = torch.randint(0, 256, (2, 3, 3, h, w), generator=g).to(dt)
+        nh, nw = IS.get_resize_size(h, w, S)
+        ref = F.interpolate(x.view(-1, 3, h, w).float(), size=(nh, nw), mode="bilinear", align_corners=False)
+        ref = F.pad(ref, (0, S - nw, 0, S - nh), "constant", 0).view(2, 3, 3, S, S)
+        got = IS.resize_pad(x.to(cuda), S)
+        assert got.shape == ref.shape and got.dtype == torch.float32
+        assert float((got.cpu() - ref).abs().max()) < 1e-3, (h, w, S, float((got.cpu() - ref).abs().max()))      # pixel values 0 .. 255, fp32
+        assert float(got[..., nh:, :].abs().max() if nh < S else 0.0) == 0.0 and float(got[..., :, nw:].abs().max() if nw < S else 0.0) == 0.0
+    # ---- ImageNorm with a real std: raw uint8 frames in, the division lives in the stem weights ----
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    model = _clipbert("ClipBertForVideoTextRetrieval", weights, cuda).eval()
+    IS.set_image_norm(model, mean, std)
+    u8 = torch.randint(0, 256, (1, 2, 3, 96, 96), generator=g, dtype=torch.uint8)
+    model.cnn._capture = {}
+    with torch.no_grad():
+        model.cnn(u8.to(cuda))
+    cap, model.cnn._capture = model.cnn._capture, None
+    xn = (u8.float() - torch.tensor(mean).view(1, 1, 3, 1, 1)) / torch.tensor(std).view(1, 1, 3, 1, 1)
+    with torch.no_grad():
+        _, st = R.grid_feat_backbone(xn, weights, return_stages=True, rnd=R.Rounding.bf16())
+    e = relerr(cap["stem"].float().permute(0, 3, 1, 2), st["stem"])
+    _record("ImageNorm std folded into the stem weights: stem output vs matched oracle on (x - mean) / std: %.3e" % e)
+    assert e < 1e-2, e          # (the two sides round different quantities to bf16: w / std here, (x - mean) / std there)
+
+
+def test_reference_checkpoint_round_trip_on_the_device(cuda, weights, tmp_path):
+    """SURVEY §8 f4 on the GPU: a reference-layout checkpoint file (e2e keys + the dead d2 heads, as ModelSaver writes it) goes
+    through load_state_dict_with_mismatch into the packed NHWC / bf16 operands, the model runs, export_state_dict writes the
+    reference layout back bit for bit, and a second model restored from that file produces the same logits bit for bit; a
+    torchvision ResNet-50 checkpoint converted with the reference's key map loads into the backbone the same way."""
+    import torchvision
+    from clipbert_b200 import load_save as LS
+    from oracle import synth
+    ck = dict(weights)
+    ck["cnn.feature.roi_heads.box_head.fc1.weight"] = torch.zeros(8, 8)            # dead d2 head: ignored
+    ck["transformer.classifier.2.weight"] = torch.zeros(7, 1536)                  # a head with another num_labels: skipped, not an error
+    path = str(tmp_path / "e2e.pt")
+    torch.save(ck, path)
+    a = _clipbert("ClipBertForVideoTextRetrieval", weights, cuda).eval()
+    with torch.no_grad():
+        for p in a.parameters():
+            p.add_(0.5)                                                            # whatever was there must be overwritten
+    res = LS.load_state_dict_with_mismatch(a, path)
+    assert res["mismatched"] == ["transformer.classifier.2.weight"] and res["unexpected"] == ["cnn.feature.roi_heads.box_head.fc1.weight"]
+    batch = synth.synth_batch(2, 2, n_ex=1, size=96, seed=71)
+    with torch.no_grad():
+        la = a(_to(batch, cuda))["logits"]
+    out = LS.export_state_dict(a)
+    for k, v in weights.items():
+        if k != "transformer.classifier.2.weight":
+            assert torch.equal(out[k], v), k                                       # fp32 masters come back bit for bit, reference layout
+    path2 = str(tmp_path / "saved.pt")
+    torch.save(out, path2)
+    b = _clipbert("ClipBertForVideoTextRetrieval", weights, cuda).eval()
+    LS.load_state_dict_with_mismatch(b, path2)
+    with torch.no_grad():
+        lb = b(_to(batch, cuda))["logits"]
+    assert torch.equal(la, lb)
+    # torchvision ResNet-50 -> detectron2 names (src/utils/load_save.py:318-363) -> backbone, forward runs
+    torch.manual_seed(3)
+    tv = torchvision.models.resnet50().state_dict()
+    loaded, ignored = LS.load_detectron2_checkpoint(b.cnn, LS.convert_torchvision_ckpt_to_detectron2(tv))
+    assert len(loaded) == 53 * 5 - 53 + 53 or len(loaded) > 200                    # 53 convs + their FrozenBN buffers
+    assert any(k.startswith("stem.fc") or "fc." in k for k in ignored)
+    with torch.no_grad():
+        lc = b(_to(batch, cuda))["logits"]
+    assert bool(torch.isfinite(lc).all()) and not torch.equal(lc, lb)
