@@ -140,13 +140,13 @@ __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restr
   }
   __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
   const float wm = warp_max(m);
-  s = warp_sum(s * __expf(m - wm));
+  s = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - wm));      // (threads / warps beyond a short row hold (-inf, 0): exp(-inf + inf) is NaN)
   if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = wm; ss[threadIdx.x >> 5] = s; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float bm = -INFINITY, bs = 0.f;
     for (int i = 0; i < CE_THREADS / 32; ++i) bm = fmaxf(bm, sm[i]);
-    for (int i = 0; i < CE_THREADS / 32; ++i) bs += ss[i] * __expf(sm[i] - bm);
+    for (int i = 0; i < CE_THREADS / 32; ++i) bs += sm[i] == -INFINITY ? 0.f : ss[i] * __expf(sm[i] - bm);
     const float lse = bm + __logf(bs);
     const int64_t y = labels[r];
     lse_out[r] = lse;
