@@ -358,7 +358,7 @@ class ClipBert(nn.Module):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         return bool(int(flag.item()))
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=64, wire="fp32", tail_ctas=None):
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=32, wire="fp32", tail_ctas=148):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
