@@ -140,7 +140,7 @@ NCU_TRAFFIC_BYTES = {(401408, 256, 64, 1, True): 257.014272e6 + 165.274624e6}
 
 
 def hbm_bound_launch(ops, rec, stream, peaks, reps=20):
-    cand = [kw for kw in rec if kw.get("mode", 0) != 1 and kw.get("ntaps", 1) == 1 and kw["k"] <= 128 and kw["m"] >= 4096]
+    cand = [kw for kw in rec if "group" not in kw and kw.get("mode", 0) != 1 and kw.get("ntaps", 1) == 1 and kw["k"] <= 128 and kw["m"] >= 4096]
     if not cand:
         return None
     kw = max(cand, key=gemm_algorithmic_bytes)
@@ -275,6 +275,7 @@ def run_b200(args):
     ops.set_mn3d(args.mn3d)
     ops.set_occ2(args.occ2, args.occ2_gflop)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
+    ops.group_wgrad = int(args.group_wgrad)
     host = make_host_batch(args, rank)
     B, n_clips, T, n_ex = args.batch, args.n_clips, args.n_frm, args.n_ex
     dbuf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
@@ -476,14 +477,19 @@ def run_b200(args):
         n_gemm = len(rec)
         gs = torch.cuda.Stream()
         gs.wait_stream(torch.cuda.current_stream())
+        def replay(kw):
+            if "group" in kw:
+                ops.gemm_wgrad_group(kw["group"])
+            else:
+                ops.gemm(**kw)
         with torch.cuda.stream(gs):
             for kw in rec:
-                ops.gemm(**kw)
+                replay(kw)
         torch.cuda.synchronize()
         gg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gg, stream=gs):
             for kw in rec:
-                ops.gemm(**kw)
+                replay(kw)
         torch.cuda.synchronize()
         gg.replay()
         torch.cuda.synchronize()
@@ -581,7 +587,7 @@ def run_b200(args):
                    config=dict(workload=workload_name(args), name=args.config,
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), group_wgrad=int(args.group_wgrad), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
                                fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
@@ -714,6 +720,7 @@ def main():
     ap.add_argument("--sm_limit", type=int, default=0, help="cap the persistent GEMM grid (0 = all SMs); leaves SMs to the overlapped NCCL kernels")
     ap.add_argument("--nccl_ctas", type=int, default=0, help="N>1: NCCL_MAX_CTAS for the process group (0 = NCCL default)")
     ap.add_argument("--mn3d", type=int, default=1, help="dgrad / wgrad GEMMs: MN-major operands as one 3-D TMA box per k-chunk (default) or BN/64 2-D boxes")
+    ap.add_argument("--group_wgrad", type=int, default=3, help="grouped weight-gradient launches (cb_gemm_wgrad_group): 0 none, 1 BertLayer + bottleneck block, 2 blocks only, 3 BertLayer only (default: measured best), 4 BertLayer as two pairs + blocks")
     ap.add_argument("--occ2", type=int, default=1, help="two GEMM CTAs per SM: 0 never, 1 only launches the tuning table marks, 2 every eligible launch up to --occ2_gflop")
     ap.add_argument("--occ2_gflop", type=float, default=0.0, help="with --occ2 2: largest launch (GFLOP) that runs two CTAs per SM (0 = no limit)")
     ap.add_argument("--cpu_batch", type=int, default=4)

@@ -60,6 +60,8 @@ def lib():
     L.cb_launch_count.restype = ctypes.c_int64
     L.cb_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
     L.cb_gemm.restype = ctypes.c_int
+    L.cb_gemm_wgrad_group.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_int, ctypes.c_void_p]
+    L.cb_gemm_wgrad_group.restype = ctypes.c_int
     _lib = L
     return L
 

@@ -1067,6 +1067,279 @@ static LaunchCfg choose_config(const cb_gemm_desc& d, bool tma_epi, int occ = 1)
   return best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grouped weight gradients: ONE persistent launch walks the tiles of several independent dW = dY^T X problems (the four
+// Linear layers of a BertLayer, the three / four convs of a bottleneck block). The problems of a group share the reduction
+// length (tokens / pixels), so their tiles cost the same and the static round-robin schedule stays balanced; what the group buys
+// is one prologue + one tail instead of four, tiles of all problems filling the SMs together, and - because four problems
+// together have enough tiles - no K-split, i.e. half the fp32 red.global traffic of the single launches
+// (profiles/r02i_gemm_autotune_report.txt: 56 us per BertLayer as four launches). Same warp roles, ring, TMEM double buffer
+// and staged red.add epilogue as gemm_kernel<BN, MODE 1, EPI 0>; the problem descriptors (tensor maps included) travel in the
+// kernel's parameter space.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_MAX_PROBLEMS = 8;
+struct WgradProblem {
+  CUtensorMap tmA, tmB;       // dY [P, M] and X [P, N] as MN-major operands: 2-D {64, BK} boxes or the 3-D {64, BK, cols / 64} view
+  float* out;                 // fp32 [M, ntaps * N] (+= accumulation)
+  const float* scale;         // optional per-output-row scale (FrozenBN fold), or nullptr
+  int64_t out_ld;
+  int M, N, K;                // output rows (= dY columns), output columns per tap, reduction length P
+  int ntaps, tap_w, tap_sign;
+  int iters_per_split, tiles_m, tiles_n;
+  int tile_begin;             // first tile of this problem in the group's tile list
+  int mn3d;
+};
+struct WgradGroup {
+  int nprob, total_tiles;
+  WgradProblem p[WG_MAX_PROBLEMS];
+};
+struct WgTile {
+  int pi, m0, n0, tap, it_begin, n_iters;
+};
+__device__ __forceinline__ WgTile wg_decode(const WgradGroup& g, int tile) {
+  WgTile t;
+  int pi = 0;
+  while (pi + 1 < g.nprob && tile >= g.p[pi + 1].tile_begin) ++pi;
+  const WgradProblem& P = g.p[pi];
+  int r = tile - P.tile_begin;
+  const int nt = r % P.tiles_n;
+  r /= P.tiles_n;
+  const int mt = r % P.tiles_m;
+  r /= P.tiles_m;
+  t.pi = pi;
+  t.m0 = mt * BM;
+  t.tap = r % P.ntaps;
+  const int split = r / P.ntaps;
+  const int kc = (P.K + BK - 1) / BK;
+  t.it_begin = split * P.iters_per_split;
+  t.n_iters = min(kc, t.it_begin + P.iters_per_split) - t.it_begin;
+  t.n0 = nt;      // (tile column index; multiplied by BN by the caller, which knows BN)
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(gemm_threads(8), 1)
+    wgrad_group_kernel(const __grid_constant__ WgradGroup g, int STAGES, int KCH, int epi_bytes) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int EPI_WARPS = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = KCH * Cfg::STAGE_BYTES;
+  uint8_t* stg_base = smem + STAGES * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + epi_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x, n_units = gridDim.x;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.nprob; ++i) {
+      tma_prefetch_desc(&g.p[i].tmA);
+      tma_prefetch_desc(&g.p[i].tmB);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = unit; tile < g.total_tiles; tile += n_units) {
+        const WgTile t = wg_decode(g, tile);
+        const WgradProblem& P = g.p[t.pi];
+        const int n0 = t.n0 * BN;
+        int shift = 0;
+        if (P.ntaps == 9) shift = P.tap_sign * ((t.tap / 3 - 1) * P.tap_w + (t.tap % 3 - 1));
+        for (int i = 0; i < t.n_iters; i += KCH) {
+          const int nch = min(KCH, t.n_iters - i);
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], nch * Cfg::STAGE_BYTES);
+          int kit = t.it_begin + i;
+          for (int ch = 0; ch < nch; ++ch, ++kit) {
+            uint8_t* sa = smem + s * stage_bytes + ch * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            const int p = kit * BK;
+            if (P.mn3d) {
+              tma_load_3d(sa, &P.tmA, &full_bar[s], 0, p, t.m0 >> 6);
+              tma_load_3d(sb, &P.tmB, &full_bar[s], 0, p + shift, n0 >> 6);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &P.tmA, &full_bar[s], t.m0 + j * 64, p);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &P.tmB, &full_bar[s], n0 + j * 64, p + shift);
+            }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = unit; tile < g.total_tiles; tile += n_units, ++local) {
+        const WgTile t = wg_decode(g, tile);
+        const int acc = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i = 0; i < t.n_iters; i += KCH) {
+          const int nch = min(KCH, t.n_iters - i);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes + ch * Cfg::STAGE_BYTES);
+            const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
+              const uint64_t bd = umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (i > 0 || ch > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> smem staging -> coalesced fp32 red.global.add =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int grp = ew >> 2;
+    uint8_t* stg = stg_base + ew * STG_BYTES;
+    uint8_t* my_row = stg + lane * STG_ROW;
+    const int srow = lane >> 3, sseg = lane & 7;
+    int local = 0;
+    for (int tile = unit; tile < g.total_tiles; tile += n_units, ++local) {
+      const WgTile t = wg_decode(g, tile);
+      const WgradProblem& P = g.p[t.pi];
+      const int n0 = t.n0 * BN;
+      const int acc = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      const int m = t.m0 + q * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const float rs = (m < P.M && P.scale) ? P.scale[m] : 1.0f;
+      float* obase = P.out + static_cast<int64_t>(t.tap) * P.N;
+      constexpr int NCH = BN / 32;
+      bool released = false;
+#pragma unroll 1
+      for (int cc = grp; cc < NCH; cc += 2) {
+        const int c = cc * 32;
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        if (cc + 2 >= NCH) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          released = true;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(my_row + j * 4) = make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
+                                                                    __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = j * 4 + srow;
+          const int mm = t.m0 + q * 32 + r;
+          const int n = n0 + c + sseg * 4;
+          if (mm < P.M && n + 4 <= P.N)
+            red_add_f32x4(obase + static_cast<int64_t>(mm) * P.out_ld + n, *reinterpret_cast<const float4*>(stg + r * STG_ROW + sseg * 16));
+        }
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_wgrad_group(const cb_gemm_desc* descs, int n, int splits, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = wgrad_group_kernel<BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", SMEM_LIMIT, cudaGetErrorString(e));
+      return CB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  alignas(64) WgradGroup g;
+  g.nprob = n;
+  int total = 0, max_iters = 0;
+  for (int i = 0; i < n; ++i) {
+    const cb_gemm_desc& d = descs[i];
+    WgradProblem& P = g.p[i];
+    const bool mn3d = g_mn3d && d.m % 64 == 0 && d.n % 64 == 0 && get_tmap_3d_mn(&P.tmA, d.a, d.m, d.a_rows, d.a_ld, BK, BM / 64) &&
+                      get_tmap_3d_mn(&P.tmB, d.b, d.n, d.b_rows, d.b_ld, BK, BN / 64);
+    if (!mn3d && !(get_tmap_2d(&P.tmA, d.a, d.m, d.a_rows, d.a_ld, 64, BK) && get_tmap_2d(&P.tmB, d.b, d.n, d.b_rows, d.b_ld, 64, BK)))
+      return CB_ERR_CUDA;
+    P.mn3d = mn3d ? 1 : 0;
+    P.out = static_cast<float*>(d.out);
+    P.scale = d.scale;
+    P.out_ld = d.out_ld;
+    P.M = d.m; P.N = d.n; P.K = d.k;
+    P.ntaps = d.ntaps; P.tap_w = d.tap_w; P.tap_sign = d.tap_sign;
+    const int kc = ceil_div(d.k, BK);
+    int sp = splits < 1 ? 1 : (splits > kc ? kc : splits);
+    P.iters_per_split = ceil_div(kc, sp);
+    sp = ceil_div(kc, P.iters_per_split);
+    P.tiles_m = ceil_div(d.m, BM);
+    P.tiles_n = ceil_div(d.n, BN);
+    P.tile_begin = total;
+    total += P.tiles_m * P.tiles_n * d.ntaps * sp;
+    if (P.iters_per_split > max_iters) max_iters = P.iters_per_split;
+  }
+  g.total_tiles = total;
+  const SmemPlan sp = plan_smem(BN, false, false, false, max_iters, 0, 1);
+  if (sp.stages < 2) {
+    set_error("cb_gemm_wgrad_group: not enough shared memory for a 2-stage pipeline (BN=%d)", BN);
+    return CB_ERR_INVALID;
+  }
+  const int smem_bytes = sp.stages * sp.kch * Cfg::STAGE_BYTES + sp.epi_bytes + Cfg::BAR_BYTES + 1024;
+  const int units = sm_count();
+  launch_k(kern, total < units ? total : units, gemm_threads(8), smem_bytes, stream, g, sp.stages, sp.kch, sp.epi_bytes);
+  return check_launch("cb_gemm_wgrad_group");
+}
+
 }  // namespace cb
 
 /* bring-up / tuning hook (not part of the public header): device buffer of >= 16 x grid int64 receiving clock64() stamps of every CTA */
@@ -1182,4 +1455,52 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream_v) {
     }
   }
   return CB_ERR_INVALID;
+}
+
+/* Several independent weight-gradient problems (CB_GEMM_WGRAD descriptors with the same reduction length) in ONE persistent launch. */
+extern "C" int cb_gemm_wgrad_group(const cb_gemm_desc* descs, int n, void* stream_v) {
+  using namespace cb;
+  CB_REQUIRE(descs != nullptr && n >= 1, "cb_gemm_wgrad_group: no problems");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  bool groupable = n >= 2 && n <= WG_MAX_PROBLEMS;
+  for (int i = 0; i < n; ++i) {
+    const cb_gemm_desc& d = descs[i];
+    CB_REQUIRE(d.mode == CB_GEMM_WGRAD && d.out_fp32 == 1, "cb_gemm_wgrad_group: problem %d is not an fp32 WGRAD descriptor", i);
+    CB_REQUIRE(d.a && d.b && d.out && d.m > 0 && d.n > 0 && d.k > 0, "cb_gemm_wgrad_group: problem %d: null operand / empty shape", i);
+    CB_REQUIRE(d.m % 8 == 0 && d.n % 8 == 0 && d.out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0,
+               "cb_gemm_wgrad_group: problem %d: m, n multiples of 8, out 16-byte aligned, out_ld a multiple of 4", i);
+    CB_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "cb_gemm_wgrad_group: problem %d: ntaps must be 1 or 9", i);
+    // one schedule for all: reduction lengths within 2 x of each other, otherwise the round-robin tiles are unbalanced
+    if (d.k * 2 < descs[0].k || descs[0].k * 2 < d.k) groupable = false;
+  }
+  if (!groupable) {      // a single problem, too many, or very different reduction lengths: the ordinary launches
+    for (int i = 0; i < n; ++i) {
+      const int rc = cb_gemm(&descs[i], stream_v);
+      if (rc != CB_OK) return rc;
+    }
+    return CB_OK;
+  }
+  // tile width: the widest that does not mostly pad; K-split: fewest fp32 red.add passes that fill the SMs (one split if the group
+  // already has >= 1 wave of tiles)
+  int min_n = descs[0].n;
+  for (int i = 1; i < n; ++i) min_n = descs[i].n < min_n ? descs[i].n : min_n;
+  const int bn = min_n >= 192 ? 256 : (min_n >= 96 ? 128 : 64);
+  int64_t base = 0;
+  int kc_min = 1 << 30;
+  for (int i = 0; i < n; ++i) {
+    base += static_cast<int64_t>(ceil_div(descs[i].m, BM)) * ceil_div(descs[i].n, bn) * descs[i].ntaps;
+    const int kc = ceil_div(descs[i].k, BK);
+    kc_min = kc < kc_min ? kc : kc_min;
+  }
+  const int sms = sm_count();
+  int best_split = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= 8 && sp <= kc_min; ++sp) {
+    const double waves = static_cast<double>((base * sp + sms - 1) / sms);
+    const double cost = waves / sp + 0.06 * sp;      // main-loop time ~ waves / split; every split adds a red.add pass over the output
+    if (cost < best_cost) { best_cost = cost; best_split = sp; }
+  }
+  if (bn == 256) return launch_wgrad_group<256>(descs, n, best_split, stream);
+  if (bn == 128) return launch_wgrad_group<128>(descs, n, best_split, stream);
+  return launch_wgrad_group<64>(descs, n, best_split, stream);
 }

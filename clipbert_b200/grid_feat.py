@@ -464,11 +464,14 @@ class GridFeatBackbone(nn.Module):
         return grid, stash
 
     # ---- backward ---------------------------------------------------------------------------------
-    def _wgrad(self, m, dy, x, p, ntaps=1, tap_w=0):
+    def _wgrad_kw(self, m, dy, x, p, ntaps=1, tap_w=0):
         """dW[cout, t*cin + c] += scale[cout] * sum_p dy[p, cout] * x[p + shift_t, c]."""
-        ops.gemm(mode=ops.CB_GEMM_WGRAD, m=m.cout, n=m.cin, k=p, a=dy, a_rows=p, a_ld=m.cout, b=x, b_rows=p, b_ld=m.cin,
-                 ntaps=ntaps, tap_w=tap_w, tap_sign=1, split_k=ops.wgrad_split(m.cout, m.cin, p, ntaps), scale=m._scale,
-                 out=m._gw, out_ld=ntaps * m.cin, out_fp32=1)
+        return dict(mode=ops.CB_GEMM_WGRAD, m=m.cout, n=m.cin, k=p, a=dy, a_rows=p, a_ld=m.cout, b=x, b_rows=p, b_ld=m.cin,
+                    ntaps=ntaps, tap_w=tap_w, tap_sign=1, split_k=ops.wgrad_split(m.cout, m.cin, p, ntaps), scale=m._scale,
+                    out=m._gw, out_ld=ntaps * m.cin, out_fp32=1)
+
+    def _wgrad(self, m, dy, x, p, ntaps=1, tap_w=0):
+        ops.gemm(**self._wgrad_kw(m, dy, x, p, ntaps, tap_w))
 
     def _dgrad1x1(self, m, dy, rows, residual=None, aux=None, rowmap=ops.ROWMAP_NONE, hw=None, out=None):
         """dx[rows, cin] = dy[rows, cout] @ w'[cout, cin]  (+residual) (* relu mask of aux)."""
@@ -522,14 +525,21 @@ class GridFeatBackbone(nn.Module):
             blk, hh, ww = st["blk"], st["h"], st["w"]
             rows = n * hh * ww
             pp = n * (hh + 2) * (ww + 2)
-            sq.run(lambda: self._wgrad(blk.conv3, g, st["b"], rows), g, st["b"])
+            # the block's three / four weight gradients as ONE grouped launch on the side queue, issued when its last dY (da) exists
+            wg = [self._wgrad_kw(blk.conv3, g, st["b"], rows)]
             db_pad = self._pad_get(pp, blk.mid, dev)
             recycle += [db_pad, st["a_pad"]]
             self._dgrad1x1(blk.conv3, g, rows, aux=st["b"], rowmap=ops.ROWMAP_PAD, hw=(hh, ww), out=db_pad)
-            sq.run(lambda: self._wgrad(blk.conv2, db_pad, st["a_pad"], pp, ntaps=9, tap_w=ww + 2), db_pad, st["a_pad"])
+            wg.append(self._wgrad_kw(blk.conv2, db_pad, st["a_pad"], pp, ntaps=9, tap_w=ww + 2))
             da = self._dgrad3x3(blk.conv2, db_pad, n, hh, ww, st["a_pad"])
+            wg.append(self._wgrad_kw(blk.conv1, da, st["xs"], rows))
             if blk.has_shortcut:
-                sq.run(lambda: (self._wgrad(blk.conv1, da, st["xs"], rows), self._wgrad(blk.shortcut, g, st["xs"], rows)), da, g, st["xs"])
+                wg.append(self._wgrad_kw(blk.shortcut, g, st["xs"], rows))
+            if ops.group_wgrad in (1, 2, 4):
+                sq.run(lambda: ops.gemm_wgrad_group(wg), g, st["b"], db_pad, st["a_pad"], da, st["xs"])
+            else:
+                sq.run(lambda: [ops.gemm(**kw) for kw in wg], g, st["b"], db_pad, st["a_pad"], da, st["xs"])
+            if blk.has_shortcut:
                 if last and self._bucket_hook is not None and st["name"] == "res5.0":
                     # every weight gradient of res5 + grid_encoder (78 % of the CNN's trainable parameters, the tail of the
                     # flat buffer) has been enqueued: its exchange can overlap the res4 / res3 backward
@@ -544,7 +554,6 @@ class GridFeatBackbone(nn.Module):
                 else:
                     ops.relu_mask(dxs, st["x_in"], g)
             else:
-                sq.run(lambda: self._wgrad(blk.conv1, da, st["xs"], rows), da, st["xs"])
                 if st["first_trainable"]:
                     break
                 g = self._dgrad1x1(blk.conv1, da, rows, residual=g, aux=st["x_in"])

@@ -497,9 +497,12 @@ class _ClipBertHeadModel(nn.Module):
         return self._mlp_head_forward(pooled, st, nseq, p_h, seed, self._num_head_outputs())
 
     # ---- backward ---------------------------------------------------------------------------------
+    def _wgrad_kw(self, li, dy, x, rows, x_ld=None):
+        return dict(mode=ops.CB_GEMM_WGRAD, m=li.n, n=li.k, k=rows, a=dy, a_rows=rows, a_ld=li.n, b=x, b_rows=rows,
+                    b_ld=li.k if x_ld is None else x_ld, split_k=ops.wgrad_split(li.n, li.k, rows), out=li.gw, out_ld=li.k, out_fp32=1)
+
     def _wgrad(self, li, dy, x, rows, x_ld=None):
-        ops.gemm(mode=ops.CB_GEMM_WGRAD, m=li.n, n=li.k, k=rows, a=dy, a_rows=rows, a_ld=li.n, b=x, b_rows=rows,
-                 b_ld=li.k if x_ld is None else x_ld, split_k=ops.wgrad_split(li.n, li.k, rows), out=li.gw, out_ld=li.k, out_fp32=1)
+        ops.gemm(**self._wgrad_kw(li, dy, x, rows, x_ld))
 
     def _dgrad(self, li, dy, rows, out, **kw):
         ops.gemm(mode=ops.CB_GEMM_NN, m=rows, n=li.k, k=li.n, a=dy, a_rows=rows, a_ld=li.n, b=li.w, b_rows=li.n, b_ld=li.k,
@@ -571,10 +574,22 @@ class _ClipBertHeadModel(nn.Module):
             ds2d = new(M, H) if p_h > 0 else None
             ops.layernorm_bwd(dx, ly["s2"], ly["st2"], g2, ds2, ds2d, dg2, db2, out_l.gb, p_h, ls + 3)
             dd = ds2d if ds2d is not None else ds2
-            sq.run(lambda: self._wgrad(out_l, dd, ly["gel"], M), dd, ly["gel"])
+            gmode = ops.group_wgrad      # the layer's four weight gradients as ONE launch (issued when the last dY, dqkv, exists) or two pairs
+            group = gmode in (1, 3, 4)
+            pairs = gmode == 4
+            wg = [self._wgrad_kw(out_l, dd, ly["gel"], M)]
+            if not group:
+                sq.run(lambda: ops.gemm(**wg[0]), dd, ly["gel"])
             du = new(M, in_l.n)
             self._dgrad(out_l, dd, M, du, aux=ly["u"], aux_ld=in_l.n, aux_mode=ops.AUX_MUL)
-            sq.run(lambda: (self._wgrad(in_l, du, ly["a"], M), ops.colsum(du, in_l.gb, M, in_l.n)), du, ly["a"])
+            wg.append(self._wgrad_kw(in_l, du, ly["a"], M))
+            if pairs:
+                wg_ffn, wg = wg, []
+                sq.run(lambda: (ops.gemm_wgrad_group(wg_ffn), ops.colsum(du, in_l.gb, M, in_l.n)), dd, ly["gel"], du, ly["a"])
+            elif group:
+                sq.run(lambda: ops.colsum(du, in_l.gb, M, in_l.n), du)
+            else:
+                sq.run(lambda: (ops.gemm(**wg[1]), ops.colsum(du, in_l.gb, M, in_l.n)), du, ly["a"])
             da = new(M, H)
             self._dgrad(in_l, du, M, da, residual=ds2, res_ld=H)
             # a = LN1(s1), s1 = dropout(ctx @ Wao^T + b) + x
@@ -582,12 +597,18 @@ class _ClipBertHeadModel(nn.Module):
             ds1d = new(M, H) if p_h > 0 else None
             ops.layernorm_bwd(da, ly["s1"], ly["st1"], g1, ds1, ds1d, dg1, db1, ao_l.gb, p_h, ls + 2)
             dd1 = ds1d if ds1d is not None else ds1
-            sq.run(lambda: self._wgrad(ao_l, dd1, ly["ctx"], M), dd1, ly["ctx"])
+            wg.append(self._wgrad_kw(ao_l, dd1, ly["ctx"], M))
+            if not group:
+                sq.run(lambda: ops.gemm(**wg[2]), dd1, ly["ctx"])
             dctx = new(M, H)
             self._dgrad(ao_l, dd1, M, dctx)
             dqkv = new(M, 3 * H)
             ops.attention_bwd(ly["qkv"], st["mask"], ly["ctx"], dctx, ly["lse"], dqkv, nseq, L, lt, heads, p_a, ls + 1)
-            sq.run(lambda: (self._wgrad(qkv_l, dqkv, ly["x"], M), ops.colsum(dqkv, qkv_l.gb, M, 3 * H)), dqkv, ly["x"])
+            wg.append(self._wgrad_kw(qkv_l, dqkv, ly["x"], M))
+            if group:
+                sq.run(lambda: (ops.gemm_wgrad_group(wg), ops.colsum(dqkv, qkv_l.gb, M, 3 * H)), dd, ly["gel"], du, ly["a"], dd1, ly["ctx"], dqkv, ly["x"])
+            else:
+                sq.run(lambda: (ops.gemm(**wg[3]), ops.colsum(dqkv, qkv_l.gb, M, 3 * H)), dqkv, ly["x"])
             dxn = new(M, H)
             self._dgrad(qkv_l, dqkv, M, dxn, residual=ds1, res_ld=H)
             dx = dxn

@@ -267,6 +267,46 @@ def gemm(**kw):
                 d.mode, d.m, d.n, d.k, d.ntaps, bool(d.residual), bool(d.aux), bool(d.out2), d.out_fp32, d.rowmap), e0, e1))
 
 
+# module switch (bench --group_wgrad): which weight-gradient GEMMs go out as grouped launches. 0 none; 1 BertLayer (4 in one) +
+# bottleneck block; 2 bottleneck blocks only; 3 BertLayer only; 4 BertLayer as two pairs (FFN pair as soon as du exists, attention
+# pair after dqkv) + bottleneck blocks
+group_wgrad = 3
+
+
+def gemm_wgrad_group(kws):
+    """cb_gemm_wgrad_group: the CB_GEMM_WGRAD problems ``kws`` (keyword dicts as for ``gemm``) in one persistent launch."""
+    if not kws:
+        return
+    if len(kws) == 1:
+        for kw in kws:
+            gemm(**kw)
+        return
+    if _gemm_record is not None:
+        _gemm_record.append(dict(group=[dict(kw) for kw in kws]))
+    arr = (L.GemmDesc * len(kws))()
+    for d, kw in zip(arr, kws):
+        d.ntaps = 1
+        d.tap_sign = 1
+        d.split_k = 0
+        for k, v in kw.items():
+            if k in _GEMM_PTR_FIELDS:
+                v = _p(v) if isinstance(v, torch.Tensor) else v
+            setattr(d, k, v)
+    timing = _gemm_timing is not None or _op_timing is not None
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = L.lib().cb_gemm_wgrad_group(arr, len(kws), _s())
+    if rc != 0:
+        raise RuntimeError("cb_gemm_wgrad_group failed (%d): %s" % (rc, L.lib().cb_last_error().decode()))
+    if timing:
+        e1.record()
+        if _gemm_timing is not None:
+            _gemm_timing.append((e0, e1))
+        if _op_timing is not None:
+            _op_timing.append(("gemm wgrad group x%d" % len(kws), e0, e1))
+
+
 def wgrad_split(m, n, k, ntaps=1, block_n=128):
     """0 = the library's launch-configuration model picks tile width, CTA pairing and the K-split."""
     return 0

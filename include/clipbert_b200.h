@@ -143,6 +143,11 @@ typedef struct cb_gemm_desc {
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
+/* n independent CB_GEMM_WGRAD problems in ONE persistent launch: the weight gradients of the four Linear layers of a BertLayer
+ * (autograd of transformers.py:238-301,363-381) or of the convs of one bottleneck block. The problems should share their
+ * reduction length k (tokens / pixels); 1 <= n <= 8. One prologue and tail instead of n, no K-split when the group fills the SMs.
+ * Falls back to n cb_gemm launches for n == 1, n > 8 or very different k. Epilogue fields other than scale / out are ignored. */
+int cb_gemm_wgrad_group(const cb_gemm_desc* descs, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm over rows of a bf16 [m, 768] matrix (fp32 statistics, warp-shuffle reductions).

@@ -433,6 +433,13 @@ def cross_entropy_bwd(logits, labels, lse, grad_loss, dlogits, ignore_index=-100
     dlogits.copy_(((p - onehot) * (grad_loss.double() * ok.double())[:, None]).float())
 
 
+def gemm_wgrad_group(kws):
+    """cb_gemm_wgrad_group: n independent weight-gradient problems; the result is that of n cb_gemm launches."""
+    from clipbert_b200 import ops as _ops
+    for kw in kws:
+        _ops.gemm(**kw)          # (the counted / recorded wrapper while the emulator is installed)
+
+
 def cast_bf16_f32(src, dst):
     dst.copy_(src.float())
 
@@ -456,7 +463,7 @@ _NAMES = ("gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_tex
           "attention_fwd", "attention_bwd", "colsum", "dropout", "gelu_bwd", "pad_cast", "cast_scale", "stem_im2col", "stem_s2d",
           "maxpool3x3s2", "subsample2", "unsubsample2_mask", "maxpool2x2_relu_fwd", "maxpool2x2_relu_bwd", "relu_mask",
           "cast_scale_segments", "clip_lse_loss", "nvls_allreduce", "dropout_offset_bind", "dropout_offset_advance", "cast_bf16_f32",
-          "clip_pool_ce_loss", "cross_entropy_fwd", "cross_entropy_bwd", "resize_pad")
+          "clip_pool_ce_loss", "cross_entropy_fwd", "cross_entropy_bwd", "resize_pad", "gemm_wgrad_group")
 
 
 @contextlib.contextmanager

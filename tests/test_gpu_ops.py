@@ -583,3 +583,58 @@ def test_pool_and_subsample_ops(cuda):
     ops.maxpool2x2_relu_bwd(dy, xg, dxp, N, H, W, C)
     assert torch.equal(dxp[:, 1:-1, 1:-1].float(), xr.grad.permute(0, 2, 3, 1))
     assert float(dxp.float().abs().sum() - dxp[:, 1:-1, 1:-1].float().abs().sum()) == 0.0
+
+
+def test_grouped_wgrad_launch(cuda):
+    """cb_gemm_wgrad_group: several independent dW = dY^T X problems in ONE persistent launch (the four Linear layers of a
+    BertLayer; the 1x1 / 3x3 / 1x1 (+ shortcut) convs of a bottleneck block with its 9-tap conv and FrozenBN row scales) against
+    fp32 torch and against the single launches; accumulation semantics (a second launch adds); the fall-backs (one problem,
+    very different reduction lengths) give the same numbers."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+
+    def lin(P, Mo, No, scale=False):
+        dY, X = _rnd(g, P, Mo), _rnd(g, P, No)
+        rs = (torch.rand(Mo, generator=g) + 0.5).to(cuda) if scale else None
+        dW = torch.zeros(Mo, No, device=cuda)
+        kw = dict(mode=ops.CB_GEMM_WGRAD, m=Mo, n=No, k=P, a=dY, a_rows=P, a_ld=Mo, b=X, b_rows=P, b_ld=No, out=dW, out_ld=No, out_fp32=1)
+        if scale:
+            kw["scale"] = rs
+        ref = dY.float().t() @ X.float()
+        return kw, dW, (ref * rs[:, None] if scale else ref)
+
+    def conv3x3(NB, H, W, Cin, Cout):
+        x, dy = _rnd(g, NB, H, W, Cin), _rnd(g, NB, H, W, Cout)
+        xp = torch.zeros(NB, H + 2, W + 2, Cin, device=cuda, dtype=torch.bfloat16)
+        dyp = torch.zeros(NB, H + 2, W + 2, Cout, device=cuda, dtype=torch.bfloat16)
+        xp[:, 1:-1, 1:-1], dyp[:, 1:-1, 1:-1] = x, dy
+        P = NB * (H + 2) * (W + 2)
+        dW = torch.zeros(Cout, 9 * Cin, device=cuda)
+        kw = dict(mode=ops.CB_GEMM_WGRAD, m=Cout, n=Cin, k=P, a=dyp, a_rows=P, a_ld=Cout, b=xp, b_rows=P, b_ld=Cin, ntaps=9, tap_w=W + 2, tap_sign=1,
+                  out=dW, out_ld=9 * Cin, out_fp32=1)
+        wz = torch.zeros(Cout, Cin, 3, 3, device=cuda, requires_grad=True)
+        F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        return kw, dW, wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)
+
+    groups = {
+        "bert layer": [lin(2624, 768, 3072), lin(2624, 3072, 768), lin(2624, 2304, 768), lin(2624, 768, 768)],
+        "bottleneck block": [lin(4 * 14 * 14, 1024, 256, True), conv3x3(4, 14, 14, 256, 256), lin(4 * 14 * 14, 256, 1024, True), lin(4 * 14 * 14, 1024, 512, True)],
+        "narrow + ragged": [lin(1000, 136, 72), lin(1100, 64, 264)],
+        "single problem": [lin(640, 128, 128)],
+        "different reduction lengths": [lin(5000, 256, 256), lin(640, 128, 128)],
+    }
+    for name, probs in groups.items():
+        kws = [p[0] for p in probs]
+        ops.gemm_wgrad_group(kws)
+        for kw, dW, ref in probs:
+            assert relerr(dW, ref) < TOL_FP32_OP, (name, kw["m"], kw["n"], relerr(dW, ref))
+        ops.gemm_wgrad_group(kws)                                           # += semantics
+        for kw, dW, ref in probs:
+            assert relerr(dW, 2 * ref) < TOL_FP32_OP, (name, "second launch")
+        singles = []
+        for kw, dW, ref in probs:
+            d1 = torch.zeros_like(dW)
+            ops.gemm(**dict(kw, out=d1))
+            singles.append(d1)
+        for (kw, dW, ref), d1 in zip(probs, singles):
+            assert relerr(dW, 2 * d1) < TOL_FP32_OP, (name, "vs single launches")

@@ -146,6 +146,7 @@ def main():
     rec = record_step(args)
     uniq = {}
     counts = {}
+    rec = [m for kw in rec for m in (kw["group"] if "group" in kw else [kw])]      # grouped wgrads: tune / list their members
     for kw in rec:
         key = ops.gemm_key(kw)
         uniq.setdefault(key, kw)

@@ -28,6 +28,7 @@ def main():
     dev = torch.device("cuda:0")
     rec = AT.record_step(args)
     uniq = {}
+    rec = [m for kw in rec for m in (kw["group"] if "group" in kw else [kw])]
     for kw in rec:
         uniq.setdefault(ops.gemm_key(kw), kw)
     del rec

@@ -55,7 +55,7 @@ def main():
                 mb = dict(visual_inputs=vis[:, c], text_input_ids=d["text_input_ids"], text_input_mask=d["text_input_mask"],
                           labels=d["labels"], n_examples_list=[n_ex] * B)
                 logits.append(model(mb)["logits"])
-        bench.lse_loss(logits, d["labels"]).backward()
+        cb.clip_lse_loss(logits, d["labels"]).backward()          # the fused clip-LSE loss, as bench.py runs it
 
     for _ in range(3):
         step()
