@@ -135,8 +135,8 @@ def gemm_algorithmic_bytes(kw):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-# (profiles/r01c_ncu_full_gemm_summary.txt, first row), keyed by the launch's shape
-NCU_TRAFFIC_BYTES = {(401408, 256, 64, 1, True): 257.014272e6 + 165.274624e6}
+# (profiles/r02z_ncu_full_gemm_summary.txt, profiled launch 4: the committed round-2 kernel), keyed by the launch's shape
+NCU_TRAFFIC_BYTES = {(401408, 256, 64, 1, True): 257.406208e6 + 162.649600e6}
 
 
 def hbm_bound_launch(ops, rec, stream, peaks, reps=20):
@@ -161,7 +161,7 @@ def hbm_bound_launch(ops, rec, stream, peaks, reps=20):
                     " + shortcut" if kw.get("residual") is not None else "", kw["m"], kw["n"], kw["k"]),
                 achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
                 peak_source="%s hbm_gbs (copy bandwidth)" % peaks["src"], algorithmic_bytes=int(nbytes), us_per_launch=round(us, 2),
-                traffic=NCU_TRAFFIC_BYTES.get(key), traffic_source="profiles/r01c_ncu_full_gemm_summary.txt (ncu --set full, one launch)",
+                traffic=NCU_TRAFFIC_BYTES.get(key), traffic_source="profiles/r02z_ncu_full_gemm_summary.txt (ncu --set full, one launch)",
                 note="%d back-to-back launches of the same problem, CUDA events on the launch stream; working set %.0f MB > 126 MB L2"
                      % (reps, nbytes / 1e6))
 
@@ -262,6 +262,7 @@ def run_b200(args):
     model = model.eval() if args.inference else model.train()
     model.cnn.pixel_mean = IMAGE_MEAN     # uint8 frames in, ImageNorm fused into the stem gather
     model.cnn.stem_mode = args.stem
+    model.zero_grad_in_forward = bool(args.zero_grad_in_forward) and not args.inference
     exchange = args.exchange
     if world > 1:
         if exchange == "auto":       # this library's NVLS all-reduce where the box has a multicast mapping (N = 8: 0.956 of linear against
@@ -274,6 +275,7 @@ def run_b200(args):
         ops.set_sm_limit(args.sm_limit)
     ops.set_mn3d(args.mn3d)
     ops.set_occ2(args.occ2, args.occ2_gflop)
+    ops.set_attention_rows48(args.attn_rows48)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     ops.group_wgrad = int(args.group_wgrad)
     host = make_host_batch(args, rank)
@@ -318,7 +320,8 @@ def run_b200(args):
     captured_launches = 0
 
     def step_device():
-        model.zero_grad()
+        if not model.zero_grad_in_forward:     # else the step clears its gradient buffers itself, beside the transformer forward
+            model.zero_grad()
         if graph is not None:
             graph.replay()
         else:
@@ -587,8 +590,8 @@ def run_b200(args):
                    config=dict(workload=workload_name(args), name=args.config,
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
-                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=bool(args.pdl), mn3d=bool(args.mn3d), group_wgrad=int(args.group_wgrad), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
-                               fused_loss=bool(args.fused_loss), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=int(args.pdl), mn3d=bool(args.mn3d), group_wgrad=int(args.group_wgrad), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
+                               fused_loss=bool(args.fused_loss), zero_grad_in_forward=bool(model.zero_grad_in_forward), attn_rows48=bool(args.attn_rows48), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -708,8 +711,11 @@ def main():
     ap.add_argument("--clip_batching", type=int, default=1, help="1: all clips of a step in one pass (forward_clips); 0: reference per-clip loop")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "im2col"], help="stem conv: space-to-depth implicit GEMM or patch matrix + GEMM")
     ap.add_argument("--overlap_wgrad", type=int, default=1, help="wgrad GEMMs on a side stream beside the dgrad chain")
-    ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels (hurts the wgrad overlap)")
+    ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels: 0 off, 1 all (hurts the wgrad overlap), 2 all but the GEMMs")
     ap.add_argument("--prefetch", type=int, default=1, help="e2e: upload batch i+1 on a copy stream while batch i computes (0: copy on the compute stream)")
+    ap.add_argument("--attn_rows48", type=int, default=1, help="1 (default): attention of sequences up to 48 tokens on the 48-row / three-warp kernels; 0: 64-row kernels")
+    ap.add_argument("--zero_grad_in_forward", type=int, default=1, help="1 (default): the step clears its two flat gradient buffers on a side stream beside "
+                    "the transformer forward (ClipBert.zero_grad_in_forward); 0: a serial model.zero_grad() before every step")
     ap.add_argument("--fused_loss", type=int, default=1, help="1 (default): clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss); 0: ~45 ATen launches")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, this library's NVLS all-reduce (csrc/nvls.cu), or auto = nvls where a multicast mapping exists")

@@ -14,7 +14,7 @@ static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 static int pdl_default() {
   const char* e = getenv("CB_PDL");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0);
 }
 std::atomic<int> g_pdl{pdl_default()};
 static std::atomic<const uint64_t*> g_drop_offset{nullptr};
@@ -167,7 +167,7 @@ const char* cb_last_error(void) { return cb::t_err; }
 int cb_version(void) { return 100; }
 int cb_sm_arch(void) { return 100; }
 int64_t cb_launch_count(void) { return cb::g_launches.load(std::memory_order_relaxed); }
-int cb_set_pdl(int enable) { return cb::g_pdl.exchange(enable ? 1 : 0, std::memory_order_relaxed); }
+int cb_set_pdl(int enable) { return cb::g_pdl.exchange(enable == 2 ? 2 : (enable ? 1 : 0), std::memory_order_relaxed); }
 int cb_dropout_offset_bind(const uint64_t* device_word) {
   cb::g_drop_offset.store(device_word, std::memory_order_relaxed);
   return CB_OK;

@@ -35,17 +35,22 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// global [rows, 64] bf16 (row pitch ld) -> smem tile [64][TC_LD], rows >= nrows zero-filled
+// global [rows, 64] bf16 (row pitch ld) -> smem tile [R][TC_LD], rows >= nrows zero-filled. R = 64, or 48 for the three-warp
+// kernels of sequences up to 48 tokens (blockDim.x = 2 R threads)
+template <int R = 64>
 __device__ __forceinline__ void tc_load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nrows) {
-  for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) {
+#pragma unroll
+  for (int i = threadIdx.x; i < R * 8; i += 2 * R) {
     const int r = i >> 3, c = (i & 7) * 8;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (r < nrows) u = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld + c);
     *reinterpret_cast<uint4*>(dst + r * TC_LD + c) = u;
   }
 }
+template <int R = 64>
 __device__ __forceinline__ void tc_store_tile(const __nv_bfloat16* src, __nv_bfloat16* dst, int64_t ld, int nrows) {
-  for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) {
+#pragma unroll
+  for (int i = threadIdx.x; i < R * 8; i += 2 * R) {
     const int r = i >> 3, c = (i & 7) * 8;
     if (r < nrows) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * ld + c) = *reinterpret_cast<const uint4*>(src + r * TC_LD + c);
   }
@@ -53,9 +58,11 @@ __device__ __forceinline__ void tc_store_tile(const __nv_bfloat16* src, __nv_bfl
 
 // acc[j][4] (j = 8-wide column tile) = A(16 x 64 rows r0.. of As) * B^T where B rows are the OUTPUT columns
 // (B stored [n][k] row-major, e.g. S = Q K^T with Bs = K, or dP = dO V^T with Bs = V)
-__device__ __forceinline__ void tc_mm_abt(float (&acc)[8][4], const __nv_bfloat16* As, const __nv_bfloat16* Bs, int r0, int lane) {
+// NJP = pairs of 8-wide output column tiles = rows of Bs / 16 (4: 64 keys, 3: 48 keys)
+template <int NJP = 4>
+__device__ __forceinline__ void tc_mm_abt(float (&acc)[2 * NJP][4], const __nv_bfloat16* As, const __nv_bfloat16* Bs, int r0, int lane) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 2 * NJP; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 #pragma unroll
@@ -63,7 +70,7 @@ __device__ __forceinline__ void tc_mm_abt(float (&acc)[8][4], const __nv_bfloat1
     uint32_t a[4];
     ldsm_x4(a, As + (r0 + (lane & 15)) * TC_LD + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {     // two 8-column tiles per ldmatrix.x4
+    for (int jp = 0; jp < NJP; ++jp) {     // two 8-column tiles per ldmatrix.x4
       uint32_t b[4];
       ldsm_x4(b, Bs + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * TC_LD + ks * 16 + ((lane >> 3) & 1) * 8);
       mma16816(acc[2 * jp], a, b[0], b[1]);
@@ -72,9 +79,11 @@ __device__ __forceinline__ void tc_mm_abt(float (&acc)[8][4], const __nv_bfloat1
   }
 }
 // acc += A(16 x 64, given as register fragments afrag[ks]) * B where B is stored [k][n] row-major (e.g. O = P V, dQ = dS K)
-__device__ __forceinline__ void tc_mm_ab_reg(float (&acc)[8][4], const uint32_t (&afrag)[4][4], const __nv_bfloat16* Bs, int lane) {
+// NKS = 16-row slabs of Bs contracted over (4: 64 keys, 3: 48 keys)
+template <int NKS = 4>
+__device__ __forceinline__ void tc_mm_ab_reg(float (&acc)[8][4], const uint32_t (&afrag)[NKS][4], const __nv_bfloat16* Bs, int lane) {
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < NKS; ++ks) {
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       uint32_t b[4];
@@ -85,13 +94,14 @@ __device__ __forceinline__ void tc_mm_ab_reg(float (&acc)[8][4], const uint32_t 
   }
 }
 // acc = A^T-stored (As holds [k][m]: out rows m0.. come from As COLUMNS) * B ([k][n] row-major): dV = Pd^T dO, dK = dS^T Q
+template <int NKS = 4>
 __device__ __forceinline__ void tc_mm_atb(float (&acc)[8][4], const __nv_bfloat16* As, const __nv_bfloat16* Bs, int m0, int lane) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < NKS; ++ks) {
     uint32_t a[4];
     const int mi = lane >> 3;
     ldsm_x4_t(a, As + (ks * 16 + (lane & 7) + (mi >> 1) * 8) * TC_LD + m0 + (mi & 1) * 8);
@@ -124,7 +134,10 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+// RT = 16-row tiles per (sequence, head): 4 (L <= 64, 128 threads) or 3 (L <= 48, 96 threads: every 224-px configuration has
+// L = 41 - a quarter fewer warps, 44 % fewer MMAs and smaller tiles than padding to 64)
+template <int RT>
+__global__ void __launch_bounds__(RT * 32) attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                  const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
                                                                  const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
                                                                  int64_t ld_ctx, float* __restrict__ lse, int L, int Lt, int H, float scale,
@@ -134,16 +147,17 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
-  __nv_bfloat16* Ks = Qs + TC_TILE;
-  __nv_bfloat16* Vs = Ks + TC_TILE;
-  float* madd = reinterpret_cast<float*>(Vs + TC_TILE);     // [64] additive key mask (-inf beyond L)
+  constexpr int R = RT * 16, TILE = R * TC_LD;
+  __nv_bfloat16* Ks = Qs + TILE;
+  __nv_bfloat16* Vs = Ks + TILE;
+  float* madd = reinterpret_cast<float*>(Vs + TILE);     // [R] additive key mask (-inf beyond L)
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = static_cast<int64_t>(b) * L;
-  tc_load_tile(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
-  tc_load_tile(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
-  tc_load_tile(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
-  if (threadIdx.x < 64) {
+  tc_load_tile<R>(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile<R>(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile<R>(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
+  if (threadIdx.x < R) {
     const int j = threadIdx.x;
     float m = -INFINITY;
     if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
@@ -151,12 +165,12 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
   }
   __syncthreads();
   const int r0 = warp * 16;
-  float s[8][4];
-  tc_mm_abt(s, Qs, Ks, r0, lane);
+  float s[2 * RT][4];
+  tc_mm_abt<RT>(s, Qs, Ks, r0, lane);
   const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 2 * RT; ++j) {
     const float m0 = madd[j * 8 + cq], m1 = madd[j * 8 + cq + 1];
     s[j][0] = s[j][0] * scale + m0; s[j][1] = s[j][1] * scale + m1;
     s[j][2] = s[j][2] * scale + m0; s[j][3] = s[j][3] * scale + m1;
@@ -166,9 +180,9 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
   mx0 = quad_max(mx0);
   mx1 = quad_max(mx1);
   float sum0 = 0.f, sum1 = 0.f;
-  uint32_t pf[4][4];     // P as A fragments for the P V product
+  uint32_t pf[RT][4];     // P as A fragments for the P V product
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 2 * RT; ++j) {
     float p0 = __expf(s[j][0] - mx0), p1 = __expf(s[j][1] - mx0), p2 = __expf(s[j][2] - mx1), p3 = __expf(s[j][3] - mx1);
     sum0 += p0 + p1;
     sum1 += p2 + p3;
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_kernel(const __nv_bflo
   __syncthreads();                       // everyone is done reading Qs: reuse it to stage the output
   tc_acc_to_smem(o, Qs, r0, lane, 1.0f);
   __syncthreads();
-  tc_store_tile(Qs, ctx + row0 * ld_ctx + h * 64, ld_ctx, L);
+  tc_store_tile<R>(Qs, ctx + row0 * ld_ctx + h * 64, ld_ctx, L);
 }
 
 // ------------------------------------------------------------------------------------------------ forward, any L
@@ -305,7 +319,8 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __n
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+template <int RT>
+__global__ void __launch_bounds__(RT * 32) attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                  const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
                                                                  const int64_t* __restrict__ text_mask, const __nv_bfloat16* __restrict__ ctx,
                                                                  const __nv_bfloat16* __restrict__ dctx, int64_t ld_ctx,
@@ -317,31 +332,34 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
-  __nv_bfloat16* Ks = Qs + TC_TILE;
-  __nv_bfloat16* Vs = Ks + TC_TILE;
-  __nv_bfloat16* dOs = Vs + TC_TILE;
-  __nv_bfloat16* Ps = dOs + TC_TILE;     // dropped probabilities [query][key]
-  __nv_bfloat16* dSs = Ps + TC_TILE;     // dS [query][key]
-  float* madd = reinterpret_cast<float*>(dSs + TC_TILE);
-  float* Dv = madd + 64;                 // D_i = sum_d dO[i][d] O[i][d]
-  float* lses = Dv + 64;
+  constexpr int R = RT * 16, TILE = R * TC_LD;
+  __nv_bfloat16* Ks = Qs + TILE;
+  __nv_bfloat16* Vs = Ks + TILE;
+  __nv_bfloat16* dOs = Vs + TILE;
+  __nv_bfloat16* Ps = Vs;                // dropped probabilities [query][key]: take over the V tile once dP has been formed
+  __nv_bfloat16* dSs = Ks;               // dS [query][key]: takes over the K tile once S and dQ have been formed
+  __nv_bfloat16* dQs = dOs + TILE;       // dQ staged for the coalesced store (its own tile: written while K / V are still being read)
+  float* madd = reinterpret_cast<float*>(dQs + TILE);
+  float* Dv = madd + R;                  // D_i = sum_d dO[i][d] O[i][d]
+  float* lses = Dv + R;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = static_cast<int64_t>(b) * L;
-  tc_load_tile(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
-  tc_load_tile(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
-  tc_load_tile(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
-  tc_load_tile(dOs, dctx + row0 * ld_ctx + h * 64, ld_ctx, L);
-  if (threadIdx.x < 64) {
+  tc_load_tile<R>(Qs, q + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile<R>(Ks, k + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile<R>(Vs, v + row0 * ld_qkv + h * 64, ld_qkv, L);
+  tc_load_tile<R>(dOs, dctx + row0 * ld_ctx + h * 64, ld_ctx, L);
+  if (threadIdx.x < R) {
     const int j = threadIdx.x;
     float m = -INFINITY;
     if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
     madd[j] = m;
     lses[j] = j < L ? lse[(static_cast<int64_t>(b) * H + h) * L + j] : 0.f;
   }
-  // D_i: 8 threads per row, 16 rows per pass
+  // D_i: 8 threads per row, 4 RT rows per pass, 4 passes
+#pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
-    const int r = pass * 16 + (threadIdx.x >> 3), c = (threadIdx.x & 7) * 8;
+    const int r = pass * (4 * RT) + (threadIdx.x >> 3), c = (threadIdx.x & 7) * 8;
     float acc = 0.f;
     if (r < L) {
       const uint4 uo = *reinterpret_cast<const uint4*>(ctx + (row0 + r) * ld_ctx + h * 64 + c);
@@ -362,14 +380,14 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
   // ---- phase 1: this warp's 16 query rows: S, P, dP, dS, dQ ----
   const int r0 = warp * 16;
   const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
-  float s[8][4], dp[8][4];
-  tc_mm_abt(s, Qs, Ks, r0, lane);
-  tc_mm_abt(dp, dOs, Vs, r0, lane);
+  float s[2 * RT][4], dp[2 * RT][4];
+  tc_mm_abt<RT>(s, Qs, Ks, r0, lane);
+  tc_mm_abt<RT>(dp, dOs, Vs, r0, lane);
   const float l0 = lses[rq], l1 = lses[rq + 8], D0 = Dv[rq], D1 = Dv[rq + 8];
   const bool ok0 = rq < L, ok1 = rq + 8 < L;
-  uint32_t dsf[4][4];
+  uint32_t dsf[RT][4], pdf[RT][4];      // dS and the dropped probabilities of this warp's rows, in the accumulator layout
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 2 * RT; ++j) {
     const float m0 = madd[j * 8 + cq], m1 = madd[j * 8 + cq + 1];
     float p0 = ok0 ? __expf(s[j][0] * scale + m0 - l0) : 0.f, p1 = ok0 ? __expf(s[j][1] * scale + m1 - l0) : 0.f;
     float p2 = ok1 ? __expf(s[j][2] * scale + m0 - l1) : 0.f, p3 = ok1 ? __expf(s[j][3] * scale + m1 - l1) : 0.f;
@@ -382,13 +400,10 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
     }
     const float ds0 = p0 * (dp[j][0] * r_0 - D0), ds1 = p1 * (dp[j][1] * r_1 - D0);
     const float ds2 = p2 * (dp[j][2] * r_2 - D1), ds3 = p3 * (dp[j][3] * r_3 - D1);
-    *reinterpret_cast<uint32_t*>(Ps + rq * TC_LD + j * 8 + cq) = pack_bf16x2(p0 * r_0, p1 * r_1);
-    *reinterpret_cast<uint32_t*>(Ps + (rq + 8) * TC_LD + j * 8 + cq) = pack_bf16x2(p2 * r_2, p3 * r_3);
-    const uint32_t d01 = pack_bf16x2(ds0, ds1), d23 = pack_bf16x2(ds2, ds3);
-    *reinterpret_cast<uint32_t*>(dSs + rq * TC_LD + j * 8 + cq) = d01;
-    *reinterpret_cast<uint32_t*>(dSs + (rq + 8) * TC_LD + j * 8 + cq) = d23;
-    dsf[j >> 1][(j & 1) * 2] = d01;
-    dsf[j >> 1][(j & 1) * 2 + 1] = d23;
+    pdf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * r_0, p1 * r_1);
+    pdf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * r_2, p3 * r_3);
+    dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(ds0, ds1);
+    dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds2, ds3);
   }
   float acc[8][4];
 #pragma unroll
@@ -396,39 +411,57 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_bwd_kernel(const __nv_bflo
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
   tc_mm_ab_reg(acc, dsf, Ks, lane);                  // dQ = dS K
-  __syncthreads();                                   // Ps / dSs complete; every warp is done reading Vs (dP) -> Vs is free
-  tc_acc_to_smem(acc, Vs, r0, lane, scale);          // stage dQ in the V tile
+  tc_acc_to_smem(acc, dQs, r0, lane, scale);
+  __syncthreads();                                   // every warp is done reading Ks (S, dQ) and Vs (dP): both tiles are free
+#pragma unroll
+  for (int j = 0; j < 2 * RT; ++j) {                 // P -> the V tile, dS -> the K tile ([query][key], read transposed below)
+    *reinterpret_cast<uint32_t*>(Ps + rq * TC_LD + j * 8 + cq) = pdf[j >> 1][(j & 1) * 2];
+    *reinterpret_cast<uint32_t*>(Ps + (rq + 8) * TC_LD + j * 8 + cq) = pdf[j >> 1][(j & 1) * 2 + 1];
+    *reinterpret_cast<uint32_t*>(dSs + rq * TC_LD + j * 8 + cq) = dsf[j >> 1][(j & 1) * 2];
+    *reinterpret_cast<uint32_t*>(dSs + (rq + 8) * TC_LD + j * 8 + cq) = dsf[j >> 1][(j & 1) * 2 + 1];
+  }
+  __syncthreads();
   // ---- phase 2: this warp's 16 key rows: dV = Pd^T dO, dK = dS^T Q ----
   float dvacc[8][4], dkacc[8][4];
-  tc_mm_atb(dvacc, Ps, dOs, r0, lane);
-  tc_mm_atb(dkacc, dSs, Qs, r0, lane);
-  __syncthreads();                                   // dQ staged by all warps; Ps / dSs fully consumed
-  tc_store_tile(Vs, dq + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_mm_atb<RT>(dvacc, Ps, dOs, r0, lane);
+  tc_mm_atb<RT>(dkacc, dSs, Qs, r0, lane);
+  __syncthreads();                                   // P, dS fully consumed: stage dV / dK in their tiles
   tc_acc_to_smem(dvacc, Ps, r0, lane, 1.0f);
   tc_acc_to_smem(dkacc, dSs, r0, lane, scale);
   __syncthreads();
-  tc_store_tile(Ps, dv + row0 * ld_dqkv + h * 64, ld_dqkv, L);
-  tc_store_tile(dSs, dk + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_store_tile<R>(dQs, dq + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_store_tile<R>(Ps, dv + row0 * ld_dqkv + h * 64, ld_dqkv, L);
+  tc_store_tile<R>(dSs, dk + row0 * ld_dqkv + h * 64, ld_dqkv, L);
 }
 
 static TcDrop make_tc_drop(float p, uint64_t seed) { return make_drop(p, seed); }
 
 // called from cb_attention_fwd / cb_attention_bwd (attention.cu) when l <= 64
-int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,
-                     int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
-  const int smem = 3 * TC_TILE * 2 + 64 * 4;
+template <int RT>
+static int launch_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,
+                         int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  constexpr int R = RT * 16;
+  const int smem = 3 * R * TC_LD * 2 + R * 4;
   static bool once = false;
   if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attention_tc_fwd smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     once = true;
   }
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   const int hid = heads * 64;
-  launch_k(attn_tc_fwd_kernel, dim3(heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
-                                                                       static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f,
-                                                                       make_tc_drop(dropout_p, seed));
+  launch_k(attn_tc_fwd_kernel<RT>, dim3(heads, nseq), RT * 32, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+           static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f, make_tc_drop(dropout_p, seed));
   return check_launch("cb_attention_fwd(tc)");
+}
+
+static int g_tc_rows48 = 1;      // 0: sequences of up to 48 tokens also run the 64-row kernels (A/B)
+void attention_tc_set_rows48(int on) { g_tc_rows48 = on; }
+
+int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l, int lt,
+                     int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  if (l <= 48 && g_tc_rows48) return launch_tc_fwd<3>(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, stream);
+  return launch_tc_fwd<4>(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, stream);
 }
 
 // called from cb_attention_fwd (attention.cu) for l > 64 when the tensor-core path for long sequences is enabled
@@ -448,25 +481,33 @@ int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_
   return check_launch("cb_attention_fwd(tc, flash)");
 }
 
-int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
-                     const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
-                     cudaStream_t stream) {
-  const int smem = 6 * TC_TILE * 2 + 3 * 64 * 4;
+template <int RT>
+static int launch_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
+                         const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
+                         cudaStream_t stream) {
+  constexpr int R = RT * 16;
+  const int smem = 5 * R * TC_LD * 2 + 3 * R * 4;
   static bool once = false;
   if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attention_tc_bwd smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     once = true;
   }
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* dbase = static_cast<__nv_bfloat16*>(dqkv);
   const int hid = heads * 64;
-  launch_k(attn_tc_bwd_kernel, dim3(heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
-                                                                       static_cast<const __nv_bfloat16*>(ctx),
-                                                                       static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase, dbase + hid,
-                                                                       dbase + 2 * hid, ld_dqkv, l, lt, heads, 0.125f,
-                                                                       make_tc_drop(dropout_p, seed));
+  launch_k(attn_tc_bwd_kernel<RT>, dim3(heads, nseq), RT * 32, smem, stream, base, base + hid, base + 2 * hid, ld_qkv, text_mask,
+           static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), ld_ctx, lse, dbase, dbase + hid,
+           dbase + 2 * hid, ld_dqkv, l, lt, heads, 0.125f, make_tc_drop(dropout_p, seed));
   return check_launch("cb_attention_bwd(tc)");
+}
+
+int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, const void* ctx, const void* dctx, int64_t ld_ctx,
+                     const float* lse, void* dqkv, int64_t ld_dqkv, int nseq, int l, int lt, int heads, float dropout_p, uint64_t seed,
+                     cudaStream_t stream) {
+  if (l <= 48 && g_tc_rows48)
+    return launch_tc_bwd<3>(qkv, ld_qkv, text_mask, ctx, dctx, ld_ctx, lse, dqkv, ld_dqkv, nseq, l, lt, heads, dropout_p, seed, stream);
+  return launch_tc_bwd<4>(qkv, ld_qkv, text_mask, ctx, dctx, ld_ctx, lse, dqkv, ld_dqkv, nseq, l, lt, heads, dropout_p, seed, stream);
 }
 
 }  // namespace cb

@@ -117,11 +117,23 @@ __device__ __forceinline__ void block_accumulate(float (&acc)[CH][8], float* sme
                                                  int warp, int lane) {
   store_row_f32(smem_buf + warp * HID, lane, acc);
   __syncthreads();
-  for (int i = threadIdx.x; i < HID; i += blockDim.x) {
-    float s = 0.f;
+  if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {      // every vector of the flat gradient buffer: 16-byte reductions
+    for (int i = threadIdx.x * 4; i < HID; i += blockDim.x * 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < ROWS_PER_BLOCK; ++w) s += smem_buf[w * HID + i];
-    if (s != 0.f) atomicAdd(gdst + i, s);
+      for (int w = 0; w < ROWS_PER_BLOCK; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(smem_buf + w * HID + i);
+        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+      }
+      if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) red_add_f32x4(gdst + i, s);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROWS_PER_BLOCK; ++w) s += smem_buf[w * HID + i];
+      if (s != 0.f) atomicAdd(gdst + i, s);
+    }
   }
   __syncthreads();
 }
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const __nv_bfloat16* __rest
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
   const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
-  __shared__ float red[ROWS_PER_BLOCK * HID];
+  __shared__ __align__(16) float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[CH][8];
   load_row_f32(gamma, lane, gam);
@@ -242,6 +254,9 @@ __global__ void __launch_bounds__(128) embed_text_fwd_kernel(const int64_t* __re
   }
 }
 
+// grid = (blocks per position, Lt): every block works on ONE text position t, so the position-embedding gradient is summed in
+// registers / shared memory and leaves the block as 768 atomics (it was one atomic per element per row: 64-way contention on the
+// Lt rows of dpos made this kernel 82 us at 64 sequences); the word rows go out as 16-byte reductions.
 __global__ void __launch_bounds__(128) embed_text_bwd_kernel(const __nv_bfloat16* __restrict__ dh,
                                                              const int64_t* __restrict__ ids, const float* word,
                                                              const float* pos, const float* type0, const float* gamma,
@@ -251,33 +266,35 @@ __global__ void __launch_bounds__(128) embed_text_bwd_kernel(const __nv_bfloat16
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
   const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
-  __shared__ float red[ROWS_PER_BLOCK * HID];
+  __shared__ __align__(16) float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float gam[CH][8];
+  const int t = blockIdx.y;
+  float gam[CH][8], p[CH][8], ty[CH][8];
   load_row_f32(gamma, lane, gam);
+  load_row_f32(pos + static_cast<int64_t>(t) * HID, lane, p);
+  load_row_f32(type0, lane, ty);
   float ag[CH][8], ab[CH][8], at[CH][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = at[c][j] = 0.f;
-  const int64_t total = static_cast<int64_t>(nseq) * Lt;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp; r < total;
-       r += static_cast<int64_t>(gridDim.x) * ROWS_PER_BLOCK) {
-    const int b = static_cast<int>(r / Lt), t = static_cast<int>(r - static_cast<int64_t>(b) * Lt);
+    for (int j = 0; j < 8; ++j) {
+      ag[c][j] = ab[c][j] = at[c][j] = 0.f;
+      p[c][j] += ty[c][j];
+    }
+  for (int b = blockIdx.x * ROWS_PER_BLOCK + warp; b < nseq; b += gridDim.x * ROWS_PER_BLOCK) {
+    const int64_t r = static_cast<int64_t>(b) * Lt + t;
     int64_t id = ids[r];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     const int64_t orow = static_cast<int64_t>(b) * L + t;
-    float g[CH][8], e[CH][8], p[CH][8], ty[CH][8];
+    float g[CH][8], e[CH][8];
     load_row_bf16(dh + orow * HID, lane, g);
     apply_dropout_row(g, dc, orow, lane);
     load_row_f32(word + id * HID, lane, e);
-    load_row_f32(pos + static_cast<int64_t>(t) * HID, lane, p);
-    load_row_f32(type0, lane, ty);
 #pragma unroll
     for (int c = 0; c < CH; ++c)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        e[c][j] = e[c][j] + p[c][j] + ty[c][j];
+        e[c][j] += p[c][j];
         ab[c][j] += g[c][j];
       }
     float gsave[CH][8];
@@ -287,19 +304,21 @@ __global__ void __launch_bounds__(128) embed_text_bwd_kernel(const __nv_bfloat16
       for (int j = 0; j < 8; ++j) gsave[c][j] = g[c][j];
     ln_backward_row(g, e, gam, stats[2 * r], stats[2 * r + 1]);
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
+    for (int c = 0; c < CH; ++c) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         ag[c][j] += gsave[c][j] * e[c][j];
         at[c][j] += g[c][j];
-        const int col = c * 256 + lane * 8 + j;
-        atomicAdd(dword + id * HID + col, g[c][j]);
-        atomicAdd(dpos + static_cast<int64_t>(t) * HID + col, g[c][j]);
       }
+      float* wrow = dword + id * HID + c * 256 + lane * 8;
+      red_add_f32x4(wrow, make_float4(g[c][0], g[c][1], g[c][2], g[c][3]));
+      red_add_f32x4(wrow + 4, make_float4(g[c][4], g[c][5], g[c][6], g[c][7]));
+    }
   }
   block_accumulate(ag, red, dgamma, warp, lane);
   block_accumulate(ab, red, dbeta, warp, lane);
   block_accumulate(at, red, dtype0, warp, lane);
+  block_accumulate(at, red, dpos + static_cast<int64_t>(t) * HID, warp, lane);      // d pos[t] = d type[0] restricted to this position
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,7 +387,7 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_kernel(const __nv_bfloat
   pdl_wait();      // PDL: everything above ran while the previous kernel drained; no global access before this
   const DropCfg dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
-  __shared__ float red[ROWS_PER_BLOCK * HID];
+  __shared__ __align__(16) float red[ROWS_PER_BLOCK * HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Lv = gh * gw;
   float gam[CH][8];
@@ -378,10 +397,11 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_kernel(const __nv_bfloat
   for (int c = 0; c < CH; ++c)
 #pragma unroll
     for (int q = 0; q < 8; ++q) ag[c][q] = ab[c][q] = at[c][q] = 0.f;
-  const int64_t total = static_cast<int64_t>(nseq) * Lv;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS_PER_BLOCK + warp; r < total;
-       r += static_cast<int64_t>(gridDim.x) * ROWS_PER_BLOCK) {
-    const int b = static_cast<int>(r / Lv), j = static_cast<int>(r - static_cast<int64_t>(b) * Lv);
+  // grid = (blocks per grid cell, Lv): a block works on ONE visual position j, so d row[j / gw], d col[j % gw] (and d type[0])
+  // leave it as one reduced vector each instead of one atomic per element per row
+  const int j = blockIdx.y;
+  for (int b = blockIdx.x * ROWS_PER_BLOCK + warp; b < nseq; b += gridDim.x * ROWS_PER_BLOCK) {
+    const int64_t r = static_cast<int64_t>(b) * Lv + j;
     const int vid = seq2vid ? seq2vid[b] : b / n_ex;
     const int64_t orow = static_cast<int64_t>(b) * L + Lt + j;
     float g[CH][8], v[CH][8];
@@ -421,14 +441,13 @@ __global__ void __launch_bounds__(128) embed_visual_bwd_kernel(const __nv_bfloat
       for (int q = 0; q < 8; ++q) {
         ag[c][q] += gsave[c][q] * v[c][q];
         at[c][q] += g[c][q];
-        const int col = c * 256 + lane * 8 + q;
-        atomicAdd(drow + static_cast<int64_t>(j / gw) * HID + col, g[c][q]);
-        atomicAdd(dcol + static_cast<int64_t>(j % gw) * HID + col, g[c][q]);
       }
   }
   block_accumulate(ag, red, dgamma, warp, lane);
   block_accumulate(ab, red, dbeta, warp, lane);
   block_accumulate(at, red, dtype0, warp, lane);
+  block_accumulate(at, red, drow + static_cast<int64_t>(j / gw) * HID, warp, lane);
+  block_accumulate(at, red, dcol + static_cast<int64_t>(j % gw) * HID, warp, lane);
 }
 
 // pass 2: dgrid[vid, t, j] = (1/T) * sum_{b' -> vid} dv[b', j]   (backward of repeat_tensor_rows + frame mean)
@@ -676,8 +695,9 @@ int cb_embed_text_bwd(const void* dh, const int64_t* ids, const float* word, con
                       void* stream) {
   CB_REQUIRE(hidden == HID, "cb_embed_text_bwd: hidden size %d unsupported", hidden);
   CB_REQUIRE(dh && ids && dword && dpos && dtype0 && dgamma && dbeta, "cb_embed_text_bwd: bad arguments");
-  const int blocks = min(ceil_div(static_cast<int64_t>(nseq) * lt, ROWS_PER_BLOCK), 148 * 4);
-  launch_k(embed_text_bwd_kernel, blocks, 128, 0, static_cast<cudaStream_t>(stream), 
+  CB_REQUIRE(nseq > 0 && lt > 0 && lt <= 65535, "cb_embed_text_bwd: bad sizes");
+  const int per_pos = max(1, min(ceil_div(nseq, 2 * ROWS_PER_BLOCK), 32));      // two (up to five at 640 sequences) rows per warp
+  launch_k(embed_text_bwd_kernel, dim3(per_pos, lt), 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dh), ids, word, pos, type0, gamma, stats, dword, dpos, dtype0, dgamma, dbeta,
       nseq, lt, l, vocab, make_drop(dropout_p, seed));
   return check_launch("cb_embed_text_bwd");
@@ -705,8 +725,9 @@ int cb_embed_visual_bwd(const void* dh, const void* grid, const int32_t* seq2vid
   CB_REQUIRE(dh && grid && dv_tmp && drow && dcol && dtype0 && dgamma && dbeta, "cb_embed_visual_bwd: bad arguments");
   CB_REQUIRE((seq2vid && vid_start) || n_ex > 0, "cb_embed_visual_bwd: need seq2vid+vid_start or uniform n_ex");
   const int Lv = gh * gw;
-  const int blocks = min(ceil_div(static_cast<int64_t>(nseq) * Lv, ROWS_PER_BLOCK), 148 * 4);
-  launch_k(embed_visual_bwd_kernel, blocks, 128, 0, static_cast<cudaStream_t>(stream), 
+  CB_REQUIRE(Lv <= 65535, "cb_embed_visual_bwd: grid of %d cells unsupported", Lv);
+  const int per_pos = max(1, min(ceil_div(nseq, 2 * ROWS_PER_BLOCK), 32));
+  launch_k(embed_visual_bwd_kernel, dim3(per_pos, Lv), 128, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(grid), seq2vid, n_ex, rowemb, colemb,
       type0, gamma, stats, dv_tmp, drow, dcol, dtype0, dgamma, dbeta, nseq, t, gh, gw, lt, l, make_drop(dropout_p, seed));
   int rc = check_launch("cb_embed_visual_bwd");

@@ -239,6 +239,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 16-byte fp32 reduction into global memory (one L2 atomic unit op instead of four)
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
 // 1 / x as ONE MUFU.RCP (<= 1 ulp). __frcp_rn compiles to MUFU.RCP + a Newton step + a conditional CALL to an IEEE slow path per
 // element, which serialised the GELU epilogue (16 calls per 16 columns, profiles/r02g: 2.5 k cycles per pass).
 __device__ __forceinline__ float fast_rcp(float x) {

@@ -259,12 +259,6 @@ __device__ __forceinline__ void epilogue_math(float (&f)[NC], const GemmEpi& epi
   }
 }
 
-__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w)
-               : "memory");
-}
-
 struct TileInfo {
   int m0, n0, nb0, tap, it_begin, n_iters;
 };
@@ -1000,7 +994,7 @@ static int launch_gemm(const cb_gemm_desc& d, const GemmEpi& epi_in, cudaStream_
   const int smem_bytes = stages * kch * Cfg::STAGE_BYTES + epi_bytes + Cfg::BAR_BYTES + 1024;
   const int units = sm_count() * OCC;
   const int grid = total < units ? total : units;
-  launch_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
+  launch_gemm_k(kern, grid, GEMM_THREADS, smem_bytes, stream, ta, tb, tc, tr, tx, tc2, d.m, d.n, d.k, d.ntaps, d.tap_w, d.tap_sign,
            iters_per_split, tiles_m, tiles_n, total, stages, kch, epi_bytes, epi);
   return check_launch("cb_gemm");
 }
@@ -1336,7 +1330,7 @@ static int launch_wgrad_group(const cb_gemm_desc* descs, int n, int splits, cuda
   }
   const int smem_bytes = sp.stages * sp.kch * Cfg::STAGE_BYTES + sp.epi_bytes + Cfg::BAR_BYTES + 1024;
   const int units = sm_count();
-  launch_k(kern, total < units ? total : units, gemm_threads(8), smem_bytes, stream, g, sp.stages, sp.kch, sp.epi_bytes);
+  launch_gemm_k(kern, total < units ? total : units, gemm_threads(8), smem_bytes, stream, g, sp.stages, sp.kch, sp.epi_bytes);
   return check_launch("cb_gemm_wgrad_group");
 }
 

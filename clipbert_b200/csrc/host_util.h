@@ -36,8 +36,10 @@ inline int check_launch(const char* what) {
 // stream but defeats the two-stream wgrad overlap (+9.6 %), see include/clipbert_b200.h.
 extern std::atomic<int> g_pdl;
 
-template <typename... KArgs, typename... Args>
-inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+// g_pdl: 0 off, 1 every kernel, 2 every kernel EXCEPT the persistent tcgen05 GEMMs (their early-launched CTAs would hold ~200 KB
+// of shared memory per SM while they wait; an LN / attention / column-sum CTA holds a few KB)
+template <bool kGemm, typename... KArgs, typename... Args>
+inline void launch_k_impl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -47,8 +49,17 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  const int mode = g_pdl.load(std::memory_order_relaxed);
+  cfg.numAttrs = (mode == 1 || (mode == 2 && !kGemm)) ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors are picked up by check_launch()
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  launch_k_impl<false>(kern, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_gemm_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  launch_k_impl<true>(kern, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 
 // 2D bf16 row-major tensor [rows, inner] (row pitch ld elements), 128B-swizzled boxes.

@@ -140,7 +140,40 @@ class ClipBert(nn.Module):
         batch["visual_inputs"] = visual_features
         if self.retrieval:
             batch["sample_size"] = len(repeat_counts)  # batch size
-        return self.transformer(_repeat_counts=list(repeat_counts), **batch)
+        zeroed = self._zero_grads_beside_the_transformer_forward(visual_features)
+        out = self.transformer(_repeat_counts=list(repeat_counts), **batch)
+        if zeroed is not None:
+            torch.cuda.current_stream().wait_event(zeroed)      # before the first weight gradient of the backward is written
+        return out
+
+    # ``optimizer.zero_grad()`` of the reference loop (run_video_retrieval.py:486) as part of the step itself: with
+    # ``model.zero_grad_in_forward = True`` the two flat gradient buffers (595 MB) are cleared on a side stream while the
+    # transformer forward runs - its GEMMs are latency-bound and leave HBM idle - instead of by a serial fill before the step.
+    # For loops that call forward exactly once per optimizer step (every reference task at gradient_accumulation_steps 1);
+    # leave it off when accumulating gradients over several forward/backward passes (``no_sync``), and with FusedAdamW's
+    # ``step(zero_grad=True)``, which already clears the buffer in the optimizer's own pass.
+    zero_grad_in_forward = False
+
+    def _zero_grads_beside_the_transformer_forward(self, like):
+        if not (self.zero_grad_in_forward and self.training and torch.is_grad_enabled()):
+            return None
+        grads = self.flat_grads()
+        if not grads:
+            return None
+        if not like.is_cuda:                 # (host-logic tests on emulated ops: no streams)
+            for g in grads:
+                g.zero_()
+            return None
+        side = getattr(self, "_zero_stream", None)
+        if side is None:
+            side = self._zero_stream = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())           # after the previous step's exchange / optimizer read them
+        with torch.cuda.stream(side):
+            for g in grads:
+                g.zero_()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
 
     def encode_clips(self, visual_inputs, num_clips):
         """CNN half only: ``(B, num_clips * num_frm, 3, H, W)`` frames -> the grid features of the ``B * num_clips``

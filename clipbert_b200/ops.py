@@ -101,6 +101,12 @@ def set_attention_flash(on):
     L.lib().cb_debug_attention_flash(int(bool(on)))
 
 
+def set_attention_rows48(on):
+    """Attention of sequences of up to 48 tokens (L = 41: every 224-px configuration): 1 (default) = 48-row tiles, three warps per
+    (sequence, head); 0 = the 64-row / four-warp kernels (A/B)."""
+    L.lib().cb_debug_attention_rows48(int(bool(on)))
+
+
 def set_mn3d(on):
     """MN-major GEMM operands (B of the dgrad mode, both operands of the wgrad mode) through ONE 3-D TMA box per k-chunk
     (default) instead of BN/64 2-D boxes (the single producer lane issues 2 instead of 5-6 TMA instructions per chunk)."""
@@ -140,8 +146,9 @@ def set_sm_limit(n):
 
 
 def set_pdl(enable):
-    """Programmatic dependent launch between the library's kernels (default on). Returns the previous setting."""
-    return int(L.lib().cb_set_pdl(int(bool(enable))))
+    """Programmatic dependent launch between the library's kernels: 0 off (default), 1 every kernel, 2 every kernel except the
+    persistent GEMMs. Returns the previous setting."""
+    return int(L.lib().cb_set_pdl(2 if int(enable) == 2 else int(bool(enable))))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -42,6 +42,7 @@ int64_t cb_launch_count(void);
  * global access, so results are identical to plain stream order. Measured on B200 (profiles/r01b_ab_runs.txt): +1.6 %
  * on a single-stream step, but it cancels the +9.6 % of running the wgrad GEMMs on a second stream, because early-
  * launched dependent CTAs hold their 200 KB of shared memory while they wait and keep the other stream off those SMs.
+ * enable = 2: every kernel EXCEPT the persistent GEMMs (an LN / attention / column-sum CTA waiting early holds a few KB).
  * Returns the previous setting. Replaces nothing in the reference (its ~400 launches per clip are plain stream-
  * ordered cuDNN/cuBLAS/ATen kernels). */
 int cb_set_pdl(int enable);

@@ -369,7 +369,7 @@ def test_embed_text_and_visual(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("dims", [(3, 41, 32), (2, 150, 100), (1, 64, 64), (2, 9, 0)])
+@pytest.mark.parametrize("dims", [(3, 41, 32), (2, 150, 100), (1, 64, 64), (2, 9, 0), (2, 48, 32), (2, 49, 32)])   # 48 | 49: the three- / four-warp kernels
 def test_attention_fwd_bwd(cuda, dims):
     ops = _ops()
     nseq, L, lt = dims

@@ -265,6 +265,48 @@ def test_training_step_clip_loop_vs_batched_pass_on_emulated_ops(weights):
     assert not bad, bad[:8]
 
 
+def test_zero_grad_in_forward_replaces_the_serial_zero_grad_on_emulated_ops(weights):
+    """ClipBert.zero_grad_in_forward: the step clears the flat gradient buffers itself (on the GPU: on a side stream beside the
+    transformer forward). Two steps on the same batch without any model.zero_grad() must leave the gradient of ONE step, in eval
+    / no_grad passes nothing is cleared, and with the switch off the second step accumulates."""
+    import clipbert_b200 as cb
+    from oracle import synth
+    model = _clipbert(weights).train()
+    for m in model.modules():
+        if hasattr(m, "p") and isinstance(getattr(m, "p"), float):
+            m.p = 0.0
+    model.transformer.config.hidden_dropout_prob = 0.0
+    model.transformer.config.attention_probs_dropout_prob = 0.0
+    n_clips, B, size = 2, 2, 64
+    batch = synth.synth_batch(B, n_clips, n_ex=1, size=size, seed=23)
+
+    def step():
+        out = model.forward_clips(dict(visual_inputs=batch["visual_inputs"], text_input_ids=batch["text_input_ids"],
+                                       text_input_mask=batch["text_input_mask"], n_examples_list=[1] * B), n_clips)["logits"]
+        cb.clip_lse_loss(out, batch["labels"]).backward()
+        return [g.detach().clone() for g in model.flat_grads()]
+
+    with emulated_transformer_ops():
+        model.zero_grad()
+        g1 = step()
+        assert len(g1) == 2 and all(float(g.abs().sum()) > 0 for g in g1)
+        model.zero_grad_in_forward = True
+        g2 = step()                                # no zero_grad() in between
+        for a, b in zip(g1, g2):
+            assert relerr(b, a) < 1e-6
+        with torch.no_grad():                      # an evaluation pass between two steps clears nothing
+            model.eval()
+            model.forward_clips(dict(visual_inputs=batch["visual_inputs"], text_input_ids=batch["text_input_ids"],
+                                     text_input_mask=batch["text_input_mask"], n_examples_list=[1] * B), n_clips)
+            model.train()
+        for a, b in zip(g2, model.flat_grads()):
+            assert torch.equal(a, b)
+        model.zero_grad_in_forward = False
+        g3 = step()                                # accumulates on top of g2
+        for a, b in zip(g1, g3):
+            assert relerr(b, 2 * a) < 1e-6
+
+
 def test_bf16_operand_refresh_contract_on_emulated_ops(weights):
     """When the bf16 operand copy is refreshed ("Weight updates"): after a backward (reference AdamW edits
     p.data in place), on version-counted writes, on mark_weights_updated(); an unannounced p.data edit between two

@@ -93,7 +93,7 @@ def main():
     rows = []
     for label, (ms, cnt) in agg.items():
         tf, lost = "", 0.0
-        if label.startswith("gemm"):
+        if label.startswith("gemm mode="):     # ("gemm wgrad group xN": several problems in one launch, no single shape)
             f = dict(kv.split("=") for kv in label.split(" ")[1:])
             m, n, k, taps, mode = int(f["m"]), int(f["n"]), int(f["k"]), int(f["taps"]), int(f["mode"])
             fl = 2.0 * m * n * k * taps
@@ -106,11 +106,11 @@ def main():
             ideal = max(fl / (peaks["tflops"] * 1e12), by / (peaks["hbm"] * 1e9)) * 1e6
             lost = (us - ideal) * cnt / 1e3
             tf = "%7.1f TF/s %7.0f GB/s  ideal %6.1f us  lost %6.3f ms" % (fl / us / 1e6, by / us / 1e3, ideal, lost)
-        rows.append((lost if label.startswith("gemm") else ms, label, ms, cnt, tf))
+        rows.append((lost if label.startswith("gemm mode=") else ms, label, ms, cnt, tf))
     for _, label, ms, cnt, tf in sorted(rows, key=lambda r: -r[2]):
         lines.append("  %-62s %8.3f ms x%-4d %8.1f us %s" % (label, ms, cnt, 1e3 * ms / cnt, tf))
     lines.append("-- gemm shapes by lost time")
-    for lost, label, ms, cnt, tf in sorted((r for r in rows if r[1].startswith("gemm")), key=lambda r: -r[0])[:25]:
+    for lost, label, ms, cnt, tf in sorted((r for r in rows if r[1].startswith("gemm mode=")), key=lambda r: -r[0])[:25]:
         lines.append("  %-62s lost %6.3f ms of %6.3f" % (label, lost, ms))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     open(args.out, "w").write("\n".join(lines) + "\n")
