@@ -407,6 +407,7 @@ int attention_tc_bwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
                      cudaStream_t stream);
 int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
                            int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream);
+void attention_tc_set_flash_pipe(int on);   // 1 (default): cp.async double-buffered key tiles in the long-sequence forward
 void attention_tc_set_rows48(int on);   // 1 (default): sequences of up to 48 tokens on the 48-row / three-warp kernels
 int g_attention_force_general = 0;   // test knob: 1 = always use the general (any L) kernels
 int g_attention_flash = 1;           // 1 = forward of sequences longer than 64 tokens on the tensor-core online-softmax kernel
@@ -421,6 +422,7 @@ extern "C" {
 void cb_debug_attention_general(int on) { cb::g_attention_force_general = on; }
 void cb_debug_attention_flash(int on) { cb::g_attention_flash = on; }
 void cb_debug_attention_rows48(int on) { cb::attention_tc_set_rows48(on); }
+void cb_debug_attention_flash_pipe(int on) { cb::attention_tc_set_flash_pipe(on); }
 
 /* qkv: bf16 [nseq*L, 3*heads*64] (Q | K | V); text_mask: int64 [nseq, Lt]; ctx: bf16 [nseq*L, heads*64];
  * lse: fp32 [nseq, heads, L] (saved for the backward; may be NULL for inference). */

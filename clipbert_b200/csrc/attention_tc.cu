@@ -224,6 +224,26 @@ __global__ void __launch_bounds__(RT * 32) attn_tc_fwd_kernel(const __nv_bfloat1
 // (index = ((b*H + h)*L + query)*L + key) and the saved log-sum-exp follow attn_fwd_kernel (attention.cu), so the general
 // backward kernels consume its output unchanged. At L = 521 the CUDA-core kernel spends 0.83 GFLOP per (sequence, layer)
 // on fp32 FMAs - more than the whole layer's tcgen05 GEMM time; this path puts those products on mma.sync.
+// PIPE = true (default): the K / V / mask tiles are double-buffered and the next key tile travels global -> shared with cp.async
+// (zero-filled beyond L) while the current one is multiplied; PIPE = false: the synchronous loads of the first version (A/B).
+__device__ __forceinline__ void cp_async16_zfill(__nv_bfloat16* dst, const __nv_bfloat16* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// global [rows, 64] bf16 -> smem tile [64][TC_LD] with cp.async, rows >= nrows zero-filled (their source address is clamped to row 0)
+__device__ __forceinline__ void tc_load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nrows) {
+#pragma unroll
+  for (int i = threadIdx.x; i < 64 * 8; i += TC_THREADS) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    const bool ok = r < nrows;
+    cp_async16_zfill(dst + r * TC_LD + c, src + (ok ? static_cast<int64_t>(r) * ld : 0) + c, ok ? 16 : 0);
+  }
+}
+
+template <bool PIPE>
 __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                        const __nv_bfloat16* __restrict__ v, int64_t ld_qkv,
                                                                        const int64_t* __restrict__ text_mask, __nv_bfloat16* __restrict__ ctx,
@@ -233,15 +253,35 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __n
   const TcDrop dc = drop_resolve(dc_in);   // seed + device-side offset (read after the wait)
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t tc_smem[];
+  constexpr int NBUF = PIPE ? 2 : 1;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(tc_smem);
-  __nv_bfloat16* Ks = Qs + TC_TILE;
-  __nv_bfloat16* Vs = Ks + TC_TILE;
-  float* madd = reinterpret_cast<float*>(Vs + TC_TILE);     // [64] additive key mask of the current key tile (-inf beyond L)
+  __nv_bfloat16* Kbuf = Qs + TC_TILE;                        // [NBUF] K tiles
+  __nv_bfloat16* Vbuf = Kbuf + NBUF * TC_TILE;               // [NBUF] V tiles
+  float* mbuf = reinterpret_cast<float*>(Vbuf + NBUF * TC_TILE);   // [NBUF][64] additive key mask of a key tile (-inf beyond L)
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = qb * 64;
   const int64_t row0 = static_cast<int64_t>(b) * L;
+  const int nkb = (L + 63) / 64;
+  auto load_keys = [&](int kb, int buf) {                    // K, V and mask of key tile kb into buffer buf
+    const int k0 = kb * 64;
+    if (PIPE) {
+      tc_load_tile_async(Kbuf + buf * TC_TILE, k + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+      tc_load_tile_async(Vbuf + buf * TC_TILE, v + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+      cp_async_commit();
+    } else {
+      tc_load_tile(Kbuf, k + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+      tc_load_tile(Vbuf, v + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
+    }
+    if (threadIdx.x < 64) {
+      const int j = k0 + threadIdx.x;
+      float m = -INFINITY;
+      if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
+      mbuf[buf * 64 + threadIdx.x] = m;
+    }
+  };
   tc_load_tile(Qs, q + (row0 + q0) * ld_qkv + h * 64, ld_qkv, L - q0);
+  if (PIPE) load_keys(0, 0);
   const int r0 = warp * 16;
   const int rq = r0 + (lane >> 2), cq = 2 * (lane & 3);
   float m0 = -INFINITY, m1 = -INFINITY, sum0 = 0.f, sum1 = 0.f;
@@ -250,19 +290,24 @@ __global__ void __launch_bounds__(TC_THREADS) attn_tc_fwd_flash_kernel(const __n
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
-  const int nkb = (L + 63) / 64;
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * 64;
-    __syncthreads();                     // the previous tile's K / V / mask have been consumed by every warp
-    tc_load_tile(Ks, k + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
-    tc_load_tile(Vs, v + (row0 + k0) * ld_qkv + h * 64, ld_qkv, L - k0);
-    if (threadIdx.x < 64) {
-      const int j = k0 + threadIdx.x;
-      float m = -INFINITY;
-      if (j < L) m = (j < Lt && text_mask[static_cast<int64_t>(b) * Lt + j] == 0) ? -10000.f : 0.f;
-      madd[threadIdx.x] = m;
+    const int buf = PIPE ? (kb & 1) : 0;
+    __syncthreads();                     // the tile multiplied in the previous iteration (buffer buf ^ 1 / the only buffer) is free
+    if (PIPE) {
+      if (kb + 1 < nkb) {
+        load_keys(kb + 1, buf ^ 1);      // travels while this tile is multiplied
+        cp_async_wait<1>();              // every group but the one just committed: this thread's part of tile kb has landed
+      } else {
+        cp_async_wait<0>();
+      }
+    } else {
+      load_keys(kb, 0);
     }
-    __syncthreads();
+    __syncthreads();                     // tile kb (and Q, and its mask) visible to every warp
+    const __nv_bfloat16* Ks = Kbuf + buf * TC_TILE;
+    const __nv_bfloat16* Vs = Vbuf + buf * TC_TILE;
+    const float* madd = mbuf + buf * 64;
     float s[8][4];
     tc_mm_abt(s, Qs, Ks, r0, lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -465,20 +510,31 @@ int attention_tc_fwd(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, 
 }
 
 // called from cb_attention_fwd (attention.cu) for l > 64 when the tensor-core path for long sequences is enabled
-int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
-                           int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
-  const int smem = 3 * TC_TILE * 2 + 64 * 4;
+template <bool PIPE>
+static int launch_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
+                               int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  constexpr int NBUF = PIPE ? 2 : 1;
+  const int smem = (1 + 2 * NBUF) * TC_TILE * 2 + NBUF * 64 * 4;
   static bool once = false;
   if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_flash_kernel<PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attention_tc_fwd_flash smem: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     once = true;
   }
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   const int hid = heads * 64;
-  launch_k(attn_tc_fwd_flash_kernel, dim3(ceil_div(l, 64), heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv,
+  launch_k(attn_tc_fwd_flash_kernel<PIPE>, dim3(ceil_div(l, 64), heads, nseq), TC_THREADS, smem, stream, base, base + hid, base + 2 * hid, ld_qkv,
            text_mask, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse, l, lt, heads, 0.125f, make_tc_drop(dropout_p, seed));
   return check_launch("cb_attention_fwd(tc, flash)");
+}
+
+static int g_tc_flash_pipe = 1;      // 0: synchronous key-tile loads (A/B)
+void attention_tc_set_flash_pipe(int on) { g_tc_flash_pipe = on; }
+
+int attention_tc_fwd_flash(const void* qkv, int64_t ld_qkv, const int64_t* text_mask, void* ctx, int64_t ld_ctx, float* lse, int nseq, int l,
+                           int lt, int heads, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  if (g_tc_flash_pipe) return launch_tc_fwd_flash<true>(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, stream);
+  return launch_tc_fwd_flash<false>(qkv, ld_qkv, text_mask, ctx, ld_ctx, lse, nseq, l, lt, heads, dropout_p, seed, stream);
 }
 
 template <int RT>

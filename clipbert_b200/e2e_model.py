@@ -391,7 +391,7 @@ class ClipBert(nn.Module):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         return bool(int(flag.item()))
 
-    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=32, wire="fp32", tail_ctas=148):
+    def enable_overlapped_allreduce(self, group=None, average=True, cnn_buckets=False, exchange="nccl", max_ctas=None, wire="fp32", tail_ctas=148):
         """Start the all-reduce of the transformer gradient buffer (75 % of the payload) as soon as the last
         outstanding transformer backward of the step has finished, so that it overlaps the remaining CNN backward
         (what Horovod's background fusion thread did for the reference). ``allreduce_grads()`` then only exchanges
@@ -400,14 +400,20 @@ class ClipBert(nn.Module):
         ``cnn_buckets``: also exchange the tail of the CNN buffer (res5 + grid_encoder, 78 % of it) as soon as the
         res5 backward has enqueued its last weight gradient, leaving only res3/res4 (33 MB) for the final exchange.
         The collective is issued from the wgrad side stream, which is the stream those gradients are written on.
-        ``wire="bf16"``: exchange the gradients as bf16 (see ``_bf16_wire_exchange``)."""
+        ``wire="bf16"``: exchange the gradients as bf16 (see ``_bf16_wire_exchange``).
+        ``max_ctas``: CTAs of the NVLS kernel while it overlaps the backward; ``None`` picks by world size - a rank reduces 1/world of
+        the buffer, so two ranks need twice the CTAs of four to finish inside the CNN backward (measured, profiles/r02_multi_gpu.txt:
+        N = 2: 64 CTAs 10.28 ms/step, 32 CTAs 11.1-11.3; N = 8: 32 CTAs 10.36 ms, 64 CTAs 10.50)."""
         assert exchange in ("nccl", "nvls") and wire in ("fp32", "bf16")
+        if not max_ctas:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+            max_ctas = 64 if world <= 2 else 32
         self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True, exchange=exchange,
                         max_ctas=int(max_ctas), tail_ctas=int(tail_ctas if tail_ctas else max_ctas), handles={}, wire=wire, shadows={})
         if exchange == "nvls":
             # ``exchange="nvls"``: this library's own all-reduce through the NVSwitch (csrc/nvls.cu) instead of NCCL. The flat
             # gradient buffers must then live in symmetric memory, so call this BEFORE the first forward (buffers that already
-            # exist are dropped and rebuilt). Experimental until it has run on a multi-GPU box.
+            # exist are dropped and rebuilt).
             import torch.distributed._symmetric_memory as symm
             from .params import FlatGroup
             FlatGroup.grad_factory = staticmethod(lambda n, dev: symm.empty(n, dtype=torch.float32, device=dev).zero_())

@@ -101,6 +101,11 @@ def set_attention_flash(on):
     L.lib().cb_debug_attention_flash(int(bool(on)))
 
 
+def set_attention_flash_pipe(on):
+    """Long-sequence attention forward: 1 (default) = key / value tiles double-buffered through cp.async, 0 = synchronous loads (A/B)."""
+    L.lib().cb_debug_attention_flash_pipe(int(bool(on)))
+
+
 def set_attention_rows48(on):
     """Attention of sequences of up to 48 tokens (L = 41: every 224-px configuration): 1 (default) = 48-row tiles, three warps per
     (sequence, head); 0 = the 64-row / four-warp kernels (A/B)."""

@@ -30,6 +30,16 @@ def main(path):
         for full, short in KEYS:
             if full in idx:
                 vals.append("%s=%s%s" % (short, r[idx[full]], units[idx[full]] if units[idx[full]] not in ("", "%") else ""))
+        stalls = []
+        for h, i in idx.items():           # warp-state sampling: warps stalled per issue-active cycle, by reason
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "selected" not in h:
+                try:
+                    stalls.append((float(r[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        stalls.sort(reverse=True)
+        if stalls:
+            vals.append("stalls: " + ", ".join("%s %.2f" % (n, v) for v, n in stalls[:4]))
         print(name + " | " + " | ".join(vals))
 
 
