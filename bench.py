@@ -276,6 +276,7 @@ def run_b200(args):
     ops.set_mn3d(args.mn3d)
     ops.set_occ2(args.occ2, args.occ2_gflop)
     ops.set_attention_rows48(args.attn_rows48)
+    ops.set_attention_flash_pipe(args.attn_flash_pipe)
     ops.overlap_wgrad = bool(args.overlap_wgrad)
     ops.group_wgrad = int(args.group_wgrad)
     host = make_host_batch(args, rank)
@@ -591,7 +592,7 @@ def run_b200(args):
                                clips_per_step_per_gpu=B * n_clips, seq_len=L, parallelism="dp%d" % world,
                                l2="per-step working set (activations + 149 M-parameter operands, > 2 GB) >> 126 MB L2; no explicit flush",
                                cuda_graph=graph is not None, clip_batching=bool(args.clip_batching), pdl=int(args.pdl), mn3d=bool(args.mn3d), group_wgrad=int(args.group_wgrad), occ2=[args.occ2, args.occ2_gflop], overlap_wgrad=bool(args.overlap_wgrad), stem=args.stem,
-                               fused_loss=bool(args.fused_loss), zero_grad_in_forward=bool(model.zero_grad_in_forward), attn_rows48=bool(args.attn_rows48), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
+                               fused_loss=bool(args.fused_loss), zero_grad_in_forward=bool(model.zero_grad_in_forward), attn_rows48=bool(args.attn_rows48), attn_flash_pipe=bool(args.attn_flash_pipe), cnn_buckets=bool(args.cnn_buckets), exchange=exchange, wire=args.wire, sm_limit=args.sm_limit, nccl_ctas=args.nccl_ctas,
                                weight_recast="in the optimizer step (FusedAdamW attached before the loop emits the bf16 operands)" if recast_attached else "inside every step (no optimizer attached)",
                                gflop_per_clip=round(fl_clip / 1e9, 2)),
                    e2e=dict(value=round(e2e_value, 2), unit="clips/s", ms_per_step=round(ms_e2e / args.steps, 4),
@@ -714,6 +715,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the library's kernels: 0 off, 1 all (hurts the wgrad overlap), 2 all but the GEMMs")
     ap.add_argument("--prefetch", type=int, default=1, help="e2e: upload batch i+1 on a copy stream while batch i computes (0: copy on the compute stream)")
     ap.add_argument("--attn_rows48", type=int, default=1, help="1 (default): attention of sequences up to 48 tokens on the 48-row / three-warp kernels; 0: 64-row kernels")
+    ap.add_argument("--attn_flash_pipe", type=int, default=1, help="1 (default): long-sequence attention forward with cp.async double-buffered key tiles; 0: synchronous tile loads")
     ap.add_argument("--zero_grad_in_forward", type=int, default=1, help="1 (default): the step clears its two flat gradient buffers on a side stream beside "
                     "the transformer forward (ClipBert.zero_grad_in_forward); 0: a serial model.zero_grad() before every step")
     ap.add_argument("--fused_loss", type=int, default=1, help="1 (default): clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss); 0: ~45 ATen launches")
