@@ -721,7 +721,7 @@ def main():
     ap.add_argument("--fused_loss", type=int, default=1, help="1 (default): clip aggregation + LSE loss fwd+bwd as one kernel (cb_clip_lse_loss); 0: ~45 ATen launches")
     ap.add_argument("--recast_in_step", type=int, default=0, help="1: no optimizer attached before the loop -> fp32 -> bf16 weight re-cast inside every step (round-1 behaviour)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvls"], help="N>1 gradient exchange: NCCL all-reduce, this library's NVLS all-reduce (csrc/nvls.cu), or auto = nvls where a multicast mapping exists")
-    ap.add_argument("--nvls_ctas", type=int, default=0, help="CTAs of the NVLS all-reduce kernel while it overlaps the backward; 0 (default) = by world size: 64 at N <= 2, "
+    ap.add_argument("--nvls_ctas", type=int, default=0, help="CTAs of the NVLS all-reduce kernel while it overlaps the backward; 0 (default) = by world size: 64 at N <= 4, "
                     "32 above (N = 8: 32 -> 0.966 of linear, 64 -> 0.953, 96 -> 0.942; N = 2: 64 -> 10.28 ms/step, 32 -> 11.2, 96 -> 10.37)")
     ap.add_argument("--nvls_tail_ctas", type=int, default=148, help="CTAs of the NVLS all-reduce of the last, exposed slices (0 = --nvls_ctas)")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"], help="N>1: gradients travel as fp32 (the flat buffers as they are) or as bf16 (cast, all-reduce, cast back: half the payload, the reference's fp16 wire precision)")

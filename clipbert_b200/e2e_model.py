@@ -403,11 +403,11 @@ class ClipBert(nn.Module):
         ``wire="bf16"``: exchange the gradients as bf16 (see ``_bf16_wire_exchange``).
         ``max_ctas``: CTAs of the NVLS kernel while it overlaps the backward; ``None`` picks by world size - a rank reduces 1/world of
         the buffer, so two ranks need twice the CTAs of four to finish inside the CNN backward (measured, profiles/r02_multi_gpu.txt:
-        N = 2: 64 CTAs 10.28 ms/step, 32 CTAs 11.1-11.3; N = 8: 32 CTAs 10.36 ms, 64 CTAs 10.50)."""
+        N = 2: 64 CTAs 10.28 ms/step, 32 CTAs 11.1-11.3; N = 4: 64 CTAs 10.15, 32 CTAs 10.21; N = 8: 32 CTAs 10.36 ms, 64 CTAs 10.50)."""
         assert exchange in ("nccl", "nvls") and wire in ("fp32", "bf16")
         if not max_ctas:
             world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-            max_ctas = 64 if world <= 2 else 32
+            max_ctas = 64 if world <= 4 else 32
         self._dp = dict(group=group, average=average, works=[], tf_started=False, cnn_lo=None, sync=True, exchange=exchange,
                         max_ctas=int(max_ctas), tail_ctas=int(tail_ctas if tail_ctas else max_ctas), handles={}, wire=wire, shadows={})
         if exchange == "nvls":
