@@ -341,7 +341,10 @@ def _nvls_worker(rank, world, port, q):
     cnn = types.SimpleNamespace(_flat=None, _bucket_hook=None, _pending_backward=0)
     object.__setattr__(m, "transformer", tf)
     object.__setattr__(m, "cnn", cnn)
+    ClipBert.enable_overlapped_allreduce(m, cnn_buckets=True, exchange="nvls")
+    assert m._dp["max_ctas"] == 64 and m._dp["tail_ctas"] == 148      # CTA count by world size: 64 up to four ranks (r02_multi_gpu.txt)
     ClipBert.enable_overlapped_allreduce(m, cnn_buckets=True, exchange="nvls", max_ctas=8)
+    assert m._dp["max_ctas"] == 8
     # the gradient buffers now come from the symmetric allocator
     tf._flat = types.SimpleNamespace(grad=FlatGroup.grad_factory(1000, "cpu"))
     cnn._flat = types.SimpleNamespace(grad=FlatGroup.grad_factory(640, "cpu"))
