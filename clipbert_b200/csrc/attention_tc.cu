@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(RT * 32) attn_tc_fwd_kernel(const __nv_bfloat1
 // (index = ((b*H + h)*L + query)*L + key) and the saved log-sum-exp follow attn_fwd_kernel (attention.cu), so the general
 // backward kernels consume its output unchanged. At L = 521 the CUDA-core kernel spends 0.83 GFLOP per (sequence, layer)
 // on fp32 FMAs - more than the whole layer's tcgen05 GEMM time; this path puts those products on mma.sync.
+// (A variant with 32 query rows per warp - every K / V fragment feeding two row tiles, two warps per CTA - passed the same tests and
+// measured level with this kernel on config 5 (735 against 723-747 clips/s, profiles/r02_ab_runs.txt call 27): 255 registers leave
+// 8 warps per SM, which costs what the saved ldmatrix traffic gains. Not kept.)
 // PIPE = true (default): the K / V / mask tiles are double-buffered and the next key tile travels global -> shared with cp.async
 // (zero-filled beyond L) while the current one is multiplied; PIPE = false: the synchronous loads of the first version (A/B).
 __device__ __forceinline__ void cp_async16_zfill(__nv_bfloat16* dst, const __nv_bfloat16* src, int src_bytes) {

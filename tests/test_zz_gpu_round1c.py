@@ -163,8 +163,9 @@ def test_fused_clip_lse_loss_kernel(cuda):
             assert abs(float(cb.clip_lse_loss(z.to(cuda), y.to(cuda))) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
 
 
+@pytest.mark.parametrize("variant", [1, 0])     # 1: cp.async double-buffered key tiles (default), 0: synchronous loads
 @pytest.mark.parametrize("dims", [(2, 69, 20), (2, 150, 100), (1, 521, 512), (3, 128, 64), (1, 65, 0)])
-def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
+def test_attention_tensor_core_forward_for_long_sequences(cuda, dims, variant):
     """The mma.sync online-softmax forward for L > 64 (attn_tc_fwd_flash_kernel; 448 px frames L = 69, paragraph retrieval
     L = 521) against fp32 torch attention and against the CUDA-core kernel it replaces: context, saved log-sum-exp (the general
     backward consumes it), and the same dropout stream. Default for L > 64 since it passed on a B200 (profiles/r02_ab_runs.txt)."""
@@ -181,6 +182,7 @@ def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
     ref_mask = mask[:, :lt]
     outs = {}
     try:
+        ops.set_attention_flash_pipe(variant)
         for flash in (0, 1):
             ops.set_attention_flash(flash)
             for p, seed in ((0.0, 0), (0.1, 5)):
@@ -190,6 +192,7 @@ def test_attention_tensor_core_forward_for_long_sequences(cuda, dims):
                 outs[(flash, p)] = (ctx, lse)
     finally:
         ops.set_attention_flash(1)
+        ops.set_attention_flash_pipe(1)
     x = qkv.float().view(nseq, L, 3, heads, 64)
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     full = torch.cat([ref_mask, torch.ones(nseq, L - lt, dtype=torch.int64, device=cuda)], 1)
